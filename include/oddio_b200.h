@@ -1,0 +1,164 @@
+/* oddio_b200.h — C ABI of the B200-native oddio hot path.
+ *
+ * This is the drop-in boundary for ONE path of Ralith/oddio 0.7.4: what `oddio::run` drives
+ * through `SpatialScene` / `Mixer` (`Signal::sample` over the active `Set`). The reference has
+ * no FFI of its own (it is pure Rust); the entry points below are what a Rust shim keeping the
+ * reference's `Signal`/`Seek`/`Frame` traits and `SpatialScene::new`/`play`/`set_motion`/`run`
+ * API binds with `extern "C"` (stub in INTEGRATION.md). Every function cites the reference item
+ * (file:line under the reference's src/) it stands in for.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; opaque handles; no C++/torch types.
+ *  - every function returns an `int` status: ODB_OK (0) or a negative ODB_E_* code;
+ *    `odb_last_error()` returns a thread-local message for the last failure. The reference has
+ *    no error returns on this path (misuse panics); codes exist because FFI cannot panic.
+ *  - threading mirrors the reference: one "audio" thread calls *_sample / *_run on a scene or
+ *    mixer; one control thread calls play / set_* / stop. Control calls take effect at the next
+ *    *_sample boundary, latest value wins (swap.rs:36-68, set.rs:141-178).
+ *  - `out` buffers of *_sample / *_run are HOST memory, interleaved frames, caller-owned.
+ *    *_sample_device leaves the result in device memory on the given CUDA stream instead.
+ *  - there is NO CPU fallback: without a CUDA device every call fails with ODB_E_CUDA.
+ */
+#ifndef ODDIO_B200_H
+#define ODDIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODB_OK 0
+#define ODB_E_INVALID (-1)     /* bad argument / unknown handle */
+#define ODB_E_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define ODB_E_UNSUPPORTED (-3) /* signal chain outside the closed set the device path accepts */
+#define ODB_E_NOMEM (-4)
+
+typedef struct odb_ctx odb_ctx;     /* one CUDA device + stream + PCM arena; one per process/GPU */
+typedef struct odb_scene odb_scene; /* SpatialSceneControl + SpatialScene pair (spatial.rs:160-189) */
+typedef struct odb_mixer odb_mixer; /* MixerControl<T> + Mixer<T> pair (mixer.rs:61-87) */
+typedef uint64_t odb_frames;        /* Arc<Frames<T>> (frames.rs:16-22); 0 is never valid */
+typedef uint64_t odb_source;        /* a playing signal: Spatial / Mixed + its inner controls */
+
+const char* odb_last_error(void);
+/* ABI version of this header; bumped on any incompatible change. */
+uint32_t odb_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int odb_ctx_create(int cuda_device, odb_ctx** out);
+int odb_ctx_destroy(odb_ctx* ctx);
+/* Blocks until all work queued on the context's stream has finished. */
+int odb_ctx_synchronize(odb_ctx* ctx);
+/* The context's CUDA stream (a cudaStream_t) so callers can order their own work after it. */
+int odb_ctx_stream(odb_ctx* ctx, void** out_stream);
+
+/* ---- Frames (frames.rs:19-77) ------------------------------------------------------------------ */
+/* Frames::from_slice (frames.rs:26-47): copies `n_frames` interleaved frames of `channels`
+ * (1 = Sample, 2 = [Sample; 2]) from HOST memory into HBM. */
+int odb_frames_from_slice(odb_ctx* ctx, uint32_t rate, int channels, const float* samples, uint64_t n_frames,
+                          odb_frames* out);
+/* Same, but `dev_samples` already is DEVICE memory on ctx's device (copied device-to-device into
+ * the arena, so the caller may free it afterwards). For PCM decoded or synthesised on the GPU. */
+int odb_frames_from_device(odb_ctx* ctx, uint32_t rate, int channels, const void* dev_samples, uint64_t n_frames,
+                           odb_frames* out);
+/* Drops one reference (Arc drop). Storage is freed once no playing source uses it. */
+int odb_frames_release(odb_ctx* ctx, odb_frames frames);
+
+/* ---- the closed set of signal chains the device path accepts ------------------ */
+/* A chain is  [Gain]( [FixedGain]( [Speed]( FramesSignal ) ) )  with each bracket optional:
+ *   FramesSignal::new(frames, start_seconds)            frames.rs:156-169
+ *   Speed::new(..)   + SpeedControl::set_speed          speed.rs:16-23, :52-54
+ *   FixedGain::new(.., db)                              gain.rs:18-23
+ *   Gain::new(..)    + Gain::set_amplitude_ratio        gain.rs:66-93
+ * SpatialSceneControl::play requires `Seek`, which Speed and Gain do not implement
+ * (speed.rs:26-40, gain.rs:95-127), so odb_scene_play rejects those flags with ODB_E_UNSUPPORTED;
+ * play_buffered and the mixer accept all of them. */
+#define ODB_CHAIN_SPEED 0x1u
+#define ODB_CHAIN_FIXED_GAIN 0x2u
+#define ODB_CHAIN_GAIN 0x4u
+typedef struct odb_chain {
+    odb_frames frames;     /* the Arc<Frames<T>> played */
+    double start_seconds;  /* FramesSignal::new start_seconds, may be negative */
+    uint32_t flags;        /* ODB_CHAIN_* */
+    float speed;           /* initial SpeedControl value (Speed::new starts at 1.0) */
+    float fixed_gain_db;   /* FixedGain::new db */
+    float gain_ratio;      /* Gain::set_amplitude_ratio initial factor (Gain::new starts at 1.0) */
+} odb_chain;
+
+/* Post-mix wrappers around the whole aggregator: Tanh<T> (tanh.rs:22-29), Reinhard<T> (reinhard.rs:28-35) */
+#define ODB_EPILOGUE_NONE 0
+#define ODB_EPILOGUE_TANH 1
+#define ODB_EPILOGUE_REINHARD 2
+
+/* ---- SpatialScene (spatial.rs) -------------------------------------------------------------------- */
+/* SpatialScene::new (spatial.rs:170-188) */
+int odb_scene_create(odb_ctx* ctx, odb_scene** out);
+int odb_scene_destroy(odb_scene* scene);
+/* Wrap the scene in Tanh / Reinhard: `Tanh::new(scene)`. */
+int odb_scene_set_epilogue(odb_scene* scene, int epilogue);
+/* SpatialSceneControl::play (spatial.rs:289-302) with SpatialOptions {position, velocity, radius} (:354-371) */
+int odb_scene_play(odb_scene* scene, const odb_chain* chain, const float position[3], const float velocity[3],
+                   float radius, odb_source* out);
+/* SpatialSceneControl::play_buffered (spatial.rs:314-340) */
+int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain, const float position[3],
+                            const float velocity[3], float radius, float max_distance, uint32_t rate,
+                            float buffer_duration, odb_source* out);
+/* SpatialSceneControl::set_listener_rotation (spatial.rs:345-349); q = mint::Quaternion as {x, y, z, s} */
+int odb_scene_set_listener_rotation(odb_scene* scene, const float q_xyzs[4]);
+/* Spatial::set_motion (spatial.rs:137-149) */
+int odb_spatial_set_motion(odb_scene* scene, odb_source src, const float position[3], const float velocity[3],
+                           int discontinuity);
+/* Spatial::is_finished (spatial.rs:154-156) */
+int odb_spatial_is_finished(odb_scene* scene, odb_source src, int* out);
+/* <SpatialScene as Signal>::sample (spatial.rs:376-471): n_frames stereo frames, interleaved L,R */
+int odb_scene_sample(odb_scene* scene, float interval, float* out, uint32_t n_frames);
+/* oddio::run(&mut scene, sample_rate, out) (lib.rs:90-93): interval = 1.0 / sample_rate as f32 */
+int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames);
+/* As odb_scene_sample, but the mixed tile is left in DEVICE memory `dev_out` (2*n_frames f32),
+ * ordered on ctx's stream, with no host synchronisation; for multi-GPU reduction of per-shard
+ * tiles and for device-resident benchmarking. */
+int odb_scene_sample_device(odb_scene* scene, float interval, void* dev_out, uint32_t n_frames);
+/* Number of sources currently in the seek set / buffered set (set.rs:191-204 Deref len). */
+int odb_scene_len(odb_scene* scene, int buffered, uint64_t* out);
+
+/* ---- Mixer (mixer.rs) ----------------------------------------------------------------------------- */
+/* Mixer::<T>::new (mixer.rs:70-81); channels 1 => Mixer<Sample>, 2 => Mixer<[Sample; 2]> */
+int odb_mixer_create(odb_ctx* ctx, int channels, odb_mixer** out);
+int odb_mixer_destroy(odb_mixer* mixer);
+int odb_mixer_set_epilogue(odb_mixer* mixer, int epilogue);
+/* MixerControl::play (mixer.rs:18-26); the chain's Frames must have the mixer's channel count */
+int odb_mixer_play(odb_mixer* mixer, const odb_chain* chain, odb_source* out);
+/* Mixed::stop / Mixed::is_stopped (mixer.rs:34-43) */
+int odb_mixed_stop(odb_mixer* mixer, odb_source src);
+int odb_mixed_is_stopped(odb_mixer* mixer, odb_source src, int* out);
+/* <Mixer<T> as Signal>::sample (mixer.rs:92-119) and oddio::run over it */
+int odb_mixer_sample(odb_mixer* mixer, float interval, float* out, uint32_t n_frames);
+int odb_mixer_run(odb_mixer* mixer, uint32_t sample_rate, float* out, uint32_t n_frames);
+int odb_mixer_sample_device(odb_mixer* mixer, float interval, void* dev_out, uint32_t n_frames);
+int odb_mixer_len(odb_mixer* mixer, uint64_t* out);
+
+/* ---- per-source controls; `owner` is the odb_scene* or odb_mixer* that returned `src` ------------------ */
+/* SpeedControl::set_speed / speed (speed.rs:47-54) */
+int odb_source_set_speed(void* owner, odb_source src, float factor);
+/* GainControl::set_amplitude_ratio / set_gain (gain.rs:143-159) */
+int odb_source_set_amplitude_ratio(void* owner, odb_source src, float factor);
+int odb_source_set_gain_db(void* owner, odb_source src, float db);
+/* FramesSignalControl::playback_position / is_finished (frames.rs:238-247) */
+int odb_source_playback_position(void* owner, odb_source src, double* out_seconds);
+int odb_source_frames_is_finished(void* owner, odb_source src, int* out);
+/* Parity aid: the FramesSignal's f64 time cursor `t` (frames.rs:145) and, for buffered sources,
+ * the Ring's f32 write cursor (ring.rs:6). Bit-exact against the reference by contract. */
+int odb_source_cursor(void* owner, odb_source src, double* out_t, float* out_ring_write);
+
+/* ---- introspection for tests / profiling ------------------------------------------------------------------ */
+/* Number of kernels launched by the last *_sample* call on this owner. */
+int odb_last_launch_count(void* owner, uint32_t* out);
+/* Selects the mix-kernel variant: 0 = default (fast path with general fallback per source),
+ * 1 = force the general kernel for every source (slow, used to cross-check the fast path). */
+int odb_set_kernel_variant(void* owner, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODDIO_B200_H */

@@ -1,0 +1,306 @@
+// Context, PCM arena, Frames handles and the SourceSet control plane (host side of the C ABI).
+#include "odb_host.h"
+
+#include <algorithm>
+
+static thread_local std::string g_err;
+std::string& odb_err() { return g_err; }
+int odb_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+extern "C" const char* odb_last_error(void) { return g_err.c_str(); }
+extern "C" uint32_t odb_abi_version(void) { return 1; }
+
+// ---- context -----------------------------------------------------------------------------------
+extern "C" int odb_ctx_create(int cuda_device, odb_ctx** out) {
+    if (!out) return odb_fail(ODB_E_INVALID, "odb_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return odb_fail(ODB_E_CUDA, "no CUDA device available (%s); oddio_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (cuda_device < 0 || cuda_device >= count) return odb_fail(ODB_E_INVALID, "cuda_device %d out of range", cuda_device);
+    ODB_CUDA(cudaSetDevice(cuda_device));
+    odb_ctx* c = new odb_ctx();
+    c->device = cuda_device;
+    cudaDeviceProp prop;
+    ODB_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
+    c->sm_count = prop.multiProcessorCount;
+    ODB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return ODB_OK;
+}
+extern "C" int odb_ctx_destroy(odb_ctx* ctx) {
+    if (!ctx) return ODB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->blocks)
+        if (b.base) cudaFree(b.base);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ODB_OK;
+}
+extern "C" int odb_ctx_synchronize(odb_ctx* ctx) {
+    if (!ctx) return odb_fail(ODB_E_INVALID, "ctx is NULL");
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ODB_OK;
+}
+extern "C" int odb_ctx_stream(odb_ctx* ctx, void** out_stream) {
+    if (!ctx || !out_stream) return odb_fail(ODB_E_INVALID, "NULL argument");
+    *out_stream = (void*)ctx->stream;
+    return ODB_OK;
+}
+
+// ---- arena: large blocks, bump allocation, freed when every Frames in a block is gone -----------
+int odb_ctx::arena_alloc(size_t bytes, float** out, int* block) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    int bi = -1;
+    if (!blocks.empty()) {
+        ArenaBlock& b = blocks.back();
+        if (b.base && b.size - b.used >= bytes) bi = (int)blocks.size() - 1;
+    }
+    if (bi < 0) {
+        ArenaBlock nb;
+        nb.size = std::max(bytes, (size_t)256 << 20);
+        ODB_CUDA(cudaMalloc((void**)&nb.base, nb.size));
+        blocks.push_back(nb);
+        bi = (int)blocks.size() - 1;
+    }
+    ArenaBlock& b = blocks[bi];
+    *out = (float*)(b.base + b.used);
+    b.used += bytes;
+    b.live++;
+    *block = bi;
+    return ODB_OK;
+}
+void odb_ctx::arena_unref(int block) {
+    if (block < 0 || block >= (int)blocks.size()) return;
+    ArenaBlock& b = blocks[block];
+    if (--b.live == 0 && block != (int)blocks.size() - 1) {
+        cudaStreamSynchronize(stream);
+        cudaFree(b.base);
+        b.base = nullptr;
+    } else if (b.live == 0) {
+        b.used = 0;  // the open block can be reused from the start
+    }
+}
+int odb_ctx::frames_ref(odb_frames id, FramesRec* out) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = frames.find(id);
+    if (it == frames.end()) return odb_fail(ODB_E_INVALID, "unknown frames handle %llu", (unsigned long long)id);
+    it->second.refs++;
+    *out = it->second;
+    return ODB_OK;
+}
+void odb_ctx::frames_unref(odb_frames id) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = frames.find(id);
+    if (it == frames.end()) return;
+    if (--it->second.refs == 0) {
+        arena_unref(it->second.block);
+        frames.erase(it);
+    }
+}
+
+static int frames_new(odb_ctx* ctx, uint32_t rate, int channels, const void* samples, uint64_t n_frames, bool from_device,
+                      odb_frames* out) {
+    if (!ctx || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    if (channels != 1 && channels != 2) return odb_fail(ODB_E_UNSUPPORTED, "channels must be 1 or 2, got %d", channels);
+    if (n_frames == 0 || n_frames > (1ull << 29)) return odb_fail(ODB_E_INVALID, "n_frames %llu out of range", (unsigned long long)n_frames);
+    if (rate == 0) return odb_fail(ODB_E_INVALID, "rate must be nonzero");
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    FramesRec rec;
+    size_t elems = (size_t)n_frames * channels;
+    float* base = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ODB_TRY(ctx->arena_alloc((elems + 2 * ODB_PCM_PAD) * sizeof(float), &base, &rec.block));
+    }
+    ODB_CUDA(cudaMemsetAsync(base, 0, ODB_PCM_PAD * sizeof(float), ctx->stream));
+    ODB_CUDA(cudaMemsetAsync(base + ODB_PCM_PAD + elems, 0, ODB_PCM_PAD * sizeof(float), ctx->stream));
+    if (samples)
+        ODB_CUDA(cudaMemcpyAsync(base + ODB_PCM_PAD, samples, elems * sizeof(float),
+                                 from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    rec.dev = base + ODB_PCM_PAD;
+    rec.n_frames = n_frames;
+    rec.channels = channels;
+    rec.rate = rate;
+    rec.refs = 1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    odb_frames id = ctx->next_frames_id++;
+    ctx->frames[id] = rec;
+    *out = id;
+    return ODB_OK;
+}
+extern "C" int odb_frames_from_slice(odb_ctx* ctx, uint32_t rate, int channels, const float* samples, uint64_t n_frames,
+                                     odb_frames* out) {
+    if (!samples) return odb_fail(ODB_E_INVALID, "samples is NULL");
+    return frames_new(ctx, rate, channels, samples, n_frames, false, out);
+}
+extern "C" int odb_frames_from_device(odb_ctx* ctx, uint32_t rate, int channels, const void* dev_samples, uint64_t n_frames,
+                                      odb_frames* out) {
+    if (!dev_samples) return odb_fail(ODB_E_INVALID, "dev_samples is NULL");
+    return frames_new(ctx, rate, channels, dev_samples, n_frames, true, out);
+}
+extern "C" int odb_frames_release(odb_ctx* ctx, odb_frames frames) {
+    if (!ctx) return odb_fail(ODB_E_INVALID, "ctx is NULL");
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->frames.find(frames) == ctx->frames.end())
+            return odb_fail(ODB_E_INVALID, "unknown frames handle %llu", (unsigned long long)frames);
+    }
+    ctx->frames_unref(frames);
+    return ODB_OK;
+}
+
+// ---- SourceSet -----------------------------------------------------------------------------------
+uint32_t SourceSet::alloc_slot() {
+    uint32_t s;
+    if (!free_slots.empty()) {
+        s = free_slots.back();
+        free_slots.pop_back();
+    } else {
+        s = (uint32_t)slots.size();
+        slots.emplace_back();
+    }
+    slots[s].in_use = true;
+    slots[s].stopped = false;
+    return s;
+}
+odb_source SourceSet::handle_of(uint32_t slot, uint32_t tag) const {
+    return ((uint64_t)slots[slot].gen << 40) | ((uint64_t)(tag & 0xFF) << 32) | (uint64_t)slot;
+}
+int SourceSet::lookup(odb_source h, uint32_t tag, uint32_t* slot, bool* stale) const {
+    uint32_t s = (uint32_t)(h & 0xFFFFFFFFu), t = (uint32_t)((h >> 32) & 0xFF), g = (uint32_t)(h >> 40);
+    if (t != tag || s >= slots.size() || g == 0 || g > slots[s].gen)
+        return odb_fail(ODB_E_INVALID, "foreign source handle %llx", (unsigned long long)h);
+    *slot = s;
+    *stale = (g != slots[s].gen) || !slots[s].in_use;
+    return ODB_OK;
+}
+void SourceSet::queue_motion(uint32_t slot, const float* pos, const float* vel, int disc) {
+    OdbMotionMsg m;
+    m.slot = slot;
+    for (int k = 0; k < 3; k++) { m.pos[k] = pos[k]; m.vel[k] = vel[k]; }
+    m.discontinuity = disc ? 1u : 0u;
+    SlotHost& sh = slots[slot];
+    if (sh.motion_idx >= 0) motions[sh.motion_idx] = m;  // latest value wins (swap.rs:36-47)
+    else { sh.motion_idx = (int)motions.size(); motions.push_back(m); }
+}
+void SourceSet::queue_param(uint32_t slot, uint32_t what, float value) {
+    OdbParamMsg m = {slot, what, value, 0u};
+    SlotHost& sh = slots[slot];
+    int* idx = what == ODB_PARAM_SPEED ? &sh.speed_idx : (what == ODB_PARAM_GAIN ? &sh.gain_idx : nullptr);
+    if (idx && *idx >= 0) { params[*idx] = m; return; }
+    if (idx) *idx = (int)params.size();
+    params.push_back(m);
+}
+
+int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
+    // inserts: set.rs:159-165 — appended to the table in send order
+    size_t ni = ins_slot.size();
+    if (ni) {
+        ODB_TRY(d_src.ensure(slots.size(), st, true));
+        ODB_TRY(h_stage_src.ensure(ni));
+        ODB_TRY(h_stage_slot.ensure(ni));
+        ODB_TRY(d_stage_src.ensure(ni, st, false));
+        ODB_TRY(d_stage_slot.ensure(ni, st, false));
+        memcpy(h_stage_src.p, ins_src.data(), ni * sizeof(OdbSource));
+        memcpy(h_stage_slot.p, ins_slot.data(), ni * sizeof(uint32_t));
+        ODB_CUDA(cudaMemcpyAsync(d_stage_src.p, h_stage_src.p, ni * sizeof(OdbSource), cudaMemcpyHostToDevice, st));
+        ODB_CUDA(cudaMemcpyAsync(d_stage_slot.p, h_stage_slot.p, ni * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        odb_launch_scatter_sources(d_src.p, d_stage_src.p, d_stage_slot.p, (int)ni, st);
+        (*launches)++;
+        for (uint32_t s : ins_slot) order.push_back(s);
+        order_dirty = true;
+        ins_src.clear();
+        ins_slot.clear();
+    }
+    size_t nm = motions.size();
+    if (nm) {
+        ODB_TRY(h_motions.ensure(nm));
+        ODB_TRY(d_motions.ensure(nm, st, false));
+        memcpy(h_motions.p, motions.data(), nm * sizeof(OdbMotionMsg));
+        ODB_CUDA(cudaMemcpyAsync(d_motions.p, h_motions.p, nm * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+        odb_launch_scatter_motion(d_src.p, d_motions.p, (int)nm, st);
+        (*launches)++;
+        for (auto& m : motions) slots[m.slot].motion_idx = -1;
+        motions.clear();
+    }
+    size_t np = params.size();
+    if (np) {
+        ODB_TRY(h_params.ensure(np));
+        ODB_TRY(d_params.ensure(np, st, false));
+        memcpy(h_params.p, params.data(), np * sizeof(OdbParamMsg));
+        ODB_CUDA(cudaMemcpyAsync(d_params.p, h_params.p, np * sizeof(OdbParamMsg), cudaMemcpyHostToDevice, st));
+        odb_launch_scatter_params(d_src.p, d_params.p, (int)np, st);
+        (*launches)++;
+        for (auto& m : params) { slots[m.slot].speed_idx = -1; slots[m.slot].gain_idx = -1; }
+        params.clear();
+    }
+    if (order_dirty) {
+        size_t n = order.size();
+        if (n) {
+            ODB_TRY(h_order.ensure(n));
+            ODB_TRY(d_order.ensure(n, st, false));
+            // the previous H2D copy out of h_order has completed: every sample() either
+            // synchronises the stream or is followed by one before the next apply()
+            memcpy(h_order.p, order.data(), n * sizeof(uint32_t));
+            ODB_CUDA(cudaMemcpyAsync(d_order.p, h_order.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        }
+        order_dirty = false;
+    }
+    ODB_TRY(d_removed.ensure(order.size() + 1, st, false));
+    ODB_TRY(h_removed.ensure(std::max<size_t>(order.size() + 1, ODB_REMOVED_CAP)));
+    return ODB_OK;
+}
+
+void SourceSet::process_removed(odb_ctx* ctx) {
+    if (!removed_pending) return;
+    removed_pending = false;
+    uint32_t count = h_removed.p[0];
+    if (count == 0) return;
+    if (count > (uint32_t)removed_order_len) count = (uint32_t)removed_order_len;
+    if (count + 1 > ODB_REMOVED_CAP) {  // rare: more removals than the eagerly copied header holds
+        cudaMemcpyAsync(h_removed.p, d_removed.p, ((size_t)count + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    // The reference walks i from len-1 down to 0 and swap_removes as it goes (spatial.rs:204,259;
+    // mixer.rs:100,104; set.rs:183-188): replaying the indices in descending order gives the same Vec.
+    std::vector<uint32_t> idx(h_removed.p + 1, h_removed.p + 1 + count);
+    std::sort(idx.begin(), idx.end(), [](uint32_t a, uint32_t b) { return a > b; });
+    for (uint32_t i : idx) {
+        if (i >= order.size()) continue;
+        uint32_t slot = order[i];
+        order[i] = order.back();
+        order.pop_back();
+        SlotHost& sh = slots[slot];
+        sh.stopped = true;
+        sh.in_use = false;
+        sh.gen++;  // older handles now read as "finished" (see lookup)
+        sh.motion_idx = sh.speed_idx = sh.gain_idx = -1;
+        if (sh.frames) ctx->frames_unref(sh.frames);
+        sh.frames = 0;
+        free_slots.push_back(slot);
+    }
+    order_dirty = true;
+}
+
+void SourceSet::release_all(odb_ctx* ctx) {
+    for (auto& sh : slots)
+        if (sh.in_use && sh.frames) ctx->frames_unref(sh.frames);
+    slots.clear();
+    d_src.release(); d_order.release(); d_stage_src.release(); d_stage_slot.release();
+    d_motions.release(); d_params.release(); d_removed.release();
+    h_stage_src.release(); h_stage_slot.release(); h_motions.release(); h_params.release();
+    h_order.release(); h_removed.release();
+}

@@ -1,0 +1,164 @@
+// Host-side runtime shared by the scene and mixer implementations of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/oddio_b200.h"
+#include "odb_kernels.h"
+
+std::string& odb_err();
+int odb_fail(int code, const char* fmt, ...);
+
+#define ODB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return odb_fail(ODB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define ODB_TRY(call)            \
+    do {                         \
+        int r__ = (call);        \
+        if (r__ != ODB_OK) return r__; \
+    } while (0)
+
+// Growable device array; growth happens on the control/apply path only, never mid-kernel.
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n, cudaStream_t st, bool keep) {
+        if (n <= cap) return ODB_OK;
+        size_t ncap = cap ? cap : 256;
+        while (ncap < n) ncap *= 2;
+        T* np = nullptr;
+        ODB_CUDA(cudaMalloc((void**)&np, ncap * sizeof(T)));
+        if (keep && p && cap) ODB_CUDA(cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (p) {
+            ODB_CUDA(cudaStreamSynchronize(st));
+            ODB_CUDA(cudaFree(p));
+        }
+        p = np;
+        cap = ncap;
+        return ODB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return ODB_OK;
+        size_t ncap = cap ? cap : 256;
+        while (ncap < n) ncap *= 2;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        ODB_CUDA(cudaMallocHost((void**)&p, ncap * sizeof(T)));
+        cap = ncap;
+        return ODB_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct FramesRec {  // Arc<Frames<T>> (frames.rs:16-22)
+    float* dev = nullptr;  // first sample; ODB_PCM_PAD zero floats on both sides
+    uint64_t n_frames = 0;
+    int channels = 1;
+    uint32_t rate = 0;
+    int refs = 0;
+    int block = -1;
+};
+struct ArenaBlock {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    int live = 0;
+};
+
+struct odb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::unordered_map<uint64_t, FramesRec> frames;
+    uint64_t next_frames_id = 1;
+    std::vector<ArenaBlock> blocks;
+    int arena_alloc(size_t bytes, float** out, int* block);
+    void arena_unref(int block);
+    int frames_ref(odb_frames id, FramesRec* out);
+    void frames_unref(odb_frames id);
+};
+
+#define ODB_KIND_SCENE 0x5343454Eu
+#define ODB_KIND_MIXER 0x4D495852u
+
+struct SlotHost {
+    odb_frames frames = 0;
+    uint32_t gen = 1;
+    bool in_use = false;
+    bool stopped = false;   // Spatial::is_finished / Mixed::is_stopped as seen by the control side
+    uint32_t chain_flags = 0;
+    uint64_t n_frames = 0;  // FramesSignalControl::samples
+    double rate = 0.0;
+    // latest-wins de-duplication of queued control messages (swap.rs semantics): index into the
+    // pending vectors, -1 if nothing is queued for this slot since the last apply()
+    int motion_idx = -1, speed_idx = -1, gain_idx = -1;
+};
+
+// A set of playing sources living in HBM plus the control-plane queues feeding it; the common
+// part of odb_scene (seek set, buffered set) and odb_mixer.
+struct SourceSet {
+    std::vector<SlotHost> slots;
+    std::vector<uint32_t> free_slots;
+    std::vector<uint32_t> order;        // the reference's Vec order (set.rs:206): slot ids
+    bool order_dirty = false;
+    // queued by the control side, applied at the next sample()
+    std::vector<OdbSource> ins_src;
+    std::vector<uint32_t> ins_slot;
+    std::vector<OdbMotionMsg> motions;
+    std::vector<OdbParamMsg> params;
+    // device
+    DevBuf<OdbSource> d_src;
+    DevBuf<uint32_t> d_order;
+    DevBuf<OdbSource> d_stage_src;
+    DevBuf<uint32_t> d_stage_slot;
+    DevBuf<OdbMotionMsg> d_motions;
+    DevBuf<OdbParamMsg> d_params;
+    DevBuf<uint32_t> d_removed;
+    PinBuf<OdbSource> h_stage_src;
+    PinBuf<uint32_t> h_stage_slot;
+    PinBuf<OdbMotionMsg> h_motions;
+    PinBuf<OdbParamMsg> h_params;
+    PinBuf<uint32_t> h_order;
+    PinBuf<uint32_t> h_removed;
+    bool removed_pending = false;       // a removed list was copied back but not yet processed
+    int removed_order_len = 0;
+
+    uint32_t alloc_slot();
+    odb_source handle_of(uint32_t slot, uint32_t tag) const;
+    // ODB_OK and *slot if `h` names a live source; *stale = true (and ODB_OK) if it names a source that
+    // has since been removed (the reference's handles outlive their signal); error otherwise.
+    int lookup(odb_source h, uint32_t tag, uint32_t* slot, bool* stale) const;
+    void queue_motion(uint32_t slot, const float* pos, const float* vel, int disc);
+    void queue_param(uint32_t slot, uint32_t what, float value);
+    // audio side: push queued control messages to the device; returns kernels launched
+    int apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches);
+    // audio side: after the stream has been synchronised, swap_remove what the kernels reported
+    void process_removed(odb_ctx* ctx);
+    void release_all(odb_ctx* ctx);
+};
+#define ODB_REMOVED_CAP 4096

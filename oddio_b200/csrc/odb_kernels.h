@@ -1,0 +1,36 @@
+// Host-callable launchers of the oddio_b200 kernels (implemented in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "odb_types.h"
+
+// Largest per-frame source advance (samples per output frame) the fast mix kernel stages in
+// shared memory; sources outside (0, ODB_FAST_DS_MAX] take the general kernel.
+#define ODB_FAST_DS_MAX 1.40f
+
+struct OdbMotionMsg {  // Spatial::set_motion payload (spatial.rs:137-149)
+    uint32_t slot;
+    float pos[3];
+    float vel[3];
+    uint32_t discontinuity;
+};
+#define ODB_PARAM_SPEED 1u
+#define ODB_PARAM_GAIN 2u
+#define ODB_PARAM_STOP 3u
+struct OdbParamMsg {  // SpeedControl::set_speed / GainControl::set_amplitude_ratio / Mixed::stop
+    uint32_t slot;
+    uint32_t what;
+    float value;
+    uint32_t pad;
+};
+
+void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const uint32_t* slots, int n, cudaStream_t st);
+void odb_launch_scatter_motion(OdbSource* src, const OdbMotionMsg* msgs, int n, cudaStream_t st);
+void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, cudaStream_t st);
+void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
+                          const OdbCallback& cb, cudaStream_t st);
+int odb_mix_general_ctas(int n_sources, int sm_count);
+cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
+                                   int only_flagged, cudaStream_t st);
+void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, float* out, int n_frames, int n_tiles,
+                       int epilogue, cudaStream_t st);

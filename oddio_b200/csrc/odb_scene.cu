@@ -1,0 +1,357 @@
+// odb_scene_*: SpatialSceneControl + SpatialScene over the device-resident source sets.
+// Reference: src/spatial.rs (cited per function), src/lib.rs:90-93.
+#include <cmath>
+
+#include "odb_host.h"
+
+#define ODB_TAG_SEEK 1u
+#define ODB_TAG_BUFFERED 2u
+#define ODB_MAX_FRAMES (4 * ODB_TILE_FRAMES)
+
+struct odb_scene {
+    uint32_t kind = ODB_KIND_SCENE;
+    odb_ctx* ctx = nullptr;
+    std::mutex mu;  // guards the control-plane queues of both sets and the rotation
+    SourceSet seek, buffered;
+    // swap::Receiver<Quaternion> (spatial.rs:161): received + pending, stored already inverted (:346)
+    OdbQuat rot_received = {0.0f, 0.0f, 0.0f, 1.0f};
+    OdbQuat rot_pending = {0.0f, 0.0f, 0.0f, 1.0f};
+    bool rot_fresh = false;
+    int epilogue = ODB_EPILOGUE_NONE;
+    int variant = 0;
+    uint32_t last_launches = 0;
+    DevBuf<OdbJob> d_jobs;
+    DevBuf<float> d_partials;
+    DevBuf<float> d_partials_fast;
+    DevBuf<float> d_out;
+    PinBuf<float> h_out;
+};
+
+static int scene_check(odb_scene* s) {
+    if (!s || s->kind != ODB_KIND_SCENE) return odb_fail(ODB_E_INVALID, "not a scene handle");
+    return ODB_OK;
+}
+
+extern "C" int odb_scene_create(odb_ctx* ctx, odb_scene** out) {
+    if (!ctx || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    odb_scene* s = new odb_scene();
+    s->ctx = ctx;
+    *out = s;
+    return ODB_OK;
+}
+extern "C" int odb_scene_destroy(odb_scene* scene) {
+    if (!scene) return ODB_OK;
+    ODB_TRY(scene_check(scene));
+    cudaSetDevice(scene->ctx->device);
+    cudaStreamSynchronize(scene->ctx->stream);
+    scene->seek.release_all(scene->ctx);
+    scene->buffered.release_all(scene->ctx);
+    scene->d_jobs.release(); scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_out.release();
+    scene->h_out.release();
+    scene->kind = 0;
+    delete scene;
+    return ODB_OK;
+}
+extern "C" int odb_scene_set_epilogue(odb_scene* scene, int epilogue) {
+    ODB_TRY(scene_check(scene));
+    if (epilogue < 0 || epilogue > 2) return odb_fail(ODB_E_INVALID, "unknown epilogue %d", epilogue);
+    scene->epilogue = epilogue;
+    return ODB_OK;
+}
+
+// Builds the device record of FramesSignal::new(frames, start) under the chain's wrappers.
+static int make_source(odb_ctx* ctx, const odb_chain* chain, int want_channels, OdbSource* out, FramesRec* rec) {
+    if (!chain) return odb_fail(ODB_E_INVALID, "chain is NULL");
+    ODB_TRY(ctx->frames_ref(chain->frames, rec));
+    if (rec->channels != want_channels) {
+        ctx->frames_unref(chain->frames);
+        return odb_fail(ODB_E_UNSUPPORTED, "signal has %d channel(s), %d required", rec->channels, want_channels);
+    }
+    OdbSource s;
+    memset(&s, 0, sizeof s);
+    s.pcm = rec->dev;
+    s.rate = (double)rec->rate;                                   // frames.rs:40
+    s.t = chain->start_seconds;                                   // frames.rs:159
+    s.sample_t = (long long)(chain->start_seconds * s.rate);      // frames.rs:160
+    s.len = (int)rec->n_frames;
+    s.channels = rec->channels;
+    s.speed = (chain->flags & ODB_CHAIN_SPEED) ? chain->speed : 1.0f;
+    s.fixed_gain = (chain->flags & ODB_CHAIN_FIXED_GAIN) ? powf(10.0f, chain->fixed_gain_db / 20.0f) : 1.0f;  // gain.rs:20
+    float g = (chain->flags & ODB_CHAIN_GAIN) ? chain->gain_ratio : 1.0f;
+    s.gain_shared = g; s.gain_prev = g; s.gain_next = g; s.gain_progress = 1.0f;                              // gain.rs:90-93
+    if (chain->flags & ODB_CHAIN_SPEED) s.flags |= ODB_SF_SPEED;
+    if (chain->flags & ODB_CHAIN_FIXED_GAIN) s.flags |= ODB_SF_FIXED_GAIN;
+    if (chain->flags & ODB_CHAIN_GAIN) s.flags |= ODB_SF_GAIN;
+    *out = s;
+    return ODB_OK;
+}
+
+// SpatialSceneControl::play, spatial.rs:289-302 (+ SpatialSignal::new :66-81, Common::new :94-116)
+extern "C" int odb_scene_play(odb_scene* scene, const odb_chain* chain, const float position[3], const float velocity[3],
+                              float radius, odb_source* out) {
+    ODB_TRY(scene_check(scene));
+    if (!chain || !position || !velocity || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    if (chain->flags & (ODB_CHAIN_SPEED | ODB_CHAIN_GAIN))
+        return odb_fail(ODB_E_UNSUPPORTED, "SpatialSceneControl::play requires Seek; Speed and Gain do not implement it (use play_buffered)");
+    OdbSource s;
+    FramesRec rec;
+    ODB_TRY(make_source(scene->ctx, chain, 1, &s, &rec));
+    s.radius = radius;
+    for (int k = 0; k < 3; k++) {
+        s.pos[k] = position[k]; s.vel[k] = velocity[k];          // Motion, discontinuity: false (:100-104)
+        s.ppos[k] = position[k]; s.pvel[k] = velocity[k];
+        s.prev_position[k] = position[k];                         // State::new (:494-499)
+    }
+    s.state_dt = 0.0f;
+    std::lock_guard<std::mutex> lk(scene->mu);
+    uint32_t slot = scene->seek.alloc_slot();
+    SlotHost& sh = scene->seek.slots[slot];
+    sh.frames = chain->frames; sh.chain_flags = chain->flags; sh.n_frames = rec.n_frames; sh.rate = (double)rec.rate;
+    scene->seek.ins_src.push_back(s);
+    scene->seek.ins_slot.push_back(slot);
+    *out = scene->seek.handle_of(slot, ODB_TAG_SEEK);
+    return ODB_OK;
+}
+
+extern "C" int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain, const float position[3],
+                                       const float velocity[3], float radius, float max_distance, uint32_t rate,
+                                       float buffer_duration, odb_source* out) {
+    ODB_TRY(scene_check(scene));
+    (void)chain; (void)position; (void)velocity; (void)radius; (void)max_distance; (void)rate; (void)buffer_duration; (void)out;
+    return odb_fail(ODB_E_UNSUPPORTED, "play_buffered: device ring path not built yet");
+}
+
+// SpatialSceneControl::set_listener_rotation, spatial.rs:345-349 (stores the conjugate, math/mod.rs:62-67)
+extern "C" int odb_scene_set_listener_rotation(odb_scene* scene, const float q[4]) {
+    ODB_TRY(scene_check(scene));
+    if (!q) return odb_fail(ODB_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(scene->mu);
+    scene->rot_pending = OdbQuat{-q[0], -q[1], -q[2], q[3]};
+    scene->rot_fresh = true;
+    return ODB_OK;
+}
+
+static SourceSet* set_of(odb_scene* scene, odb_source src, uint32_t* tag) {
+    *tag = (uint32_t)((src >> 32) & 0xFF);
+    return *tag == ODB_TAG_SEEK ? &scene->seek : (*tag == ODB_TAG_BUFFERED ? &scene->buffered : nullptr);
+}
+
+// Spatial::set_motion, spatial.rs:137-149
+extern "C" int odb_spatial_set_motion(odb_scene* scene, odb_source src, const float position[3], const float velocity[3],
+                                      int discontinuity) {
+    ODB_TRY(scene_check(scene));
+    if (!position || !velocity) return odb_fail(ODB_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(scene->mu);
+    uint32_t tag, slot; bool stale;
+    SourceSet* set = set_of(scene, src, &tag);
+    if (!set) return odb_fail(ODB_E_INVALID, "not a spatial source handle");
+    ODB_TRY(set->lookup(src, tag, &slot, &stale));
+    if (stale) return ODB_OK;  // the signal is gone; the reference's Sender writes into a slot nobody reads
+    set->queue_motion(slot, position, velocity, discontinuity);
+    return ODB_OK;
+}
+// Spatial::is_finished, spatial.rs:154-156
+extern "C" int odb_spatial_is_finished(odb_scene* scene, odb_source src, int* out) {
+    ODB_TRY(scene_check(scene));
+    if (!out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(scene->mu);
+    uint32_t tag, slot; bool stale;
+    SourceSet* set = set_of(scene, src, &tag);
+    if (!set) return odb_fail(ODB_E_INVALID, "not a spatial source handle");
+    ODB_TRY(set->lookup(src, tag, &slot, &stale));
+    *out = stale ? 1 : 0;
+    return ODB_OK;
+}
+extern "C" int odb_scene_len(odb_scene* scene, int buffered, uint64_t* out) {
+    ODB_TRY(scene_check(scene));
+    if (!out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(scene->mu);
+    *out = buffered ? scene->buffered.order.size() : scene->seek.order.size();
+    return ODB_OK;
+}
+
+// <SpatialScene as Signal>::sample, spatial.rs:376-471. Leaves the mixed tile in scene->d_out (or
+// `dev_out` when given) on the context's stream.
+static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames) {
+    odb_ctx* ctx = scene->ctx;
+    cudaStream_t st = ctx->stream;
+    if (n_frames > ODB_MAX_FRAMES)
+        return odb_fail(ODB_E_UNSUPPORTED, "n_frames %u exceeds the %d frames one callback may render", n_frames, ODB_MAX_FRAMES);
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    uint32_t launches = 0;
+    OdbCallback cb;
+    {
+        std::lock_guard<std::mutex> lk(scene->mu);
+        // a removed list left over from a *_sample_device call must be folded in before the order is used
+        if (scene->seek.removed_pending) {
+            ODB_CUDA(cudaStreamSynchronize(st));
+            scene->seek.process_removed(ctx);
+        }
+        ODB_TRY(scene->seek.apply(ctx, st, &launches));                     // set.update(), spatial.rs:437
+        cb.prev_rot = scene->rot_received;                                 // spatial.rs:382-386
+        if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
+        cb.rot = scene->rot_received;
+    }
+    cb.interval = interval;
+    cb.n_frames = (int)n_frames;
+    cb.elapsed = interval * (float)n_frames;                               // spatial.rs:394
+    cb.n_tiles = (int)((n_frames + ODB_TILE_FRAMES - 1) / ODB_TILE_FRAMES);
+    cb.n_sources = (int)scene->seek.order.size();
+    const int ns = cb.n_sources, nt = cb.n_tiles;
+
+    ODB_CUDA(cudaMemsetAsync(scene->seek.d_removed.p, 0, sizeof(uint32_t), st));
+    if (ns > 0) {
+        ODB_TRY(scene->d_jobs.ensure((size_t)ns * (nt > 0 ? nt : 1), st, false));
+        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs.p, scene->seek.d_removed.p, ns, cb, st);
+        launches++;
+    }
+    if (nt > 0) {
+        int n_parts = 0;
+        if (ns > 0) {
+            n_parts = odb_mix_general_ctas(ns, ctx->sm_count);
+            ODB_TRY(scene->d_partials.ensure((size_t)nt * n_parts * 2 * ODB_TILE_FRAMES, st, false));
+            cudaError_t e = odb_launch_mix_general(scene->d_jobs.p, ns, nt, scene->d_partials.p, n_parts, /*only_flagged=*/0, st);
+            if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_general launch failed: %s", cudaGetErrorString(e));
+            launches++;
+        }
+        odb_launch_reduce(scene->d_partials.p, n_parts, nullptr, 0, dev_out, (int)n_frames, nt, scene->epilogue, st);
+        launches++;
+    }
+    // bring back what walk_set removed (header eagerly, the rest on demand in process_removed)
+    size_t hdr = std::min<size_t>((size_t)ns + 1, ODB_REMOVED_CAP);
+    ODB_CUDA(cudaMemcpyAsync(scene->seek.h_removed.p, scene->seek.d_removed.p, hdr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    scene->seek.removed_pending = true;
+    scene->seek.removed_order_len = ns;
+    scene->last_launches = launches;
+    ODB_CUDA(cudaGetLastError());
+    return ODB_OK;
+}
+
+extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, uint32_t n_frames) {
+    ODB_TRY(scene_check(scene));
+    if (!out && n_frames) return odb_fail(ODB_E_INVALID, "out is NULL");
+    odb_ctx* ctx = scene->ctx;
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)n_frames * 2;
+    ODB_TRY(scene->d_out.ensure(n ? n : 2, ctx->stream, false));
+    ODB_TRY(scene->h_out.ensure(n ? n : 2));
+    ODB_TRY(scene_sample_impl(scene, interval, scene->d_out.p, n_frames));
+    if (n) ODB_CUDA(cudaMemcpyAsync(scene->h_out.p, scene->d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
+    std::lock_guard<std::mutex> lk(scene->mu);
+    scene->seek.process_removed(ctx);
+    return ODB_OK;
+}
+// oddio::run, lib.rs:90-93
+extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {
+    float interval = 1.0f / (float)sample_rate;
+    return odb_scene_sample(scene, interval, out, n_frames);
+}
+extern "C" int odb_scene_sample_device(odb_scene* scene, float interval, void* dev_out, uint32_t n_frames) {
+    ODB_TRY(scene_check(scene));
+    if (!dev_out && n_frames) return odb_fail(ODB_E_INVALID, "dev_out is NULL");
+    return scene_sample_impl(scene, interval, (float*)dev_out, n_frames);
+}
+
+// ---- per-source controls / read-backs ---------------------------------------------------------------
+static int owner_set(void* owner, odb_source src, odb_ctx** ctx, std::mutex** mu, SourceSet** set, uint32_t* tag);
+
+static int read_source(void* owner, odb_source src, OdbSource* out, bool* stale, SlotHost* shost) {
+    odb_ctx* ctx; std::mutex* mu; SourceSet* set; uint32_t tag, slot;
+    ODB_TRY(owner_set(owner, src, &ctx, &mu, &set, &tag));
+    std::lock_guard<std::mutex> lk(*mu);
+    ODB_TRY(set->lookup(src, tag, &slot, stale));
+    if (shost) *shost = set->slots[slot];
+    if (*stale) return ODB_OK;
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    if (slot >= set->d_src.cap) {  // queued but not yet applied: answer from the queue
+        for (size_t i = 0; i < set->ins_slot.size(); i++)
+            if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
+    }
+    for (size_t i = 0; i < set->ins_slot.size(); i++)
+        if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
+    ODB_CUDA(cudaMemcpyAsync(out, set->d_src.p + slot, sizeof(OdbSource), cudaMemcpyDeviceToHost, ctx->stream));
+    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ODB_OK;
+}
+
+extern "C" int odb_source_playback_position(void* owner, odb_source src, double* out_seconds) {
+    if (!out_seconds) return odb_fail(ODB_E_INVALID, "NULL argument");
+    OdbSource s; bool stale; SlotHost sh;
+    ODB_TRY(read_source(owner, src, &s, &stale, &sh));
+    if (stale) return odb_fail(ODB_E_INVALID, "source no longer exists");
+    *out_seconds = (double)s.sample_t / s.rate;  // frames.rs:238-240
+    return ODB_OK;
+}
+extern "C" int odb_source_frames_is_finished(void* owner, odb_source src, int* out) {
+    if (!out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    OdbSource s; bool stale; SlotHost sh;
+    ODB_TRY(read_source(owner, src, &s, &stale, &sh));
+    if (stale) { *out = 1; return ODB_OK; }
+    *out = (s.sample_t >= 0 && (unsigned long long)s.sample_t >= (unsigned long long)s.len) ? 1 : 0;  // frames.rs:244-247
+    return ODB_OK;
+}
+extern "C" int odb_source_cursor(void* owner, odb_source src, double* out_t, float* out_ring_write) {
+    OdbSource s; bool stale; SlotHost sh;
+    ODB_TRY(read_source(owner, src, &s, &stale, &sh));
+    if (stale) return odb_fail(ODB_E_INVALID, "source no longer exists");
+    if (out_t) *out_t = s.t;
+    if (out_ring_write) *out_ring_write = s.ring_write;
+    return ODB_OK;
+}
+
+// mixer side lives in odb_mixer.cu
+int odb_mixer_owner_set(void* owner, odb_source src, odb_ctx** ctx, std::mutex** mu, SourceSet** set, uint32_t* tag);
+int odb_mixer_last_launches(void* owner, uint32_t* out);
+int odb_mixer_set_variant(void* owner, int variant);
+
+static int owner_set(void* owner, odb_source src, odb_ctx** ctx, std::mutex** mu, SourceSet** set, uint32_t* tag) {
+    if (!owner) return odb_fail(ODB_E_INVALID, "owner is NULL");
+    uint32_t kind = *(uint32_t*)owner;
+    if (kind == ODB_KIND_SCENE) {
+        odb_scene* sc = (odb_scene*)owner;
+        *ctx = sc->ctx; *mu = &sc->mu;
+        *set = set_of(sc, src, tag);
+        if (!*set) return odb_fail(ODB_E_INVALID, "not a source of this scene");
+        return ODB_OK;
+    }
+    if (kind == ODB_KIND_MIXER) return odb_mixer_owner_set(owner, src, ctx, mu, set, tag);
+    return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
+}
+
+static int queue_param(void* owner, odb_source src, uint32_t what, float value, uint32_t need_flag, const char* name) {
+    odb_ctx* ctx; std::mutex* mu; SourceSet* set; uint32_t tag, slot; bool stale;
+    ODB_TRY(owner_set(owner, src, &ctx, &mu, &set, &tag));
+    std::lock_guard<std::mutex> lk(*mu);
+    ODB_TRY(set->lookup(src, tag, &slot, &stale));
+    if (stale) return ODB_OK;
+    if (need_flag && !(set->slots[slot].chain_flags & need_flag))
+        return odb_fail(ODB_E_INVALID, "source has no %s in its chain", name);
+    set->queue_param(slot, what, value);
+    return ODB_OK;
+}
+extern "C" int odb_source_set_speed(void* owner, odb_source src, float factor) {
+    return queue_param(owner, src, ODB_PARAM_SPEED, factor, ODB_CHAIN_SPEED, "Speed");
+}
+extern "C" int odb_source_set_amplitude_ratio(void* owner, odb_source src, float factor) {
+    return queue_param(owner, src, ODB_PARAM_GAIN, factor, ODB_CHAIN_GAIN, "Gain");
+}
+extern "C" int odb_source_set_gain_db(void* owner, odb_source src, float db) {
+    return queue_param(owner, src, ODB_PARAM_GAIN, powf(10.0f, db / 20.0f), ODB_CHAIN_GAIN, "Gain");  // gain.rs:143-145
+}
+
+extern "C" int odb_last_launch_count(void* owner, uint32_t* out) {
+    if (!owner || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    uint32_t kind = *(uint32_t*)owner;
+    if (kind == ODB_KIND_SCENE) { *out = ((odb_scene*)owner)->last_launches; return ODB_OK; }
+    if (kind == ODB_KIND_MIXER) return odb_mixer_last_launches(owner, out);
+    return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
+}
+extern "C" int odb_set_kernel_variant(void* owner, int variant) {
+    if (!owner) return odb_fail(ODB_E_INVALID, "NULL argument");
+    uint32_t kind = *(uint32_t*)owner;
+    if (kind == ODB_KIND_SCENE) { ((odb_scene*)owner)->variant = variant; return ODB_OK; }
+    if (kind == ODB_KIND_MIXER) return odb_mixer_set_variant(owner, variant);
+    return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
+}

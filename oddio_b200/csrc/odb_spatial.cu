@@ -1,0 +1,309 @@
+// Spatial-scene kernels: walk (per-source set-up), general mix (exact, any parameters), reduce.
+// Reference: src/spatial.rs, src/frames.rs, src/frame.rs, src/math/mod.rs (cited per function).
+#include <cuda_runtime.h>
+
+#include "odb_kernels.h"
+#include "odb_math.cuh"
+
+namespace odbk {
+
+// ------------------------------------------------------------------------------------------
+// Control-plane scatter kernels: apply what SetHandle::insert / Spatial::set_motion queued since
+// the previous callback (set.rs:141-178 drain_msgs, swap.rs:57-64 refresh).
+__global__ void k_scatter_sources(OdbSource* __restrict__ src, const OdbSource* __restrict__ staged,
+                                  const uint32_t* __restrict__ slots, int n) {
+    // one 16-byte word per thread: sizeof(OdbSource)/16 words per source
+    const int words = (int)(sizeof(OdbSource) / 16);
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = gid / words, w = gid % words;
+    if (i >= n) return;
+    const uint4* s = reinterpret_cast<const uint4*>(staged + i);
+    uint4* d = reinterpret_cast<uint4*>(src + slots[i]);
+    d[w] = s[w];
+}
+
+__global__ void k_scatter_motion(OdbSource* __restrict__ src, const OdbMotionMsg* __restrict__ msgs, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OdbMotionMsg m = msgs[i];
+    OdbSource* s = src + m.slot;
+    s->ppos[0] = m.pos[0]; s->ppos[1] = m.pos[1]; s->ppos[2] = m.pos[2];
+    s->pvel[0] = m.vel[0]; s->pvel[1] = m.vel[1]; s->pvel[2] = m.vel[2];
+    uint32_t f = s->flags | ODB_SF_MOTION_FRESH;
+    f = m.discontinuity ? (f | ODB_SF_PENDING_DISC) : (f & ~ODB_SF_PENDING_DISC);
+    s->flags = f;
+}
+
+__global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg* __restrict__ msgs, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OdbParamMsg m = msgs[i];
+    OdbSource* s = src + m.slot;
+    if (m.what == ODB_PARAM_SPEED) s->speed = m.value;               // SpeedControl::set_speed speed.rs:52-54
+    else if (m.what == ODB_PARAM_GAIN) s->gain_shared = m.value;     // GainControl::set_amplitude_ratio gain.rs:157-159
+    else if (m.what == ODB_PARAM_STOP) s->flags |= ODB_SF_STOP_REQ;  // Mixed::stop mixer.rs:34-36
+}
+
+// ------------------------------------------------------------------------------------------
+// walk_set for the seek set (spatial.rs:191-265) plus everything of the mix closure
+// (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
+// cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213). One thread per source.
+// Writes one OdbJob per (tile, source) and the source's state for the next callback.
+__global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
+                                                   OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
+                                                   int removed_cap, OdbCallback cb) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cb.n_sources) return;
+    OdbSource* sp = src + order[idx];
+    OdbSource s = *sp;
+    const int n = cb.n_frames;
+    const float elapsed = cb.elapsed;
+
+    // --- motion refresh, spatial.rs:216-226
+    V3 pos = {s.pos[0], s.pos[1], s.pos[2]}, vel = {s.vel[0], s.vel[1], s.vel[2]};
+    V3 statep = {s.prev_position[0], s.prev_position[1], s.prev_position[2]};
+    float state_dt = s.state_dt;
+    uint32_t flags = s.flags;
+    if (flags & ODB_SF_MOTION_FRESH) {
+        V3 npos = {s.ppos[0], s.ppos[1], s.ppos[2]}, nvel = {s.pvel[0], s.pvel[1], s.pvel[2]};
+        statep = (flags & ODB_SF_PENDING_DISC) ? npos : smoothed_position(statep, state_dt, 0.0f, pos, vel);
+        state_dt = 0.0f;
+        pos = npos; vel = nvel;
+        flags &= ~ODB_SF_MOTION_FRESH;
+        sp->pos[0] = pos.x; sp->pos[1] = pos.y; sp->pos[2] = pos.z;
+        sp->vel[0] = vel.x; sp->vel[1] = vel.y; sp->vel[2] = vel.z;
+    }
+    // --- smoothed start/end positions in the listener's frame, spatial.rs:228-235
+    V3 prev_position = q_rotate(cb.prev_rot, smoothed_position(statep, state_dt, 0.0f, pos, vel));
+    V3 next_position = q_rotate(cb.rot, smoothed_position(statep, state_dt, elapsed, pos, vel));
+    state_dt = state_dt + elapsed;  // :238
+    sp->prev_position[0] = statep.x; sp->prev_position[1] = statep.y; sp->prev_position[2] = statep.z;
+    sp->state_dt = state_dt;
+
+    // --- finished / stopped bookkeeping, spatial.rs:243-261
+    double t = s.t;
+    const double rate = s.rate;
+    bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
+    if (!was_stopped) {
+        float distance = v_norm(prev_position);
+        if (flags & ODB_SF_HAS_FINISHED_FOR) {
+            if (s.finished_for > distance / ODB_SPEED_OF_SOUND) flags |= ODB_SF_STOPPED;
+            else sp->finished_for = s.finished_for + elapsed;
+        } else if (t >= (double)(s.len - 1) / rate) {  // FramesSignal::is_finished frames.rs:204-206
+            flags |= ODB_SF_HAS_FINISHED_FOR;
+            sp->finished_for = elapsed;
+        }
+    }
+    sp->flags = flags;
+    const int nt = cb.n_tiles, ns = cb.n_sources;
+    if (flags & ODB_SF_STOPPED) {
+        if (!was_stopped) {  // set.remove(i): report the index so the host can swap_remove it
+            uint32_t k = atomicAdd(removed, 1u);
+            if ((int)k < removed_cap) removed[1 + k] = (uint32_t)idx;
+        }
+        for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
+        return;
+    }
+
+    // --- mix closure set-up, spatial.rs:446-468
+    const float nf = (float)n;
+    const float ratef = (float)rate;  // `self.data.rate as f32` frames.rs:178
+    const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
+    uint32_t jflags[4] = {0, 0, 0, 0};  // per tile (n_tiles <= 4 enforced by the host)
+    long long sample_t = s.sample_t;
+    for (int e = 0; e < 2; e++) {
+        EarSt ps = ear_state(prev_position, e, s.radius);
+        EarSt nx = ear_state(next_position, e, s.radius);
+        t = t + (double)ps.offset;                                    // :449 seek(prev.offset)
+        float eff = (elapsed + nx.offset) - ps.offset;                // :451
+        float dt = eff / nf;                                          // :452
+        float d_gain = (nx.gain - ps.gain) / nf;                      // :453
+        float ds = dt * ratef;                                        // frames.rs:178
+        bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
+        bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
+        for (int cg = 0; cg < n_chunks; cg++) {
+            int tl = cg / ODB_TILE_CHUNKS, c = cg % ODB_TILE_CHUNKS;
+            int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
+            double s0 = t * rate;                                     // frames.rs:177
+            long long base = (long long)s0;                           // frames.rs:179
+            float off0 = (float)(s0 - (double)base);                  // frames.rs:183 / :189
+            if (off0 < 0.0f) general = true;                          // negative-fract quirk
+            OdbJob* j = jobs + (size_t)tl * ns + idx;
+            j->base[e][c] = sat_i32(base);
+            j->off0[e][c] = off0;
+            t = t + (double)dt * (double)m;                           // frames.rs:198
+            sample_t = (long long)(t * rate);                         // frames.rs:199-200
+        }
+        t = t + (double)(-eff - ps.offset);                           // :465
+        for (int tl = 0; tl < nt; tl++) {
+            OdbJob* j = jobs + (size_t)tl * ns + idx;
+            j->ds[e] = ds; j->pg[e] = ps.gain; j->dg[e] = d_gain;
+            jflags[tl] |= (fast ? (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R) : 0u) | (general ? ODB_JF_GENERAL : 0u);
+        }
+    }
+    t = t + (double)elapsed;                                          // :468
+    sp->t = t;
+    sp->sample_t = sample_t;
+    for (int tl = 0; tl < nt; tl++) {
+        OdbJob* j = jobs + (size_t)tl * ns + idx;
+        j->pcm = s.pcm; j->len = s.len;
+        j->fixed_gain = s.fixed_gain;
+        j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
+        j->frame0 = (float)(tl * ODB_TILE_FRAMES);
+        j->flags = jflags[tl] | ((flags & ODB_SF_FIXED_GAIN) ? (ODB_JF_FIXED_GAIN | ODB_JF_GENERAL) : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// General mix kernel: exact for every parameter combination (any ds incl. <= 0, negative
+// offsets, FixedGain). One warp per (tile, source); lanes 0..7 each walk one (ear, chunk)
+// chain literally as FramesSignal::sample does (frames.rs:184-196) and write the per-frame
+// contribution s * gain (spatial.rs:459-460) into a warp-private smem tile; all 32 lanes then
+// fold the tile into register accumulators (lane l owns frames l, l+32, ...). Every operation
+// is a single unfused IEEE op in the reference's order, so a source's contribution is
+// bit-identical to the reference's.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __restrict__ jobs, int n_sources,
+                                                            float* __restrict__ partials, int only_flagged) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = smem + warp * (2 * ODB_TILE_FRAMES);
+    const int tl = blockIdx.y;
+    const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    float2 acc[ODB_TILE_FRAMES / 32];
+#pragma unroll
+    for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) acc[j] = make_float2(0.0f, 0.0f);
+
+    for (int sidx = gw; sidx < n_sources; sidx += GW) {
+        const OdbJob* job = jobs + (size_t)tl * n_sources + sidx;
+        const uint32_t jf = job->flags;
+        if (jf & ODB_JF_SKIP) continue;
+        if (only_flagged && !(jf & ODB_JF_GENERAL)) continue;
+        if (lane < 2 * ODB_TILE_CHUNKS) {
+            const int e = lane & 1, c = lane >> 1;
+            const float* __restrict__ pcm = job->pcm;
+            const int len = job->len;
+            const int m = max(0, min(ODB_SPATIAL_CHUNK, job->n_frames - c * ODB_SPATIAL_CHUNK));
+            const float ds = job->ds[e], pg = job->pg[e], dg = job->dg[e], fg = job->fixed_gain;
+            const long long base = job->base[e][c];
+            const bool fast = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
+            const bool has_fg = (jf & ODB_JF_FIXED_GAIN) != 0;
+            float offset = job->off0[e][c];
+            float fi = job->frame0 + (float)(c * ODB_SPATIAL_CHUNK);  // exact: small integers
+            for (int k = 0; k < ODB_SPATIAL_CHUNK; k++) {
+                float contrib = 0.0f;
+                if (k < m) {
+                    float a, b, fract;
+                    if (fast) {                                            // frames.rs:183-187
+                        get_pair_mono(pcm, len, base + k, a, b);
+                        fract = offset;
+                    } else {                                               // frames.rs:189-196
+                        long long tr = (long long)offset;
+                        get_pair_mono(pcm, len, base + tr, a, b);
+                        fract = offset - (float)tr;
+                        offset = offset + ds;
+                    }
+                    float smp = a + fract * (b - a);                       // frame.rs:39-41
+                    if (has_fg) smp = smp * fg;                            // gain.rs:35
+                    float gain = pg + fi * dg;                             // spatial.rs:459
+                    contrib = smp * gain;                                  // spatial.rs:460
+                    fi = fi + 1.0f;
+                }
+                tile[(c * ODB_SPATIAL_CHUNK + k) * 2 + e] = contrib;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) {
+            float2 v = *reinterpret_cast<const float2*>(tile + (32 * j + lane) * 2);
+            acc[j].x = acc[j].x + v.x;
+            acc[j].y = acc[j].y + v.y;
+        }
+        __syncwarp();
+    }
+    // CTA-level fold in fixed warp order, then one partial tile per CTA.
+#pragma unroll
+    for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) *reinterpret_cast<float2*>(tile + (32 * j + lane) * 2) = acc[j];
+    __syncthreads();
+    float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * (2 * ODB_TILE_FRAMES);
+    for (int f = threadIdx.x; f < 2 * ODB_TILE_FRAMES; f += WARPS * 32) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) sum = sum + smem[w * (2 * ODB_TILE_FRAMES) + f];
+        dst[f] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Second-stage reduce: sums the per-CTA partial tiles of up to two partial sets in a fixed
+// order (deterministic), applies the optional Tanh / Reinhard wrapper (tanh.rs:24-28,
+// reinhard.rs:30-34) and writes the interleaved stereo output.
+__global__ void k_reduce_tiles(const float* __restrict__ pa, int na, const float* __restrict__ pb, int nb,
+                               float* __restrict__ out, int n_frames, int epilogue) {
+    const int tl = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= 2 * ODB_TILE_FRAMES) return;
+    const int frame = tl * ODB_TILE_FRAMES + (f >> 1);
+    if (frame >= n_frames) return;
+    float sum = 0.0f;
+    const float* p = pa + (size_t)tl * na * (2 * ODB_TILE_FRAMES) + f;
+    for (int i = 0; i < na; i++) sum = sum + p[(size_t)i * (2 * ODB_TILE_FRAMES)];
+    if (nb > 0) {
+        const float* q = pb + (size_t)tl * nb * (2 * ODB_TILE_FRAMES) + f;
+        for (int i = 0; i < nb; i++) sum = sum + q[(size_t)i * (2 * ODB_TILE_FRAMES)];
+    }
+    if (epilogue == 1) sum = tanhf(sum);
+    else if (epilogue == 2) sum = sum / (1.0f + fabsf(sum));
+    out[(size_t)frame * 2 + (f & 1)] = sum;
+}
+
+}  // namespace odbk
+
+// ------------------------------------------------------------------------------------------
+// Launchers (host side, called from odb_api.cu)
+using namespace odbk;
+
+void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const uint32_t* slots, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    long long total = (long long)n * (long long)(sizeof(OdbSource) / 16);
+    k_scatter_sources<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, staged, slots, n);
+}
+void odb_launch_scatter_motion(OdbSource* src, const OdbMotionMsg* msgs, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_scatter_motion<<<(n + 127) / 128, 128, 0, st>>>(src, msgs, n);
+}
+void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_scatter_params<<<(n + 127) / 128, 128, 0, st>>>(src, msgs, n);
+}
+void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
+                          const OdbCallback& cb, cudaStream_t st) {
+    if (cb.n_sources <= 0) return;
+    k_walk_seek<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, cb);
+}
+
+static const int GEN_WARPS = 8;
+int odb_mix_general_ctas(int n_sources, int sm_count) {
+    int want = (n_sources + GEN_WARPS - 1) / GEN_WARPS;
+    int cap = sm_count * 3;
+    return want < 1 ? 1 : (want > cap ? cap : want);
+}
+cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
+                                   int only_flagged, cudaStream_t st) {
+    static bool attr_set = false;
+    const int smem = GEN_WARPS * 2 * ODB_TILE_FRAMES * (int)sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_mix_general<GEN_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(n_ctas, n_tiles);
+    k_mix_general<GEN_WARPS><<<grid, GEN_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged);
+    return cudaGetLastError();
+}
+void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, float* out, int n_frames, int n_tiles,
+                       int epilogue, cudaStream_t st) {
+    if (n_frames <= 0) return;
+    dim3 grid((2 * ODB_TILE_FRAMES + 255) / 256, n_tiles);
+    k_reduce_tiles<<<grid, 256, 0, st>>>(pa, na, pb, nb, out, n_frames, epilogue);
+}

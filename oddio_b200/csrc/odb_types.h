@@ -1,0 +1,89 @@
+// Device/host shared data layout of the oddio_b200 hot path. See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <stdint.h>
+
+#define ODB_SPATIAL_CHUNK 256   // spatial.rs:393 `let mut buf = [0.0; 256]`
+#define ODB_MIXER_CHUNK 1024    // mixer.rs:77 staging buffer
+#define ODB_TILE_FRAMES 1024    // output frames one mix-kernel pass accumulates in registers
+#define ODB_TILE_CHUNKS (ODB_TILE_FRAMES / ODB_SPATIAL_CHUNK)
+#define ODB_PCM_PAD 64          // zero floats kept before and after every Frames block in the arena
+
+// source flags
+#define ODB_SF_STOPPED 0x1u          // Common::stopped (spatial.rs:90) / MixedSignal::stop (mixer.rs:47)
+#define ODB_SF_HAS_FINISHED_FOR 0x2u // Common::finished_for is Some (spatial.rs:89)
+#define ODB_SF_MOTION_FRESH 0x4u     // swap::Receiver::refresh() would return true (swap.rs:57-64)
+#define ODB_SF_PENDING_DISC 0x8u     // pending Motion::discontinuity
+#define ODB_SF_MOTION_DISC 0x10u     // received Motion::discontinuity
+#define ODB_SF_FIXED_GAIN 0x20u      // chain has FixedGain
+#define ODB_SF_SPEED 0x40u           // chain has Speed
+#define ODB_SF_GAIN 0x80u            // chain has Gain
+#define ODB_SF_STOP_REQ 0x100u       // Mixed::stop() requested from the control side
+
+// One playing source: SpatialSignal<FramesSignal chain> (spatial.rs:60-63) or MixedSignal (mixer.rs:46-49).
+// 160 bytes, 16-byte aligned; an array of these lives in HBM, indexed by slot.
+struct __attribute__((aligned(16))) OdbSource {
+    const float* pcm;      // first sample of the Frames block (ODB_PCM_PAD zeros on both sides)
+    double rate;           // Frames::rate (frames.rs:20)
+    double t;              // FramesSignal::t (frames.rs:145)
+    long long sample_t;    // FramesSignal::sample_t (frames.rs:149)
+    int len;               // frames in the Frames block
+    int channels;          // 1 or 2
+    uint32_t flags;        // ODB_SF_*
+    float radius;          // Common::radius
+    float finished_for;    // Common::finished_for payload
+    float state_dt;        // State::dt (spatial.rs:490)
+    float prev_position[3];// State::prev_position (spatial.rs:488)
+    float pos[3];          // received Motion (spatial.rs:480-484)
+    float vel[3];
+    float ppos[3];         // pending Motion (written by set_motion, consumed at the next sample)
+    float pvel[3];
+    float speed;           // Speed::speed (speed.rs:10)
+    float fixed_gain;      // FixedGain::gain = 10^(db/20) (gain.rs:20)
+    float gain_shared;     // Gain::shared (gain.rs:59)
+    float gain_prev;       // Smoothed::prev / next / progress (smooth.rs:27-31)
+    float gain_next;
+    float gain_progress;
+    // buffered (play_buffered) sources only
+    float* ring;           // Ring::buffer (ring.rs:5)
+    int ring_cap;
+    float ring_write;      // Ring::write (ring.rs:6)
+    float max_delay;       // SpatialSignalBuffered::max_delay
+    uint32_t ring_rate;    // SpatialSignalBuffered::rate
+};
+
+// What one (source, 1024-frame tile) pass of the spatial mix kernel needs; written by the walk
+// kernel each callback. 128 bytes.
+struct __attribute__((aligned(16))) OdbJob {
+    const float* pcm;
+    int len;
+    uint32_t flags;                 // ODB_JF_*
+    float ds[2];                    // per ear: dt * rate as f32 (frames.rs:178)
+    float pg[2];                    // prev_state.gain (spatial.rs:459)
+    float dg[2];                    // d_gain (spatial.rs:453)
+    float fixed_gain;
+    int n_frames;                   // frames of this tile (<= ODB_TILE_FRAMES)
+    int base[2][ODB_TILE_CHUNKS];   // per ear, per 256-chunk: `base` (frames.rs:179), saturated to int32
+    float off0[2][ODB_TILE_CHUNKS]; // initial `offset` / constant `fract` (frames.rs:183,189)
+    float frame0;                   // f32 index of the tile's first frame (i as f32, spatial.rs:459)
+    uint32_t pad;
+};
+#define ODB_JF_SKIP 0x1u        // source removed/stopped this callback: contributes nothing
+#define ODB_JF_FAST_L 0x2u      // |ds-1| <= EPSILON for the left ear (frames.rs:180)
+#define ODB_JF_FAST_R 0x4u
+#define ODB_JF_FIXED_GAIN 0x8u
+#define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
+
+struct OdbQuat { float x, y, z, s; };
+
+// Parameters of one scene callback, passed by value to the kernels.
+struct OdbCallback {
+    OdbQuat prev_rot, rot;   // (prev_rot, rot) of spatial.rs:382-386, already inverted (spatial.rs:346)
+    float interval;
+    float elapsed;           // interval * n_frames as f32 (spatial.rs:394)
+    int n_frames;
+    int n_tiles;
+    int n_sources;           // entries of the active list
+};
+
+static_assert(sizeof(OdbSource) % 16 == 0, "OdbSource is moved in 16-byte words");
+static_assert(sizeof(OdbJob) == 128, "OdbJob is one 128-byte line");
