@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — source-frames/s of the spatial-mix hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], "C3"): one SpatialScene with 65 536 moving point sources
+(`SpatialSceneControl::play` of a FramesSignal each: propagation delay, doppler resampling, distance
+attenuation, stereo pan), 1024 stereo frames per callback at 48 kHz. A "step" is one `oddio::run`
+callback over all sources. Every source owns its own PCM (no sharing; 19 GB in HBM in total), every
+callback reads fresh PCM, so the inputs of a step are larger than L2 by construction.
+
+One JSON line on stdout (rank 0). `value` = N_sources * frames / device time per callback with
+everything resident in HBM; `e2e` = the same through the host-buffer C-ABI call
+(`odb_scene_run`: host output tile, D2H inside the timed region, plus `set_motion` updates for 1/16 of
+the sources every callback, H2D inside the timed region); `roofline` = algorithmic PCM bytes of the
+staged mix kernel / its device time against the measured HBM peak; `cpu_baseline` = the CPU oracle
+(the only runnable statement of the Rust reference here) on a bounded sample of the same workload.
+
+N > 1: sources are sharded round-robin over the ranks (strong scaling: the 65 536 sources are the
+job); each callback ends with one NCCL all-reduce (sum) of the 8 KiB stereo tile.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RATE = 48000
+START_S = 1.0          # FramesSignal::new(frames, 1.0): > 300 m / 343 m/s, so every read hits valid PCM
+SHELL = (2.0, 300.0)   # source distance from the listener, metres
+SPEED_MAX = 50.0       # m/s  (examples/offline.rs:4 uses 50 m/s)
+DS_MAX = 1.0 + SPEED_MAX / 343.0 + 0.01
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def scene_geometry(n_sources: int, seed: int = 0x0DD10):
+    """Positions uniform in direction, U[2,300] m in range; velocities uniform in direction, U[0,50] m/s."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n_sources, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pos = (d * rng.uniform(SHELL[0], SHELL[1], size=(n_sources, 1))).astype(np.float32)
+    v = rng.normal(size=(n_sources, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    vel = (v * rng.uniform(0.0, SPEED_MAX, size=(n_sources, 1))).astype(np.float32)
+    f = rng.uniform(100.0, 4000.0, size=n_sources)
+    ph = rng.uniform(0.0, 2 * np.pi, size=n_sources)
+    return pos, vel, f, ph
+
+
+def pcm_len(frames: int, callbacks: int) -> int:
+    return int(START_S * RATE + np.ceil(DS_MAX * frames * (callbacks + 2)) + 2048)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import oddio_b200 as odb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = odb.Context(local, stream=stream.cuda_stream)  # our kernels and NCCL share one stream: no extra events
+
+    N, M, K, W = args.sources, args.frames, args.steps, args.warmup
+    pos, vel, freq, phase = scene_geometry(N)
+    mine = np.arange(rank, N, world)  # round-robin shard
+    n_local = len(mine)
+    L = pcm_len(M, K + W)
+
+    # ---- synthetic PCM, generated on the device, one private Frames block per source ------------------
+    t_setup = time.time()
+    frames = []
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x0DD10 + rank)
+    kk = torch.arange(L, device=dev, dtype=torch.float32)
+    B = 512
+    for b0 in range(0, n_local, B):
+        ids = mine[b0:b0 + B]
+        w = torch.tensor(2 * np.pi * freq[ids] / RATE, device=dev, dtype=torch.float32)[:, None]
+        ph = torch.tensor(phase[ids], device=dev, dtype=torch.float32)[:, None]
+        x = 0.5 * torch.sin(w * kk[None, :] + ph) + 0.05 * (2 * torch.rand((len(ids), L), device=dev, generator=gen) - 1)
+        x = x.contiguous()
+        torch.cuda.synchronize(dev)
+        for r in range(len(ids)):
+            frames.append(odb.Frames.from_device(RATE, 1, x[r].data_ptr(), L, ctx))
+        del x
+    pcm_gb = n_local * L * 4 / 1e9
+
+    def new_scene():
+        ctl, scene = odb.SpatialScene.new(ctx)
+        handles = []
+        for i, g in enumerate(mine):
+            handles.append(ctl.play(odb.FramesSignal(frames[i], START_S), odb.SpatialOptions(pos[g], vel[g], 0.1)))
+        return ctl, scene, handles
+
+    interval = float(np.float32(1.0) / np.float32(RATE))  # oddio::run, lib.rs:91
+    tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+
+    def step_device(scene):
+        scene.sample_device(interval, tile.data_ptr(), M)
+        if world > 1:
+            dist.all_reduce(tile)  # one NCCL sum of the 8 KiB tile per callback
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- (1) device-resident throughput ------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        ctl, scene, handles = new_scene()
+        setup_s = time.time() - t_setup
+        for _ in range(W):
+            step_device(scene)
+        launches_per_step = scene.last_launch_count() + (1 if world > 1 else 0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record(stream)
+            for _ in range(K):
+                step_device(scene)
+            e1.record(stream)
+            barrier()
+        ms = e0.elapsed_time(e1)
+        counters = scene.last_job_counters()
+        assert counters["general"] == 0, f"{counters['general']} jobs fell back to the general kernel during timing"
+        assert scene.len() == n_local, "a source finished during the timed region"
+        checksum = float(tile.abs().sum().item())
+        scene.close()
+
+        # ---- (2) mix-kernel device time for the roofline (separate pass: events around the kernel) ------------
+        ctl, scene, handles = new_scene()
+        scene.set_profiling(True)
+        kms = []
+        for i in range(W + K):
+            step_device(scene)
+            if i >= W:
+                kms.append(scene.last_mix_kernel_ms())
+        scene.close()
+
+        # ---- (3) end to end through the host-buffer call --------------------------------------------------------
+        ctl, scene, handles = new_scene()
+        host_out = np.zeros((M, 2), dtype=np.float32)
+        n_upd = max(1, n_local // 16)
+        ids_all = [h._src for h in handles]
+        rng = np.random.default_rng(7 + rank)
+        upd = []
+        for s in range(W + K):
+            sel = rng.choice(n_local, n_upd, replace=False)
+            gl = mine[sel]
+            ids = (C.c_uint64 * n_upd)(*[ids_all[i] for i in sel])
+            # the game thread nudges positions along the trajectory it already announced
+            p = (pos[gl] + vel[gl] * np.float32((s + 1) * M / RATE)).astype(np.float32)
+            upd.append((ids, p, vel[gl].copy()))
+
+        def step_e2e(s):
+            ids, p, v = upd[s]
+            ctl.set_motion_ids(ids, n_upd, p, v)
+            odb.run(scene, RATE, host_out)  # host tile: H2D of the updates and D2H of the result inside
+            if world > 1:
+                t = torch.from_numpy(host_out).to(dev, non_blocking=False)
+                dist.all_reduce(t)
+                host_out[:] = t.cpu().numpy()
+
+        for s in range(W):
+            step_e2e(s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            step_e2e(s)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        scene.close()
+
+    # max over ranks
+    times = torch.tensor([ms, e2e_s * 1e3, float(np.mean(kms))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = [float(x) for x in times.tolist()]
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        # algorithmic bytes: the PCM window, once per source per callback: 4 B * M * mean(ds)
+        r = pos / np.linalg.norm(pos, axis=1, keepdims=True)
+        ds_mean = float(np.mean(1.0 - np.sum(vel * r, axis=1) / 343.0))
+        alg_bytes = 4.0 * M * ds_mean * n_local
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        value = N * M / (ms / K * 1e-3)
+        out = {
+            "metric": "source-frames/sec (N sources x buffer frames) spatial mix",
+            "value": value, "unit": "source-frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
+                                   f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
+                       "sources": N, "frames": M, "rate": RATE, "parallelism": f"source-shard x{world}",
+                       "l2": "inputs larger than L2: every callback reads fresh PCM "
+                             f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
+                       "kernel_variant": "staged, strict (bit-exact per-source contributions)",
+                       "setup_s": round(setup_s, 1)},
+            "clocks": clk.summary(),
+            "e2e": {"value": N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
+                    "h2d_bytes_per_step": n_upd * 32, "d2h_bytes_per_step": M * 8 + 4,
+                    "note": "odb_scene_run with a host tile + set_motion on 1/16 of the sources every callback"},
+            "gpu_launches": launches_per_step * K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_mix_fast<strict>", "kernel_ms": kernel_ms,
+                         "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "kernel_share_of_step": kernel_ms / (ms / K)},
+            "checksum": checksum,
+        }
+        if args.cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, threads=1, n=args.cpu_sources)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, threads: int, n: int, reps: int = 3, warm: int = 1):
+    """Times the CPU oracle (oracle/, the restatement of the Rust reference) on a bounded sample of the
+    same workload: the first `n` sources of the same scene, same frames per callback."""
+    from oracle import pyoracle as o
+
+    M = args.frames
+    n = min(n, args.sources)
+    pos, vel, freq, phase = scene_geometry(args.sources)
+    L = pcm_len(M, reps + warm)
+    rng = np.random.default_rng(1)
+    kk = np.arange(L, dtype=np.float32)
+    scenes = [o.SpatialScene() for _ in range(threads)]
+    keep = []
+    for i in range(n):
+        x = (0.5 * np.sin(np.float32(2 * np.pi * freq[i] / RATE) * kk + np.float32(phase[i]))
+             + 0.05 * (2 * rng.random(L, dtype=np.float32) - 1)).astype(np.float32)
+        fr = o.Frames.from_slice(RATE, x)
+        keep.append(fr)
+        scenes[i % threads].play(o.FramesSignal(fr, START_S), pos[i], vel[i], 0.1)
+    secs, tile = o.time_run_sharded(scenes, RATE, M, warm, reps)
+    per_cb = secs / reps
+    return {"value": n * M / per_cb, "unit": "source-frames/s", "cores": threads,
+            "kind": "port", "sample": f"first {n} of the {args.sources} sources x {M} frames, {reps} callbacks after {warm} warm-up "
+                                      f"({per_cb * 1e3:.1f} ms per callback); C++ restatement of the Rust reference (no rustc here)",
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port; the Rust crate
+    cannot be built here) with all host threads, sources sharded over threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t0 = time.time()
+    base = cpu_baseline(args, threads=threads, n=args.ref_sources, reps=args.steps, warm=args.warmup)
+    N, M = args.sources, args.frames
+    line = {
+        "impl": "reference", "metric": "source-frames/sec (N sources x buffer frames) spatial mix",
+        "value": base["value"], "unit": "source-frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": N * M / base["value"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
+                               f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
+                   "sources": N, "frames": M, "rate": RATE, "parallelism": f"{threads} host threads, sources sharded"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "source-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(time.time() - t0, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sources", type=int, default=65536)
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--cpu-sources", type=int, default=2048, help="sources in the bounded CPU sample")
+    ap.add_argument("--ref-sources", type=int, default=8192, help="sources in the --impl reference sample")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

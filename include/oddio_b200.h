@@ -47,6 +47,10 @@ uint32_t odb_abi_version(void);
 
 /* ---- context ------------------------------------------------------------------------------- */
 int odb_ctx_create(int cuda_device, odb_ctx** out);
+/* Same, but all work is queued on the caller's CUDA stream (a cudaStream_t; NULL = the legacy
+ * default stream) instead of a private one, so it orders with the caller's own kernels and
+ * collectives (e.g. the NCCL reduce of per-GPU tiles) without extra events. */
+int odb_ctx_create_on_stream(int cuda_device, void* cuda_stream, odb_ctx** out);
 int odb_ctx_destroy(odb_ctx* ctx);
 /* Blocks until all work queued on the context's stream has finished. */
 int odb_ctx_synchronize(odb_ctx* ctx);
@@ -109,6 +113,11 @@ int odb_scene_set_listener_rotation(odb_scene* scene, const float q_xyzs[4]);
 /* Spatial::set_motion (spatial.rs:137-149) */
 int odb_spatial_set_motion(odb_scene* scene, odb_source src, const float position[3], const float velocity[3],
                            int discontinuity);
+/* Spatial::set_motion for `n` sources in one FFI call (same semantics, applied in array order; one foreign
+ * call per moving source per callback is what the reference's cheap Rust method call would become).
+ * positions / velocities are n x 3 floats, discontinuity n bytes (may be NULL = all false). */
+int odb_spatial_set_motion_many(odb_scene* scene, uint32_t n, const odb_source* srcs, const float* positions,
+                                const float* velocities, const uint8_t* discontinuity);
 /* Spatial::is_finished (spatial.rs:154-156) */
 int odb_spatial_is_finished(odb_scene* scene, odb_source src, int* out);
 /* <SpatialScene as Signal>::sample (spatial.rs:376-471): n_frames stereo frames, interleaved L,R */
@@ -154,8 +163,19 @@ int odb_source_cursor(void* owner, odb_source src, double* out_t, float* out_rin
 /* ---- introspection for tests / profiling ------------------------------------------------------------------ */
 /* Number of kernels launched by the last *_sample* call on this owner. */
 int odb_last_launch_count(void* owner, uint32_t* out);
-/* Selects the mix-kernel variant: 0 = default (fast path with general fallback per source),
- * 1 = force the general kernel for every source (slow, used to cross-check the fast path). */
+/* Per-callback job counters of the last *_sample* call on this owner, out[0] = (source, tile) jobs that
+ * took the literal general kernel, out[1] = jobs that took the staged kernel; out[2..3] reserved.
+ * Synchronises the context's stream. Benchmarks assert out[0] == 0. */
+int odb_last_job_counters(void* owner, uint32_t out[4]);
+/* Kernel timing for roofline reports: when enabled, *_sample* brackets its mix kernel with CUDA events on
+ * the context's stream; odb_last_mix_kernel_ms then synchronises and returns the device time of the
+ * dominant (staged mix) kernel of the last call. Off by default (events cost a few microseconds). */
+int odb_set_profiling(void* owner, int enabled);
+int odb_last_mix_kernel_ms(void* owner, float* out_ms);
+/* Selects the mix-kernel variant: 0 = default (staged kernel, strict arithmetic: a source's
+ * contribution is bit-identical to the reference's; general kernel per source as fallback), 1 = force the
+ * literal general kernel for every source (slow, used to cross-check), 2 = staged kernel with the three
+ * value multiply-adds contracted to FMA (cursors and indices still bit-exact). */
 int odb_set_kernel_variant(void* owner, int variant);
 
 #ifdef __cplusplus

@@ -19,7 +19,7 @@ extern "C" const char* odb_last_error(void) { return g_err.c_str(); }
 extern "C" uint32_t odb_abi_version(void) { return 1; }
 
 // ---- context -----------------------------------------------------------------------------------
-extern "C" int odb_ctx_create(int cuda_device, odb_ctx** out) {
+static int ctx_create(int cuda_device, bool own_stream, cudaStream_t stream, odb_ctx** out) {
     if (!out) return odb_fail(ODB_E_INVALID, "odb_ctx_create: out is NULL");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -33,9 +33,15 @@ extern "C" int odb_ctx_create(int cuda_device, odb_ctx** out) {
     cudaDeviceProp prop;
     ODB_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
     c->sm_count = prop.multiProcessorCount;
-    ODB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = own_stream;
+    if (own_stream) ODB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    else c->stream = stream;
     *out = c;
     return ODB_OK;
+}
+extern "C" int odb_ctx_create(int cuda_device, odb_ctx** out) { return ctx_create(cuda_device, true, nullptr, out); }
+extern "C" int odb_ctx_create_on_stream(int cuda_device, void* cuda_stream, odb_ctx** out) {
+    return ctx_create(cuda_device, false, (cudaStream_t)cuda_stream, out);
 }
 extern "C" int odb_ctx_destroy(odb_ctx* ctx) {
     if (!ctx) return ODB_OK;
@@ -43,7 +49,7 @@ extern "C" int odb_ctx_destroy(odb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->blocks)
         if (b.base) cudaFree(b.base);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ODB_OK;
 }
@@ -220,7 +226,11 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
         ODB_CUDA(cudaMemcpyAsync(d_stage_slot.p, h_stage_slot.p, ni * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         odb_launch_scatter_sources(d_src.p, d_stage_src.p, d_stage_slot.p, (int)ni, st);
         (*launches)++;
-        for (uint32_t s : ins_slot) order.push_back(s);
+        for (uint32_t s : ins_slot) {
+            if (pos_of_slot.size() <= s) pos_of_slot.resize(slots.size(), -1);
+            pos_of_slot[s] = (int)order.size();
+            order.push_back(s);
+        }
         order_dirty = true;
         ins_src.clear();
         ins_slot.clear();
@@ -259,30 +269,74 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
         }
         order_dirty = false;
     }
-    ODB_TRY(d_removed.ensure(order.size() + 1, st, false));
-    ODB_TRY(h_removed.ensure(std::max<size_t>(order.size() + 1, ODB_REMOVED_CAP)));
+    // removal report ring: every live source reports at most once, so a ring of >= order.size() never overflows
+    if (removed_cap < order.size() || !d_removed.p) {
+        if (d_removed.p) ODB_TRY(fold_removed(ctx, st, true));
+        uint32_t ncap = 1024;
+        while (ncap < 2 * order.size()) ncap *= 2;
+        d_removed.release();
+        ODB_TRY(d_removed.ensure((size_t)ncap + 1, st, false));
+        ODB_CUDA(cudaMemsetAsync(d_removed.p, 0, sizeof(uint32_t), st));
+        ODB_TRY(h_removed.ensure(ncap));
+        ODB_TRY(h_removed_count.ensure(1));
+        if (!ev_removed) ODB_CUDA(cudaEventCreateWithFlags(&ev_removed, cudaEventDisableTiming));
+        removed_cap = ncap;
+        removed_consumed = 0;
+        count_in_flight = false;
+    }
     return ODB_OK;
 }
 
-void SourceSet::process_removed(odb_ctx* ctx) {
-    if (!removed_pending) return;
-    removed_pending = false;
-    uint32_t count = h_removed.p[0];
-    if (count == 0) return;
-    if (count > (uint32_t)removed_order_len) count = (uint32_t)removed_order_len;
-    if (count + 1 > ODB_REMOVED_CAP) {  // rare: more removals than the eagerly copied header holds
-        cudaMemcpyAsync(h_removed.p, d_removed.p, ((size_t)count + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
+int SourceSet::post_callback(odb_ctx* ctx, cudaStream_t st) {
+    (void)ctx;
+    if (count_in_flight || !d_removed.p) return ODB_OK;  // the previous read-back has not been looked at yet
+    ODB_CUDA(cudaMemcpyAsync(h_removed_count.p, d_removed.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ODB_CUDA(cudaEventRecord(ev_removed, st));
+    count_in_flight = true;
+    return ODB_OK;
+}
+
+int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait) {
+    if (!d_removed.p) return ODB_OK;
+    if (!count_in_flight) {
+        if (!wait) return ODB_OK;
+        ODB_TRY(post_callback(ctx, st));
     }
+    if (wait) ODB_CUDA(cudaEventSynchronize(ev_removed));
+    else {
+        cudaError_t q = cudaEventQuery(ev_removed);
+        if (q == cudaErrorNotReady) return ODB_OK;
+        ODB_CUDA(q);
+    }
+    count_in_flight = false;
+    const uint32_t count = h_removed_count.p[0];
+    uint32_t n_new = count - removed_consumed;
+    if (n_new == 0) return ODB_OK;
+    if (n_new > removed_cap) return odb_fail(ODB_E_INVALID, "internal: removal ring overflow (%u reports)", n_new);
+    // fetch the report entries (only happens on callbacks where sources actually finished)
+    const uint32_t mask = removed_cap - 1, first = removed_consumed & mask;
+    const uint32_t span1 = n_new < removed_cap - first ? n_new : removed_cap - first;
+    ODB_CUDA(cudaMemcpyAsync(h_removed.p, d_removed.p + 1 + first, span1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (n_new > span1)
+        ODB_CUDA(cudaMemcpyAsync(h_removed.p + span1, d_removed.p + 1, (n_new - span1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ODB_CUDA(cudaStreamSynchronize(st));
+    removed_consumed = count;
     // The reference walks i from len-1 down to 0 and swap_removes as it goes (spatial.rs:204,259;
-    // mixer.rs:100,104; set.rs:183-188): replaying the indices in descending order gives the same Vec.
-    std::vector<uint32_t> idx(h_removed.p + 1, h_removed.p + 1 + count);
-    std::sort(idx.begin(), idx.end(), [](uint32_t a, uint32_t b) { return a > b; });
-    for (uint32_t i : idx) {
-        if (i >= order.size()) continue;
-        uint32_t slot = order[i];
-        order[i] = order.back();
+    // mixer.rs:100,104; set.rs:183-188): replaying the positions in descending order gives the same Vec.
+    std::vector<int> pos;
+    pos.reserve(n_new);
+    for (uint32_t i = 0; i < n_new; i++) {
+        uint32_t slot = h_removed.p[i];
+        if (slot < pos_of_slot.size() && pos_of_slot[slot] >= 0) pos.push_back(pos_of_slot[slot]);
+    }
+    std::sort(pos.begin(), pos.end(), [](int a, int b) { return a > b; });
+    for (int i : pos) {
+        uint32_t slot = order[(size_t)i];
+        uint32_t moved = order.back();
+        order[(size_t)i] = moved;
         order.pop_back();
+        pos_of_slot[moved] = i;
+        pos_of_slot[slot] = -1;
         SlotHost& sh = slots[slot];
         sh.stopped = true;
         sh.in_use = false;
@@ -293,6 +347,7 @@ void SourceSet::process_removed(odb_ctx* ctx) {
         free_slots.push_back(slot);
     }
     order_dirty = true;
+    return ODB_OK;
 }
 
 void SourceSet::release_all(odb_ctx* ctx) {
@@ -302,5 +357,8 @@ void SourceSet::release_all(odb_ctx* ctx) {
     d_src.release(); d_order.release(); d_stage_src.release(); d_stage_slot.release();
     d_motions.release(); d_params.release(); d_removed.release();
     h_stage_src.release(); h_stage_slot.release(); h_motions.release(); h_params.release();
-    h_order.release(); h_removed.release();
+    h_order.release(); h_removed.release(); h_removed_count.release();
+    if (ev_removed) cudaEventDestroy(ev_removed);
+    ev_removed = nullptr;
+    removed_cap = 0;
 }

@@ -93,6 +93,7 @@ struct odb_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     std::mutex mu;
     std::unordered_map<uint64_t, FramesRec> frames;
     uint64_t next_frames_id = 1;
@@ -138,15 +139,20 @@ struct SourceSet {
     DevBuf<uint32_t> d_stage_slot;
     DevBuf<OdbMotionMsg> d_motions;
     DevBuf<OdbParamMsg> d_params;
-    DevBuf<uint32_t> d_removed;
+    DevBuf<uint32_t> d_removed;         // [0] = monotonic count of removals the walk kernels reported,
+                                        // [1 + (k & (removed_cap-1))] = slot of the k-th report
     PinBuf<OdbSource> h_stage_src;
     PinBuf<uint32_t> h_stage_slot;
     PinBuf<OdbMotionMsg> h_motions;
     PinBuf<OdbParamMsg> h_params;
     PinBuf<uint32_t> h_order;
-    PinBuf<uint32_t> h_removed;
-    bool removed_pending = false;       // a removed list was copied back but not yet processed
-    int removed_order_len = 0;
+    PinBuf<uint32_t> h_removed;         // report entries, fetched only when the count moved
+    PinBuf<uint32_t> h_removed_count;   // landing slot of the asynchronous count read-back
+    uint32_t removed_cap = 0;           // ring capacity: power of two >= live sources
+    uint32_t removed_consumed = 0;      // reports already folded into `order`
+    cudaEvent_t ev_removed = nullptr;   // recorded behind the count read-back
+    bool count_in_flight = false;
+    std::vector<int> pos_of_slot;       // position of a slot in `order`, -1 if not a member
 
     uint32_t alloc_slot();
     odb_source handle_of(uint32_t slot, uint32_t tag) const;
@@ -157,8 +163,10 @@ struct SourceSet {
     void queue_param(uint32_t slot, uint32_t what, float value);
     // audio side: push queued control messages to the device; returns kernels launched
     int apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches);
-    // audio side: after the stream has been synchronised, swap_remove what the kernels reported
-    void process_removed(odb_ctx* ctx);
+    // audio side, after a callback's kernels are queued: start the asynchronous read-back of the report count
+    int post_callback(odb_ctx* ctx, cudaStream_t st);
+    // audio side: fold the removals the kernels reported into `order` (set.rs:183-188 swap_remove). With
+    // wait = false only reports whose read-back has already completed are folded (no host-device sync).
+    int fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait);
     void release_all(odb_ctx* ctx);
 };
-#define ODB_REMOVED_CAP 4096

@@ -7,6 +7,8 @@
 // Largest per-frame source advance (samples per output frame) the fast mix kernel stages in
 // shared memory; sources outside (0, ODB_FAST_DS_MAX] take the general kernel.
 #define ODB_FAST_DS_MAX 1.40f
+// Floats of PCM the staged kernel keeps per source and 1024-frame tile (1024 * 1.40 + ear skew + slack).
+#define ODB_FAST_PCM_CAP 1536
 
 struct OdbMotionMsg {  // Spatial::set_motion payload (spatial.rs:137-149)
     uint32_t slot;
@@ -28,9 +30,12 @@ void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const u
 void odb_launch_scatter_motion(OdbSource* src, const OdbMotionMsg* msgs, int n, cudaStream_t st);
 void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, cudaStream_t st);
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
-                          const OdbCallback& cb, cudaStream_t st);
+                          uint32_t* counters, const OdbCallback& cb, cudaStream_t st);
 int odb_mix_general_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
-                                   int only_flagged, cudaStream_t st);
-void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, float* out, int n_frames, int n_tiles,
-                       int epilogue, cudaStream_t st);
+                                   int only_flagged, const uint32_t* counters, cudaStream_t st);
+int odb_mix_fast_ctas(int n_sources, int sm_count);
+cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int strict,
+                                cudaStream_t st);
+void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const uint32_t* counters, int b_is_general,
+                       float* out, int n_frames, int n_tiles, int epilogue, cudaStream_t st);

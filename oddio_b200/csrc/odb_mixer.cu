@@ -91,3 +91,4 @@ int odb_mixer_owner_set(void* owner, odb_source src, odb_ctx** ctx, std::mutex**
 }
 int odb_mixer_last_launches(void* owner, uint32_t* out) { *out = ((odb_mixer*)owner)->last_launches; return ODB_OK; }
 int odb_mixer_set_variant(void* owner, int variant) { ((odb_mixer*)owner)->variant = variant; return ODB_OK; }
+int odb_mixer_job_counters(void* owner, uint32_t out[4]) { (void)owner; for (int i = 0; i < 4; i++) out[i] = 0; return ODB_OK; }

@@ -23,7 +23,10 @@ struct odb_scene {
     DevBuf<OdbJob> d_jobs;
     DevBuf<float> d_partials;
     DevBuf<float> d_partials_fast;
+    DevBuf<uint32_t> d_counters;
     DevBuf<float> d_out;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     PinBuf<float> h_out;
 };
 
@@ -46,8 +49,10 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     cudaStreamSynchronize(scene->ctx->stream);
     scene->seek.release_all(scene->ctx);
     scene->buffered.release_all(scene->ctx);
-    scene->d_jobs.release(); scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_out.release();
+    scene->d_jobs.release(); scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_counters.release();
+    scene->d_out.release();
     scene->h_out.release();
+    if (scene->ev0) { cudaEventDestroy(scene->ev0); cudaEventDestroy(scene->ev1); }
     scene->kind = 0;
     delete scene;
     return ODB_OK;
@@ -150,6 +155,21 @@ extern "C" int odb_spatial_set_motion(odb_scene* scene, odb_source src, const fl
     set->queue_motion(slot, position, velocity, discontinuity);
     return ODB_OK;
 }
+extern "C" int odb_spatial_set_motion_many(odb_scene* scene, uint32_t n, const odb_source* srcs, const float* positions,
+                                           const float* velocities, const uint8_t* discontinuity) {
+    ODB_TRY(scene_check(scene));
+    if (n && (!srcs || !positions || !velocities)) return odb_fail(ODB_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(scene->mu);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t tag, slot; bool stale;
+        SourceSet* set = set_of(scene, srcs[i], &tag);
+        if (!set) return odb_fail(ODB_E_INVALID, "srcs[%u] is not a spatial source handle", i);
+        ODB_TRY(set->lookup(srcs[i], tag, &slot, &stale));
+        if (stale) continue;
+        set->queue_motion(slot, positions + 3 * (size_t)i, velocities + 3 * (size_t)i, discontinuity ? discontinuity[i] : 0);
+    }
+    return ODB_OK;
+}
 // Spatial::is_finished, spatial.rs:154-156
 extern "C" int odb_spatial_is_finished(odb_scene* scene, odb_source src, int* out) {
     ODB_TRY(scene_check(scene));
@@ -182,11 +202,8 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     OdbCallback cb;
     {
         std::lock_guard<std::mutex> lk(scene->mu);
-        // a removed list left over from a *_sample_device call must be folded in before the order is used
-        if (scene->seek.removed_pending) {
-            ODB_CUDA(cudaStreamSynchronize(st));
-            scene->seek.process_removed(ctx);
-        }
+        // removals reported by earlier callbacks whose read-back has landed (never waits for the device)
+        ODB_TRY(scene->seek.fold_removed(ctx, st, false));
         ODB_TRY(scene->seek.apply(ctx, st, &launches));                     // set.update(), spatial.rs:437
         cb.prev_rot = scene->rot_received;                                 // spatial.rs:382-386
         if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
@@ -197,31 +214,47 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     cb.elapsed = interval * (float)n_frames;                               // spatial.rs:394
     cb.n_tiles = (int)((n_frames + ODB_TILE_FRAMES - 1) / ODB_TILE_FRAMES);
     cb.n_sources = (int)scene->seek.order.size();
+    cb.force_general = scene->variant == 1;
     const int ns = cb.n_sources, nt = cb.n_tiles;
 
-    ODB_CUDA(cudaMemsetAsync(scene->seek.d_removed.p, 0, sizeof(uint32_t), st));
+    ODB_TRY(scene->d_counters.ensure(ODB_CNT_WORDS, st, false));
+    ODB_CUDA(cudaMemsetAsync(scene->d_counters.p, 0, ODB_CNT_WORDS * sizeof(uint32_t), st));
     if (ns > 0) {
         ODB_TRY(scene->d_jobs.ensure((size_t)ns * (nt > 0 ? nt : 1), st, false));
-        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs.p, scene->seek.d_removed.p, ns, cb, st);
+        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs.p, scene->seek.d_removed.p,
+                             (int)scene->seek.removed_cap, scene->d_counters.p, cb, st);
         launches++;
     }
     if (nt > 0) {
-        int n_parts = 0;
+        int n_fast = 0, n_gen = 0;
         if (ns > 0) {
-            n_parts = odb_mix_general_ctas(ns, ctx->sm_count);
-            ODB_TRY(scene->d_partials.ensure((size_t)nt * n_parts * 2 * ODB_TILE_FRAMES, st, false));
-            cudaError_t e = odb_launch_mix_general(scene->d_jobs.p, ns, nt, scene->d_partials.p, n_parts, /*only_flagged=*/0, st);
+            const bool use_fast = scene->variant != 1;
+            if (use_fast) {  // staged kernel for everything the walk kernel did not flag
+                n_fast = odb_mix_fast_ctas(ns, ctx->sm_count);
+                ODB_TRY(scene->d_partials_fast.ensure((size_t)nt * n_fast * 2 * ODB_TILE_FRAMES, st, false));
+                if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev0, st));
+                cudaError_t e = odb_launch_mix_fast(scene->d_jobs.p, ns, nt, scene->d_partials_fast.p, n_fast,
+                                                    /*strict=*/scene->variant != 2, st);
+                if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_fast launch failed: %s", cudaGetErrorString(e));
+                if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev1, st));
+                launches++;
+            }
+            // literal kernel for the flagged rest (exits at once when the walk kernel flagged nothing)
+            n_gen = odb_mix_general_ctas(use_fast ? (ns < 2048 ? ns : 2048) : ns, ctx->sm_count);
+            ODB_TRY(scene->d_partials.ensure((size_t)nt * n_gen * 2 * ODB_TILE_FRAMES, st, false));
+            cudaError_t e = odb_launch_mix_general(scene->d_jobs.p, ns, nt, scene->d_partials.p, n_gen,
+                                                   /*only_flagged=*/use_fast ? 1 : 0, scene->d_counters.p, st);
             if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_general launch failed: %s", cudaGetErrorString(e));
             launches++;
         }
-        odb_launch_reduce(scene->d_partials.p, n_parts, nullptr, 0, dev_out, (int)n_frames, nt, scene->epilogue, st);
+        odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_counters.p,
+                          /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, scene->epilogue, st);
         launches++;
     }
-    // bring back what walk_set removed (header eagerly, the rest on demand in process_removed)
-    size_t hdr = std::min<size_t>((size_t)ns + 1, ODB_REMOVED_CAP);
-    ODB_CUDA(cudaMemcpyAsync(scene->seek.h_removed.p, scene->seek.d_removed.p, hdr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    scene->seek.removed_pending = true;
-    scene->seek.removed_order_len = ns;
+    {   // start the read-back of what walk_set removed; folded in by a later call without waiting
+        std::lock_guard<std::mutex> lk(scene->mu);
+        ODB_TRY(scene->seek.post_callback(ctx, st));
+    }
     scene->last_launches = launches;
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
@@ -240,8 +273,7 @@ extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, ui
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
     std::lock_guard<std::mutex> lk(scene->mu);
-    scene->seek.process_removed(ctx);
-    return ODB_OK;
+    return scene->seek.fold_removed(ctx, ctx->stream, true);  // like the reference, removals are visible when sample returns
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {
@@ -347,6 +379,42 @@ extern "C" int odb_last_launch_count(void* owner, uint32_t* out) {
     if (kind == ODB_KIND_SCENE) { *out = ((odb_scene*)owner)->last_launches; return ODB_OK; }
     if (kind == ODB_KIND_MIXER) return odb_mixer_last_launches(owner, out);
     return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
+}
+extern "C" int odb_set_profiling(void* owner, int enabled) {
+    if (!owner) return odb_fail(ODB_E_INVALID, "NULL argument");
+    if (*(uint32_t*)owner != ODB_KIND_SCENE) return odb_fail(ODB_E_UNSUPPORTED, "profiling events: scene only");
+    odb_scene* sc = (odb_scene*)owner;
+    ODB_CUDA(cudaSetDevice(sc->ctx->device));
+    if (enabled && !sc->ev0) {
+        ODB_CUDA(cudaEventCreate(&sc->ev0));
+        ODB_CUDA(cudaEventCreate(&sc->ev1));
+    }
+    sc->profiling = enabled != 0;
+    return ODB_OK;
+}
+extern "C" int odb_last_mix_kernel_ms(void* owner, float* out_ms) {
+    if (!owner || !out_ms) return odb_fail(ODB_E_INVALID, "NULL argument");
+    if (*(uint32_t*)owner != ODB_KIND_SCENE) return odb_fail(ODB_E_UNSUPPORTED, "profiling events: scene only");
+    odb_scene* sc = (odb_scene*)owner;
+    if (!sc->profiling || !sc->ev0) return odb_fail(ODB_E_INVALID, "profiling is not enabled");
+    ODB_CUDA(cudaSetDevice(sc->ctx->device));
+    ODB_CUDA(cudaEventSynchronize(sc->ev1));
+    ODB_CUDA(cudaEventElapsedTime(out_ms, sc->ev0, sc->ev1));
+    return ODB_OK;
+}
+int odb_mixer_job_counters(void* owner, uint32_t out[4]);
+extern "C" int odb_last_job_counters(void* owner, uint32_t out[4]) {
+    if (!owner || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    uint32_t kind = *(uint32_t*)owner;
+    if (kind == ODB_KIND_MIXER) return odb_mixer_job_counters(owner, out);
+    if (kind != ODB_KIND_SCENE) return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
+    odb_scene* sc = (odb_scene*)owner;
+    for (int i = 0; i < 4; i++) out[i] = 0;
+    if (!sc->d_counters.p) return ODB_OK;
+    ODB_CUDA(cudaSetDevice(sc->ctx->device));
+    ODB_CUDA(cudaMemcpyAsync(out, sc->d_counters.p, ODB_CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    ODB_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    return ODB_OK;
 }
 extern "C" int odb_set_kernel_variant(void* owner, int variant) {
     if (!owner) return odb_fail(ODB_E_INVALID, "NULL argument");

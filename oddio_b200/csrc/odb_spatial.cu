@@ -51,7 +51,7 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 // Writes one OdbJob per (tile, source) and the source's state for the next callback.
 __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                    OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
-                                                   int removed_cap, OdbCallback cb) {
+                                                   int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cb.n_sources) return;
     OdbSource* sp = src + order[idx];
@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     sp->flags = flags;
     const int nt = cb.n_tiles, ns = cb.n_sources;
     if (flags & ODB_SF_STOPPED) {
-        if (!was_stopped) {  // set.remove(i): report the index so the host can swap_remove it
+        if (!was_stopped) {  // set.remove(i): report the slot so the host can swap_remove it from its Vec
             uint32_t k = atomicAdd(removed, 1u);
-            if ((int)k < removed_cap) removed[1 + k] = (uint32_t)idx;
+            removed[1 + (k & (uint32_t)(removed_cap - 1))] = order[idx];
         }
         for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
         return;
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     const float ratef = (float)rate;  // `self.data.rate as f32` frames.rs:178
     const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
     uint32_t jflags[4] = {0, 0, 0, 0};  // per tile (n_tiles <= 4 enforced by the host)
+    long long wlo[4], whi[4];           // per tile: PCM index range both ears can touch
+    for (int tl = 0; tl < 4; tl++) { wlo[tl] = (1ll << 40); whi[tl] = -(1ll << 40); }
     long long sample_t = s.sample_t;
+    bool fast_e[2];
     for (int e = 0; e < 2; e++) {
         EarSt ps = ear_state(prev_position, e, s.radius);
         EarSt nx = ear_state(next_position, e, s.radius);
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
         float d_gain = (nx.gain - ps.gain) / nf;                      // :453
         float ds = dt * ratef;                                        // frames.rs:178
         bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
+        fast_e[e] = fast;
         bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
         for (int cg = 0; cg < n_chunks; cg++) {
             int tl = cg / ODB_TILE_CHUNKS, c = cg % ODB_TILE_CHUNKS;
@@ -128,9 +132,15 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
             long long base = (long long)s0;                           // frames.rs:179
             float off0 = (float)(s0 - (double)base);                  // frames.rs:183 / :189
             if (off0 < 0.0f) general = true;                          // negative-fract quirk
+            if (base > (1ll << 29) || base < -(1ll << 29)) general = true;
             OdbJob* j = jobs + (size_t)tl * ns + idx;
             j->base[e][c] = sat_i32(base);
             j->off0[e][c] = off0;
+            // PCM indices this chain can read: [base, base + trunc(offset_{m-1}) + 1]; the f32 chain stays
+            // within 1e-2 of off0 + (m-1)*ds for m <= 256, so +3 is a safe upper bound.
+            long long last = fast ? base + m : base + (long long)((double)off0 + (double)(m - 1) * (double)ds) + 3;
+            wlo[tl] = base < wlo[tl] ? base : wlo[tl];
+            whi[tl] = last > whi[tl] ? last : whi[tl];
             t = t + (double)dt * (double)m;                           // frames.rs:198
             sample_t = (long long)(t * rate);                         // frames.rs:199-200
         }
@@ -144,14 +154,28 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     t = t + (double)elapsed;                                          // :468
     sp->t = t;
     sp->sample_t = sample_t;
+    uint32_t n_general = 0, n_fast = 0;
     for (int tl = 0; tl < nt; tl++) {
         OdbJob* j = jobs + (size_t)tl * ns + idx;
         j->pcm = s.pcm; j->len = s.len;
         j->fixed_gain = s.fixed_gain;
         j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
-        j->frame0 = (float)(tl * ODB_TILE_FRAMES);
-        j->flags = jflags[tl] | ((flags & ODB_SF_FIXED_GAIN) ? (ODB_JF_FIXED_GAIN | ODB_JF_GENERAL) : 0u);
+        // window for the staged (fast) mix kernel: 16-byte aligned start, whole float4s, inside the
+        // zero-padded Frames block; anything else goes to the general kernel
+        long long ws = wlo[tl] & ~3ll;
+        long long wl = ((whi[tl] - ws + 1) + 3) & ~3ll;
+        uint32_t f = jflags[tl];
+        if (fast_e[0] != fast_e[1]) f |= ODB_JF_GENERAL;
+        if (wl > ODB_FAST_PCM_CAP || ws < -(long long)ODB_PCM_PAD || ws + wl > (long long)s.len + ODB_PCM_PAD) f |= ODB_JF_GENERAL;
+        if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
+        if (cb.force_general) f |= ODB_JF_GENERAL;
+        j->w_start = (int)ws;
+        j->w_len = (f & ODB_JF_GENERAL) ? 0 : (int)wl;
+        j->flags = f;
+        if (f & ODB_JF_GENERAL) n_general++; else n_fast++;
     }
+    if (n_general) atomicAdd(counters + ODB_CNT_GENERAL, n_general);
+    if (n_fast) atomicAdd(counters + ODB_CNT_FAST, n_fast);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -164,8 +188,11 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
 // bit-identical to the reference's.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __restrict__ jobs, int n_sources,
-                                                            float* __restrict__ partials, int only_flagged) {
+                                                            float* __restrict__ partials, int only_flagged,
+                                                            const uint32_t* __restrict__ counters) {
     extern __shared__ float smem[];
+    // nothing flagged for this kernel: leave at once; k_reduce_tiles reads the same counter and skips our tiles
+    if (only_flagged && counters[ODB_CNT_GENERAL] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = smem + warp * (2 * ODB_TILE_FRAMES);
     const int tl = blockIdx.y;
@@ -189,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
             const bool fast = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
             const bool has_fg = (jf & ODB_JF_FIXED_GAIN) != 0;
             float offset = job->off0[e][c];
-            float fi = job->frame0 + (float)(c * ODB_SPATIAL_CHUNK);  // exact: small integers
+            float fi = (float)(tl * ODB_TILE_FRAMES + c * ODB_SPATIAL_CHUNK);  // exact: small integers
             for (int k = 0; k < ODB_SPATIAL_CHUNK; k++) {
                 float contrib = 0.0f;
                 if (k < m) {
@@ -235,23 +262,33 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// Second-stage reduce: sums the per-CTA partial tiles of up to two partial sets in a fixed
-// order (deterministic), applies the optional Tanh / Reinhard wrapper (tanh.rs:24-28,
-// reinhard.rs:30-34) and writes the interleaved stereo output.
-__global__ void k_reduce_tiles(const float* __restrict__ pa, int na, const float* __restrict__ pb, int nb,
-                               float* __restrict__ out, int n_frames, int epilogue) {
+// Second-stage reduce: sums the per-CTA partial tiles of up to two partial sets (a: staged kernel,
+// b: general kernel) in a fixed order (deterministic), applies the optional Tanh / Reinhard wrapper
+// (tanh.rs:24-28, reinhard.rs:30-34) and writes the interleaved stereo output. Each block owns 32
+// consecutive output floats; its 8 warps take every 8th partial tile, then fold through shared memory.
+#define RED_GROUPS 8
+__global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* __restrict__ pa, int na,
+                                                                 const float* __restrict__ pb, int nb,
+                                                                 const uint32_t* __restrict__ counters, int b_is_general,
+                                                                 float* __restrict__ out, int n_frames, int epilogue) {
+    __shared__ float fold[RED_GROUPS][32];
     const int tl = blockIdx.y;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= 2 * ODB_TILE_FRAMES) return;
-    const int frame = tl * ODB_TILE_FRAMES + (f >> 1);
-    if (frame >= n_frames) return;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + lane;  // float index inside the tile
+    if (b_is_general && counters[ODB_CNT_GENERAL] == 0) nb = 0;
     float sum = 0.0f;
     const float* p = pa + (size_t)tl * na * (2 * ODB_TILE_FRAMES) + f;
-    for (int i = 0; i < na; i++) sum = sum + p[(size_t)i * (2 * ODB_TILE_FRAMES)];
-    if (nb > 0) {
-        const float* q = pb + (size_t)tl * nb * (2 * ODB_TILE_FRAMES) + f;
-        for (int i = 0; i < nb; i++) sum = sum + q[(size_t)i * (2 * ODB_TILE_FRAMES)];
-    }
+    for (int i = grp; i < na; i += RED_GROUPS) sum = sum + p[(size_t)i * (2 * ODB_TILE_FRAMES)];
+    const float* q = pb + (size_t)tl * nb * (2 * ODB_TILE_FRAMES) + f;
+    for (int i = grp; i < nb; i += RED_GROUPS) sum = sum + q[(size_t)i * (2 * ODB_TILE_FRAMES)];
+    fold[grp][lane] = sum;
+    __syncthreads();
+    if (grp != 0) return;
+    sum = 0.0f;
+#pragma unroll
+    for (int g = 0; g < RED_GROUPS; g++) sum = sum + fold[g][lane];
+    const int frame = tl * ODB_TILE_FRAMES + (f >> 1);
+    if (frame >= n_frames) return;
     if (epilogue == 1) sum = tanhf(sum);
     else if (epilogue == 2) sum = sum / (1.0f + fabsf(sum));
     out[(size_t)frame * 2 + (f & 1)] = sum;
@@ -277,9 +314,9 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
     k_scatter_params<<<(n + 127) / 128, 128, 0, st>>>(src, msgs, n);
 }
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
-                          const OdbCallback& cb, cudaStream_t st) {
+                          uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
-    k_walk_seek<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, cb);
+    k_walk_seek<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
 }
 
 static const int GEN_WARPS = 8;
@@ -289,7 +326,7 @@ int odb_mix_general_ctas(int n_sources, int sm_count) {
     return want < 1 ? 1 : (want > cap ? cap : want);
 }
 cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
-                                   int only_flagged, cudaStream_t st) {
+                                   int only_flagged, const uint32_t* counters, cudaStream_t st) {
     static bool attr_set = false;
     const int smem = GEN_WARPS * 2 * ODB_TILE_FRAMES * (int)sizeof(float);
     if (!attr_set) {
@@ -298,12 +335,12 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
         attr_set = true;
     }
     dim3 grid(n_ctas, n_tiles);
-    k_mix_general<GEN_WARPS><<<grid, GEN_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged);
+    k_mix_general<GEN_WARPS><<<grid, GEN_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged, counters);
     return cudaGetLastError();
 }
-void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, float* out, int n_frames, int n_tiles,
-                       int epilogue, cudaStream_t st) {
+void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const uint32_t* counters, int b_is_general,
+                       float* out, int n_frames, int n_tiles, int epilogue, cudaStream_t st) {
     if (n_frames <= 0) return;
-    dim3 grid((2 * ODB_TILE_FRAMES + 255) / 256, n_tiles);
-    k_reduce_tiles<<<grid, 256, 0, st>>>(pa, na, pb, nb, out, n_frames, epilogue);
+    dim3 grid(2 * ODB_TILE_FRAMES / 32, n_tiles);
+    k_reduce_tiles<<<grid, 32 * RED_GROUPS, 0, st>>>(pa, na, pb, nb, counters, b_is_general, out, n_frames, epilogue);
 }

@@ -51,27 +51,46 @@ struct __attribute__((aligned(16))) OdbSource {
     uint32_t ring_rate;    // SpatialSignalBuffered::rate
 };
 
-// What one (source, 1024-frame tile) pass of the spatial mix kernel needs; written by the walk
-// kernel each callback. 128 bytes.
+// What one (source, 1024-frame tile) pass of the spatial mix kernels needs; written by the walk
+// kernel each callback. Exactly one 128-byte line: a warp reads it as 32 words, lane l = word l.
 struct __attribute__((aligned(16))) OdbJob {
-    const float* pcm;
-    int len;
-    uint32_t flags;                 // ODB_JF_*
-    float ds[2];                    // per ear: dt * rate as f32 (frames.rs:178)
-    float pg[2];                    // prev_state.gain (spatial.rs:459)
-    float dg[2];                    // d_gain (spatial.rs:453)
-    float fixed_gain;
-    int n_frames;                   // frames of this tile (<= ODB_TILE_FRAMES)
-    int base[2][ODB_TILE_CHUNKS];   // per ear, per 256-chunk: `base` (frames.rs:179), saturated to int32
-    float off0[2][ODB_TILE_CHUNKS]; // initial `offset` / constant `fract` (frames.rs:183,189)
-    float frame0;                   // f32 index of the tile's first frame (i as f32, spatial.rs:459)
-    uint32_t pad;
+    const float* pcm;               // words 0-1
+    int len;                        // word 2
+    uint32_t flags;                 // word 3: ODB_JF_*
+    float ds[2];                    // words 4-5: per ear dt * rate as f32 (frames.rs:178)
+    float pg[2];                    // words 6-7: prev_state.gain (spatial.rs:459)
+    float dg[2];                    // words 8-9: d_gain (spatial.rs:453)
+    float fixed_gain;               // word 10
+    int n_frames;                   // word 11: frames of this tile (<= ODB_TILE_FRAMES)
+    int base[2][ODB_TILE_CHUNKS];   // words 12-19: per ear, per 256-chunk `base` (frames.rs:179), saturated to int32
+    float off0[2][ODB_TILE_CHUNKS]; // words 20-27: initial `offset` / constant `fract` (frames.rs:183,189)
+    int w_start;                    // word 28: first PCM index the tile can touch, rounded down to a multiple of 4
+    int w_len;                      // word 29: floats from w_start that cover every index of both ears (multiple of 4)
+    uint32_t pad[2];
 };
+#define ODB_JW_PCM_LO 0
+#define ODB_JW_PCM_HI 1
+#define ODB_JW_LEN 2
+#define ODB_JW_FLAGS 3
+#define ODB_JW_DS 4
+#define ODB_JW_PG 6
+#define ODB_JW_DG 8
+#define ODB_JW_FIXED_GAIN 10
+#define ODB_JW_N_FRAMES 11
+#define ODB_JW_BASE 12
+#define ODB_JW_OFF0 20
+#define ODB_JW_W_START 28
+#define ODB_JW_W_LEN 29
 #define ODB_JF_SKIP 0x1u        // source removed/stopped this callback: contributes nothing
 #define ODB_JF_FAST_L 0x2u      // |ds-1| <= EPSILON for the left ear (frames.rs:180)
 #define ODB_JF_FAST_R 0x4u
 #define ODB_JF_FIXED_GAIN 0x8u
 #define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
+
+// Device counters written by the walk kernels each callback (uint32 each).
+#define ODB_CNT_GENERAL 0       // jobs flagged ODB_JF_GENERAL
+#define ODB_CNT_FAST 1          // jobs the fast mix kernel takes
+#define ODB_CNT_WORDS 4
 
 struct OdbQuat { float x, y, z, s; };
 
@@ -83,6 +102,7 @@ struct OdbCallback {
     int n_frames;
     int n_tiles;
     int n_sources;           // entries of the active list
+    int force_general;       // kernel variant 1: every job takes the general (literal) kernel
 };
 
 static_assert(sizeof(OdbSource) % 16 == 0, "OdbSource is moved in 16-byte words");

@@ -3,6 +3,7 @@
 #include "oddio_oracle.hpp"
 
 #include <chrono>
+#include <thread>
 
 using namespace orc;
 
@@ -96,6 +97,30 @@ double orc_time_run(void* h, uint32_t rate, float* out, size_t n, int warmup, in
         if (dt < best) best = dt;
     }
     return best;
+}
+
+// Source-sharded CPU run: `n_sig` independent aggregators (each holding a shard of the sources) are run
+// on one thread each into private tiles which are then summed. NOT reference behaviour (the reference is
+// single-threaded per signal graph, signal.rs:19); it is the "all host threads" arm of bench.py.
+// Returns total wall seconds of `reps` rounds (after `warmup` untimed rounds); out = last summed tile.
+double orc_time_run_sharded(void** sigs, int n_sig, uint32_t rate, float* out, size_t n, int channels, int warmup, int reps) {
+    std::vector<std::vector<float>> tiles((size_t)n_sig, std::vector<float>(n * (size_t)channels, 0.0f));
+    auto round = [&]() {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_sig; i++)
+            th.emplace_back([&, i]() { run(*((Obj*)sigs[i])->signal, rate, tiles[(size_t)i].data(), n); });
+        for (auto& t : th) t.join();
+        for (size_t k = 0; k < n * (size_t)channels; k++) {
+            float acc = 0.0f;
+            for (int i = 0; i < n_sig; i++) acc = acc + tiles[(size_t)i][k];
+            out[k] = acc;
+        }
+    };
+    for (int i = 0; i < warmup; i++) round();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; i++) round();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 // ---- FramesSignal read-backs ---------------------------------------------------------------

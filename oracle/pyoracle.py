@@ -69,6 +69,7 @@ def lib():
         "orc_signal_is_finished": (i32, [vp]),
         "orc_signal_seek": (None, [vp, f32]),
         "orc_time_run": (f64, [vp, u32, fp, sz, i32, i32]),
+        "orc_time_run_sharded": (f64, [C.POINTER(vp), i32, u32, fp, sz, i32, i32, i32]),
         "orc_frames_signal_t": (f64, [vp]),
         "orc_frames_signal_sample_t": (C.c_long, [vp]),
         "orc_frames_signal_playback_position": (f64, [vp]),
@@ -184,6 +185,16 @@ def time_run(signal: Signal, sample_rate: int, n: int, warmup: int, reps: int) -
     """Best-of-`reps` wall seconds of one run() call, timed inside C++ (steady_clock)."""
     out = np.zeros((n, signal.channels), dtype=np.float32)
     return lib().orc_time_run(signal._h, int(sample_rate), _fptr(out), n, warmup, reps)
+
+
+def time_run_sharded(signals, sample_rate: int, n: int, warmup: int, reps: int):
+    """Runs `signals` (aggregators holding disjoint shards of the sources) on one thread each and sums
+    their tiles; returns (total wall seconds of `reps` rounds, last summed tile). Not reference behaviour."""
+    ch = signals[0].channels
+    out = np.zeros((n, ch), dtype=np.float32)
+    arr = (C.c_void_p * len(signals))(*[s._h for s in signals])
+    secs = lib().orc_time_run_sharded(arr, len(signals), int(sample_rate), _fptr(out), n, ch, warmup, reps)
+    return secs, out
 
 
 class FramesSignal(Signal):

@@ -19,3 +19,5 @@ def oracle():
 
     pyoracle.lib()
     return pyoracle
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
