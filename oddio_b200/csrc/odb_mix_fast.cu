@@ -58,6 +58,15 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (the scalar forms are
+// left alone), and also sees through fma(a, b, -0.0). The strict kernel therefore multiplies with an FFMA2
+// whose addend is a (-0.0, -0.0) pair that arrives as a kernel argument: RN(a*b + -0) == RN(a*b) for every
+// input including signed zeros, and the compiler cannot fold what it cannot see.
+__device__ __forceinline__ u64 mulx(u64 a, u64 b, u64 neg_zero2) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(neg_zero2));
+    return r;
+}
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -120,7 +129,7 @@ template <bool STRICT, bool FULL>
 __device__ __forceinline__ void consume_chunk_doppler(u64* __restrict__ acc, const int c, const int lane, const float fbase,
                                                       const uint32_t offs_sa, const uint32_t KL, const uint32_t KR,
                                                       const u64 d1, const u64 d2, const u64 d3, const u64 pgp,
-                                                      const u64 dgp, const int nfr) {
+                                                      const u64 dgp, const int nfr, const u64 nz) {
     const u64 magic = pk2(ODB_MAGIC, ODB_MAGIC);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -144,14 +153,14 @@ __device__ __forceinline__ void consume_chunk_doppler(u64* __restrict__ acc, con
         const u64 fi2 = pk2(fi, fi);
         u64 s, g;
         if (STRICT) {
-            s = add2(a, mul2(fr, d));
-            g = add2(pgp, mul2(fi2, dgp));                 // prev_state.gain + i as f32 * d_gain
+            s = add2(a, mulx(fr, d, nz));
+            g = add2(pgp, mulx(fi2, dgp, nz));             // prev_state.gain + i as f32 * d_gain
         } else {
             s = fma2(fr, d, a);
             g = fma2(fi2, dgp, pgp);
         }
         if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j + lane >= nfr) s = 0ull;  // frame beyond the tile: contributes +0
-        if (STRICT) acc[c * 8 + j] = add2(acc[c * 8 + j], mul2(s, g));        // o[ear] += s * gain (spatial.rs:460)
+        if (STRICT) acc[c * 8 + j] = add2(acc[c * 8 + j], mulx(s, g, nz));     // o[ear] += s * gain (spatial.rs:460)
         else acc[c * 8 + j] = fma2(s, g, acc[c * 8 + j]);
     }
 }
@@ -160,7 +169,7 @@ __device__ __forceinline__ void consume_chunk_doppler(u64* __restrict__ acc, con
 template <bool STRICT, bool FULL>
 __device__ __forceinline__ void consume_chunk_unit(u64* __restrict__ acc, const int c, const int lane, const float fbase,
                                                    const uint32_t AL, const uint32_t AR, const u64 fr, const u64 pgp,
-                                                   const u64 dgp, const int nfr) {
+                                                   const u64 dgp, const int nfr, const u64 nz) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j >= nfr) break;
@@ -172,21 +181,21 @@ __device__ __forceinline__ void consume_chunk_unit(u64* __restrict__ acc, const 
         const u64 fi2 = pk2(fi, fi);
         u64 s, g;
         if (STRICT) {
-            s = add2(a, mul2(fr, d));
-            g = add2(pgp, mul2(fi2, dgp));
+            s = add2(a, mulx(fr, d, nz));
+            g = add2(pgp, mulx(fi2, dgp, nz));
         } else {
             s = fma2(fr, d, a);
             g = fma2(fi2, dgp, pgp);
         }
         if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j + lane >= nfr) s = 0ull;
-        if (STRICT) acc[c * 8 + j] = add2(acc[c * 8 + j], mul2(s, g));
+        if (STRICT) acc[c * 8 + j] = add2(acc[c * 8 + j], mulx(s, g, nz));
         else acc[c * 8 + j] = fma2(s, g, acc[c * 8 + j]);
     }
 }
 
 template <bool STRICT>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 2) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
-                                                                  float* __restrict__ partials) {
+                                                                  float* __restrict__ partials, const u64 nz) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tl = blockIdx.y;
@@ -260,15 +269,15 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) k_mix_fast(const OdbJob* _
             if (!unit) {
                 const uint32_t KL = pcm_sa + (uint32_t)((baseL - w_start) * 4) - (ODB_MAGIC_BITS << 2);
                 const uint32_t KR = pcm_sa + (uint32_t)((baseR - w_start) * 4) - (ODB_MAGIC_BITS << 2);
-                if (full) consume_chunk_doppler<STRICT, true>(acc, c, lane, fbase, offs_sa, KL, KR, d1, d2, d3, pgp, dgp, nfr);
-                else consume_chunk_doppler<STRICT, false>(acc, c, lane, fbase, offs_sa, KL, KR, d1, d2, d3, pgp, dgp, nfr);
+                if (full) consume_chunk_doppler<STRICT, true>(acc, c, lane, fbase, offs_sa, KL, KR, d1, d2, d3, pgp, dgp, nfr, nz);
+                else consume_chunk_doppler<STRICT, false>(acc, c, lane, fbase, offs_sa, KL, KR, d1, d2, d3, pgp, dgp, nfr, nz);
             } else {
                 const uint32_t AL = pcm_sa + (uint32_t)((baseL - w_start + lane) * 4);
                 const uint32_t AR = pcm_sa + (uint32_t)((baseR - w_start + lane) * 4);
                 const u64 fr = pk2(__uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_OFF0 + c)),
                                    __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_OFF0 + ODB_TILE_CHUNKS + c)));
-                if (full) consume_chunk_unit<STRICT, true>(acc, c, lane, fbase, AL, AR, fr, pgp, dgp, nfr);
-                else consume_chunk_unit<STRICT, false>(acc, c, lane, fbase, AL, AR, fr, pgp, dgp, nfr);
+                if (full) consume_chunk_unit<STRICT, true>(acc, c, lane, fbase, AL, AR, fr, pgp, dgp, nfr, nz);
+                else consume_chunk_unit<STRICT, false>(acc, c, lane, fbase, AL, AR, fr, pgp, dgp, nfr, nz);
             }
         }
         __syncwarp();  // every lane is done with the PCM and cursor buffers before they are refilled
@@ -313,7 +322,7 @@ cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, 
         attr_set = true;
     }
     dim3 grid(n_ctas, n_tiles);
-    if (strict) k_mix_fast<true><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials);
-    else k_mix_fast<false><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials);
+    if (strict) k_mix_fast<true><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
+    else k_mix_fast<false><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
     return cudaGetLastError();
 }

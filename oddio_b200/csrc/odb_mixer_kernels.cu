@@ -1,0 +1,289 @@
+// Mixer kernels: walk (per-source set-up of Mixer::sample, mixer.rs:92-119, over the closed chain
+// Gain(FixedGain(Speed(FramesSignal)))), the streaming kernel for FramesSignal's ds ~= 1 path
+// (frames.rs:180-187) and the literal kernel for everything else (resampling chains, gain ramps).
+// A mixer tile is one staging chunk of the reference: 1024 frames (mixer.rs:77, :110-111).
+#include <cuda_runtime.h>
+
+#include "odb_kernels.h"
+#include "odb_math.cuh"
+
+namespace odbk {
+
+// ------------------------------------------------------------------------------------------
+// One thread per source. mixer.rs:100-107 (stop / finished -> remove), then per <=1024-frame chunk
+// the O(1) part of the chain: Speed (speed.rs:32-35), FramesSignal's cursor set-up (frames.rs:177-183)
+// and f64 advance (:198-200), Gain's Smoothed state machine (gain.rs:104-121, smooth.rs:47-72).
+__global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
+                                                    OdbMixJob* __restrict__ jobs, uint32_t* __restrict__ removed,
+                                                    int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cb.n_sources) return;
+    OdbSource* sp = src + order[idx];
+    OdbSource s = *sp;
+    const int ns = cb.n_sources, nt = cb.n_tiles;
+    uint32_t flags = s.flags;
+    const bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
+    double t = s.t;
+    const double rate = s.rate;
+    // mixer.rs:102: `signal.stop.load() || signal.inner.is_finished()`; is_finished forwards through
+    // Gain / FixedGain / Speed (gain.rs:39-41,:124-126, speed.rs:37-39) to frames.rs:204-206
+    if (was_stopped || (flags & ODB_SF_STOP_REQ) || t >= (double)(s.len - 1) / rate) {
+        if (!was_stopped) {
+            uint32_t k = atomicAdd(removed, 1u);
+            removed[1 + (k & (uint32_t)(removed_cap - 1))] = order[idx];
+            sp->flags = flags | ODB_SF_STOPPED;
+        }
+        for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
+        return;
+    }
+    const float ratef = (float)rate;
+    const float iv = (flags & ODB_SF_SPEED) ? cb.interval * s.speed : cb.interval;  // speed.rs:34
+    const float ds = iv * ratef;                                                    // frames.rs:178
+    const bool unit = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;                          // frames.rs:180
+    const int ch = s.channels;
+    float gprev = s.gain_prev, gnext = s.gain_next, gprog = s.gain_progress;
+    const float gstep = cb.interval / ODB_GAIN_SMOOTHING;                           // gain.rs:120
+    long long sample_t = s.sample_t;
+    uint32_t n_general = 0, n_fast = 0;
+    for (int tl = 0; tl < nt; tl++) {
+        const int n = min(ODB_MIXER_CHUNK, cb.n_frames - tl * ODB_MIXER_CHUNK);
+        OdbMixJob j;
+        j.pcm = s.pcm; j.len = s.len; j.n_frames = n; j.ds = ds;
+        uint32_t jf = unit ? ODB_JF_FAST_L : 0u;
+        const double s0 = t * rate;                                                 // frames.rs:177
+        const long long base = (long long)s0;                                       // frames.rs:179
+        const float off0 = (float)(s0 - (double)base);                              // frames.rs:183 / :189
+        j.base = sat_i32(base); j.off0 = off0;
+        t = t + (double)iv * (double)n;                                             // frames.rs:198
+        sample_t = (long long)(t * rate);                                           // frames.rs:199-200
+        j.fixed_gain = s.fixed_gain;                                                // 1.0 when the chain has no FixedGain
+        j.g = 1.0f; j.gprev = 0.0f; j.gnext = 0.0f; j.gprog = 0.0f; j.gstep = gstep;
+        if (flags & ODB_SF_GAIN) {                                                  // gain.rs:104-121
+            if (gnext != s.gain_shared) {                                           // Smoothed::set, smooth.rs:57-64
+                gprev = gprev + gprog * (gnext - gprev);
+                gnext = s.gain_shared;
+                gprog = 0.0f;
+            }
+            if (gprog == 1.0f) {
+                j.g = gprev + gprog * (gnext - gprev);                              // Smoothed::get at progress 1 (smooth.rs:86-91)
+            } else {
+                jf |= ODB_JF_RAMP | ODB_JF_GENERAL;
+                j.gprev = gprev; j.gnext = gnext; j.gprog = gprog;
+                for (int i = 0; i < n; i++) gprog = fminf(gprog + gstep, 1.0f);     // Smoothed::advance per sample (gain.rs:120)
+            }
+        }
+        // what the streaming kernel may touch: frames [base, base + n] of the zero-padded block
+        const long long pad_frames = ODB_PCM_PAD / ch;
+        if (!unit || off0 < 0.0f || base < -(pad_frames - 1) || base + n + 1 > (long long)s.len + pad_frames - 1 ||
+            base > (1ll << 29) || base < -(1ll << 29) || cb.force_general)
+            jf |= ODB_JF_GENERAL;
+        j.flags = jf;
+        jobs[(size_t)tl * ns + idx] = j;
+        if (jf & ODB_JF_GENERAL) n_general++; else n_fast++;
+    }
+    sp->t = t;
+    sp->sample_t = sample_t;
+    sp->gain_prev = gprev; sp->gain_next = gnext; sp->gain_progress = gprog;
+    if (n_general) atomicAdd(counters + ODB_CNT_GENERAL, n_general);
+    if (n_fast) atomicAdd(counters + ODB_CNT_FAST, n_fast);
+}
+
+// ------------------------------------------------------------------------------------------
+// Streaming kernel, ds ~= 1 path: out[i] += ((a + fract * (b - a)) * fixed_gain) * g with a = x[base+i],
+// b = x[base+i+1] read straight from HBM (coalesced; the neighbour comes from L1), one warp per
+// (source, tile), lane l owns frames l, l+32, ...; 1024*CH/32 register accumulators per lane.
+// Multiplying by a gain of exactly 1.0 is the identity, so the reference's `if g != 1.0` (gain.rs:111)
+// and the absence of a FixedGain need no branches.
+template <int CH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_mixer_unit(const OdbMixJob* __restrict__ jobs, int n_sources,
+                                                           float* __restrict__ partials) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tl = blockIdx.y;
+    const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    constexpr int NACC = ODB_MIXER_CHUNK / 32;
+    float acc[NACC][CH];
+#pragma unroll
+    for (int j = 0; j < NACC; j++)
+#pragma unroll
+        for (int c = 0; c < CH; c++) acc[j][c] = 0.0f;
+
+    for (int sidx = gw; sidx < n_sources; sidx += GW) {
+        const OdbMixJob* job = jobs + (size_t)tl * n_sources + sidx;
+        const uint32_t jf = job->flags;
+        if (jf & (ODB_JF_SKIP | ODB_JF_GENERAL)) continue;
+        const float* __restrict__ x = job->pcm + (long long)job->base * CH;
+        const float fract = job->off0, fg = job->fixed_gain, g = job->g;
+        const int n = job->n_frames;
+#pragma unroll 8
+        for (int j = 0; j < NACC; j++) {
+            const int i = 32 * j + lane;
+            if (i < n) {
+                if (CH == 1) {
+                    const float a = x[i], b = x[i + 1];
+                    float v = a + fract * (b - a);      // frame::lerp (frame.rs:39-41)
+                    v = v * fg;                         // FixedGain (gain.rs:35)
+                    v = v * g;                          // Gain, steady state (gain.rs:112-114)
+                    acc[j][0] = acc[j][0] + v;          // frame::mix (frame.rs:44-46, mixer.rs:115)
+                } else {
+                    const float2 a = *reinterpret_cast<const float2*>(x + 2 * i);
+                    const float2 b = *reinterpret_cast<const float2*>(x + 2 * i + 2);
+                    float v0 = a.x + fract * (b.x - a.x), v1 = a.y + fract * (b.y - a.y);
+                    v0 = v0 * fg; v1 = v1 * fg;
+                    v0 = v0 * g; v1 = v1 * g;
+                    acc[j][0] = acc[j][0] + v0;
+                    acc[j][CH - 1] = acc[j][CH - 1] + v1;
+                }
+            }
+        }
+    }
+    // fold: warp -> CTA (fixed order) -> one partial tile per CTA
+    float* tile = smem + warp * (ODB_MIXER_CHUNK * CH);
+#pragma unroll
+    for (int j = 0; j < NACC; j++)
+#pragma unroll
+        for (int c = 0; c < CH; c++) tile[(32 * j + lane) * CH + c] = acc[j][c];
+    __syncthreads();
+    float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * (ODB_MIXER_CHUNK * CH);
+    for (int f = threadIdx.x; f < ODB_MIXER_CHUNK * CH; f += WARPS * 32) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) sum = sum + smem[w * (ODB_MIXER_CHUNK * CH) + f];
+        dst[f] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Literal kernel: exact for every parameter combination (any ds, negative offsets, out-of-range
+// indices, gain ramps). One warp per (source, tile); lane c < CH walks channel c's chain exactly as
+// FramesSignal::sample / FixedGain::sample / Gain::sample do and parks the samples in a warp-private
+// shared tile, which all lanes then fold into their register accumulators.
+template <int CH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_mixer_general(const OdbMixJob* __restrict__ jobs, int n_sources,
+                                                              float* __restrict__ partials, int only_flagged,
+                                                              const uint32_t* __restrict__ counters) {
+    extern __shared__ float smem[];
+    if (only_flagged && counters[ODB_CNT_GENERAL] == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tl = blockIdx.y;
+    const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    constexpr int TILE = ODB_MIXER_CHUNK * CH;
+    float* tile = smem + warp * TILE;
+    float acc[TILE / 32];
+#pragma unroll
+    for (int j = 0; j < TILE / 32; j++) acc[j] = 0.0f;
+
+    for (int sidx = gw; sidx < n_sources; sidx += GW) {
+        const OdbMixJob* job = jobs + (size_t)tl * n_sources + sidx;
+        const uint32_t jf = job->flags;
+        if (jf & ODB_JF_SKIP) continue;
+        if (only_flagged && !(jf & ODB_JF_GENERAL)) continue;
+        const int n = job->n_frames;
+        if (lane < CH) {
+            const float* __restrict__ pcm = job->pcm;
+            const long long len = job->len, base = job->base, pad_frames = ODB_PCM_PAD / CH;
+            const float ds = job->ds, fg = job->fixed_gain;
+            const bool unit = (jf & ODB_JF_FAST_L) != 0, ramp = (jf & ODB_JF_RAMP) != 0;
+            const float g = job->g, gprev = job->gprev, gnext = job->gnext, gstep = job->gstep;
+            float gprog = job->gprog;
+            float offset = job->off0;
+            for (int i = 0; i < ODB_MIXER_CHUNK; i++) {
+                float v = 0.0f;
+                if (i < n) {
+                    long long k;
+                    float fract;
+                    if (unit) {                                    // frames.rs:183-187
+                        k = base + i;
+                        fract = offset;
+                    } else {                                       // frames.rs:189-196
+                        const long long tr = (long long)offset;
+                        k = base + tr;
+                        fract = offset - (float)tr;
+                        offset = offset + ds;
+                    }
+                    float a = 0.0f, b = 0.0f;                      // get_pair, frames.rs:105-123 (zeros from the padding)
+                    if (k >= -(pad_frames - 1) && k < len + pad_frames - 2) {
+                        a = pcm[k * CH + lane];
+                        b = pcm[(k + 1) * CH + lane];
+                    }
+                    v = a + fract * (b - a);                       // frame.rs:39-41
+                    v = v * fg;                                    // gain.rs:35
+                    if (ramp) {                                    // gain.rs:118-121
+                        v = v * (gprev + gprog * (gnext - gprev));
+                        gprog = fminf(gprog + gstep, 1.0f);
+                    } else {
+                        v = v * g;                                 // gain.rs:112-114 (x * 1.0 == x)
+                    }
+                }
+                tile[i * CH + lane] = v;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < TILE / 32; j++) acc[j] = acc[j] + tile[32 * j + lane];
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < TILE / 32; j++) tile[32 * j + lane] = acc[j];
+    __syncthreads();
+    float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * TILE;
+    for (int f = threadIdx.x; f < TILE; f += WARPS * 32) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) sum = sum + smem[w * TILE + f];
+        dst[f] = sum;
+    }
+}
+
+}  // namespace odbk
+
+using namespace odbk;
+
+static const int MIX_WARPS = 8;
+
+void odb_launch_walk_mixer(OdbSource* src, const uint32_t* order, OdbMixJob* jobs, uint32_t* removed, int removed_cap,
+                           uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
+    if (cb.n_sources <= 0) return;
+    k_walk_mixer<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
+}
+
+int odb_mixer_ctas(int n_sources, int sm_count, int per_sm) {
+    int want = (n_sources + MIX_WARPS - 1) / MIX_WARPS;
+    int cap = sm_count * per_sm;
+    return want < 1 ? 1 : (want > cap ? cap : want);
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+cudaError_t odb_launch_mixer_unit(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
+                                  int n_ctas, cudaStream_t st) {
+    dim3 grid(n_ctas, n_tiles);
+    const int smem = MIX_WARPS * ODB_MIXER_CHUNK * channels * (int)sizeof(float);
+    cudaError_t e;
+    if (channels == 1) {
+        if ((e = set_smem(k_mixer_unit<1, MIX_WARPS>, smem)) != cudaSuccess) return e;
+        k_mixer_unit<1, MIX_WARPS><<<grid, MIX_WARPS * 32, smem, st>>>(jobs, n_sources, partials);
+    } else {
+        if ((e = set_smem(k_mixer_unit<2, MIX_WARPS>, smem)) != cudaSuccess) return e;
+        k_mixer_unit<2, MIX_WARPS><<<grid, MIX_WARPS * 32, smem, st>>>(jobs, n_sources, partials);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t odb_launch_mixer_general(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
+                                     int n_ctas, int only_flagged, const uint32_t* counters, cudaStream_t st) {
+    dim3 grid(n_ctas, n_tiles);
+    const int smem = MIX_WARPS * ODB_MIXER_CHUNK * channels * (int)sizeof(float);
+    cudaError_t e;
+    if (channels == 1) {
+        if ((e = set_smem(k_mixer_general<1, MIX_WARPS>, smem)) != cudaSuccess) return e;
+        k_mixer_general<1, MIX_WARPS><<<grid, MIX_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged, counters);
+    } else {
+        if ((e = set_smem(k_mixer_general<2, MIX_WARPS>, smem)) != cudaSuccess) return e;
+        k_mixer_general<2, MIX_WARPS><<<grid, MIX_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged, counters);
+    }
+    return cudaGetLastError();
+}
