@@ -104,6 +104,9 @@ struct odb_ctx {
     void frames_unref(odb_frames id);
 };
 
+// Builds the device record of FramesSignal::new(frames, start) under the chain's wrappers; takes a reference on the Frames.
+int odb_make_source(odb_ctx* ctx, const odb_chain* chain, int want_channels, OdbSource* out, FramesRec* rec);
+
 #define ODB_KIND_SCENE 0x5343454Eu
 #define ODB_KIND_MIXER 0x4D495852u
 
@@ -112,6 +115,7 @@ struct SlotHost {
     uint32_t gen = 1;
     bool in_use = false;
     bool stopped = false;   // Spatial::is_finished / Mixed::is_stopped as seen by the control side
+    bool stop_requested = false;  // Mixed::stop() was called (mixer.rs:34-36); visible to is_stopped at once
     uint32_t chain_flags = 0;
     uint64_t n_frames = 0;  // FramesSignalControl::samples
     double rate = 0.0;

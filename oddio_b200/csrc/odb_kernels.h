@@ -6,9 +6,10 @@
 
 // Largest per-frame source advance (samples per output frame) the fast mix kernel stages in
 // shared memory; sources outside (0, ODB_FAST_DS_MAX] take the general kernel.
-#define ODB_FAST_DS_MAX 1.40f
-// Floats of PCM the staged kernel keeps per source and 1024-frame tile (1024 * 1.40 + ear skew + slack).
-#define ODB_FAST_PCM_CAP 1536
+#define ODB_FAST_DS_MAX 2.0f
+// Floats of PCM the staged kernel can hold per source and tile (two such buffers per warp): a full 1024-frame
+// tile fits up to ds = 1.21 (1024 * 1.21 + ear skew + slack), shorter callbacks up to ODB_FAST_DS_MAX.
+#define ODB_FAST_PCM_CAP 1280
 
 struct OdbMotionMsg {  // Spatial::set_motion payload (spatial.rs:137-149)
     uint32_t slot;
@@ -37,5 +38,13 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
 int odb_mix_fast_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int strict,
                                 cudaStream_t st);
+void odb_launch_walk_mixer(OdbSource* src, const uint32_t* order, OdbMixJob* jobs, uint32_t* removed, int removed_cap,
+                           uint32_t* counters, const OdbCallback& cb, cudaStream_t st);
+int odb_mixer_ctas(int n_sources, int sm_count, int per_sm);
+cudaError_t odb_launch_mixer_unit(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
+                                  int n_ctas, cudaStream_t st);
+cudaError_t odb_launch_mixer_general(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
+                                     int n_ctas, int only_flagged, const uint32_t* counters, cudaStream_t st);
+// Sums partial tiles of `tile_floats` floats each (1024 frames x channels) into the interleaved output.
 void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const uint32_t* counters, int b_is_general,
-                       float* out, int n_frames, int n_tiles, int epilogue, cudaStream_t st);
+                       float* out, int n_frames, int n_tiles, int channels, int epilogue, cudaStream_t st);

@@ -2,21 +2,25 @@
 // over FramesSignal::sample (frames.rs:176-201) for every source whose PCM window of one 1024-frame
 // tile fits in shared memory.
 //
-// One warp per source, sources strided over a persistent grid:
-//   1. lane 0 starts a bulk async copy (TMA, cp.async.bulk -> UBLKCP) of the source's PCM window
-//      HBM -> this warp's shared-memory buffer, completion on a per-warp mbarrier;
-//   2. while the copy is in flight, lanes 0..3 (one per 256-frame chunk, both ears packed in an
-//      f32x2) walk the reference's serial cursor `offset += ds` (frames.rs:195) literally and store
-//      every 4th cursor value to shared memory. The chain is the one part of the path that is not
-//      associative: it is evaluated with exactly the reference's sequence of f32 additions, so frame
-//      indices are bit-exact;
-//   3. all 32 lanes consume: lane l owns frames l, l+32, ... of the tile, re-derives its cursor from
-//      the stored checkpoint with <= 3 more literal additions, splits it into index and fraction with
-//      a round-down magic add (no F2I/I2F), gathers the sample pair from shared memory, lerps
-//      (frame.rs:39-41), applies the per-frame gain ramp (spatial.rs:459) and accumulates into 64
-//      register accumulators (32 frames x 2 ears, ears packed as FP32x2: FADD2/FMUL2/FFMA2);
-//   4. after its last source a warp parks the accumulators in shared memory, the CTA folds its warps
-//      in a fixed order and writes one partial tile; k_reduce_tiles sums the partial tiles.
+// A persistent grid of one 12-warp CTA per SM; every warp works on its own batches of 4 consecutive
+// sources and never synchronises with the other warps until the final fold:
+//   1. the warp stages the batch's four 128-byte job records in shared memory and lane 0 starts a bulk
+//      async copy (TMA, cp.async.bulk -> UBLKCP) of the first source's PCM window HBM -> one of the warp's
+//      two PCM buffers, completion on a per-buffer mbarrier;
+//   2. while the copy is in flight all 32 lanes - one per (source, ear, 256-frame chunk) - walk the
+//      reference's serial cursor `offset += ds` (frames.rs:195) literally and store every 4th cursor value
+//      to shared memory. The chain is the one part of the path that is not associative: it is evaluated
+//      with exactly the reference's sequence of f32 additions, so frame indices are bit-exact
+//      (SURVEY.md §7 H1);
+//   3. per source, all 32 lanes consume (the next source's window is already being copied into the other
+//      buffer): lane l owns frames l, l+32, ... of the tile, re-derives its cursor from the stored
+//      checkpoint with <= 3 more literal additions, splits it into index and fraction with a round-down
+//      magic add (no F2I/I2F), gathers the sample pair from shared memory, lerps (frame.rs:39-41),
+//      applies the per-frame gain ramp (spatial.rs:459) and accumulates into 64 register accumulators
+//      (32 frames x 2 ears, ears packed as FP32x2: FADD2/FFMA2). An ear on FramesSignal's ds ~= 1 path
+//      (frames.rs:180-187) skips the cursor and uses index base + i with a constant fraction;
+//   4. after its last batch a warp parks the accumulators in shared memory, the CTA folds its warps in a
+//      fixed order and writes one partial tile; k_reduce_tiles sums the partial tiles.
 //
 // STRICT = true keeps every value operation unfused in the reference's order, so a source's
 // contribution is bit-identical to the reference's; STRICT = false contracts the three value
@@ -89,9 +93,13 @@ __device__ __forceinline__ u64 lds_u64(uint32_t addr) {
     asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_v2u64(uint32_t addr, u64 a, u64 b) {
-    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -114,38 +122,60 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr int FAST_WARPS = 8;
-constexpr int FAST_PCM_BYTES = ODB_FAST_PCM_CAP * 4;                        // 6144
+constexpr int FAST_WARPS = 12;                                              // one CTA per SM
+constexpr int FAST_BATCH = 4;                                               // sources per warp batch: 4 x 2 ears x 4 chunks = 32 chains
+constexpr int FAST_PCM_BYTES = ODB_FAST_PCM_CAP * 4;                        // 5120, two of them per warp
 constexpr int FAST_POINTS = ODB_SPATIAL_CHUNK / 4;                          // every 4th cursor value of a chunk
-constexpr int FAST_OFFS_BYTES = ODB_TILE_CHUNKS * FAST_POINTS * 8;          // 2048: [chunk][point] (L, R)
-constexpr int FAST_WARP_BYTES = FAST_PCM_BYTES + FAST_OFFS_BYTES;           // 8192 = one stereo tile, reused for the fold
-static_assert(FAST_WARP_BYTES == 2 * ODB_TILE_FRAMES * 4, "the warp region doubles as its partial tile");
-constexpr int FAST_SMEM_BYTES = FAST_WARPS * FAST_WARP_BYTES + FAST_WARPS * 8;
+constexpr int FAST_ROW_BYTES = FAST_POINTS * 8 + 8;                         // one (source, chunk) row of (L, R) cursors; +8 skews the banks
+constexpr int FAST_OFFS_BYTES = FAST_BATCH * ODB_TILE_CHUNKS * FAST_ROW_BYTES;  // 8320
+constexpr int FAST_WARP_BYTES = 2 * FAST_PCM_BYTES + FAST_OFFS_BYTES;       // 18560
+static_assert(FAST_WARP_BYTES >= 2 * ODB_TILE_FRAMES * 4, "the warp region doubles as its partial tile");
+static_assert(FAST_WARP_BYTES % 16 == 0, "TMA destinations are 16-byte aligned");
+constexpr int FAST_JOBS_OFF = FAST_WARPS * FAST_WARP_BYTES;                 // staged job records: 4 x 128 B per warp
+constexpr int FAST_BARS_OFF = FAST_JOBS_OFF + FAST_WARPS * FAST_BATCH * 128;
+constexpr int FAST_SMEM_BYTES = FAST_BARS_OFF + FAST_WARPS * 16;
 #define ODB_MAGIC 8388608.0f          // 2^23: ulp 1, so x +rd 2^23 = 2^23 + floor(x)
 #define ODB_MAGIC_BITS 0x4B000000u
 
-// One 256-frame chunk of one source, doppler (serial-cursor) path. FULL: every frame of the chunk is inside the tile.
-template <bool STRICT, bool FULL>
-__device__ __forceinline__ void consume_chunk_doppler(u64* __restrict__ acc, const int c, const int lane, const float fbase,
-                                                      const uint32_t offs_sa, const uint32_t KL, const uint32_t KR,
-                                                      const u64 d1, const u64 d2, const u64 d3, const u64 pgp,
-                                                      const u64 dgp, const int nfr, const u64 nz) {
+// One 256-frame chunk of one source. UL / UR: that ear is on the ds ~= 1 path (constant fraction, index
+// base + i); otherwise its cursor comes from the chain checkpoints. FULL: every frame of the chunk is
+// inside the tile. KL / KR: doppler ear = shared address of PCM index `base` minus the magic bits,
+// unit ear = shared address of PCM index base + lane.
+template <bool STRICT, bool FULL, bool UL, bool UR>
+__device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c, const int lane, const float fbase,
+                                              const uint32_t row_sa, const uint32_t KL, const uint32_t KR, const u64 d1,
+                                              const u64 d2, const u64 d3, const u64 fr_unit, const u64 pgp,
+                                              const u64 dgp, const int nfr, const u64 nz) {
     const u64 magic = pk2(ODB_MAGIC, ODB_MAGIC);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j >= nfr) break;  // warp-uniform
-        // cursor of frame k = 32j + lane: checkpoint k & ~3, then (k & 3) literal `offset += ds` steps (frames.rs:195)
-        u64 o = lds_u64(offs_sa + (uint32_t)(((c * FAST_POINTS) + 8 * j) * 8) + (uint32_t)((lane >> 2) * 8));
-        o = add2(o, d1);
-        o = add2(o, d2);
-        o = add2(o, d3);
-        // trunc = offset as isize; fract = offset - trunc as f32 (frames.rs:191-193), offset >= 0 here
-        const u64 t = add2_rm(o, magic);
-        const u64 fl = sub2(t, magic);
-        const u64 fr = sub2(o, fl);
-        uint32_t tL, tR;
-        upk2u(t, tL, tR);
-        const uint32_t aL = KL + (tL << 2), aR = KR + (tR << 2);
+        uint32_t aL, aR;
+        u64 fr;
+        if (!(UL && UR)) {
+            // cursor of frame k = 32j + lane: checkpoint k & ~3, then (k & 3) literal `offset += ds` steps (frames.rs:195)
+            u64 o = lds_u64(row_sa + (uint32_t)(64 * j));
+            o = add2(o, d1);
+            o = add2(o, d2);
+            o = add2(o, d3);
+            // trunc = offset as isize; fract = offset - trunc as f32 (frames.rs:191-193), offset >= 0 here
+            const u64 t = add2_rm(o, magic);
+            const u64 fl = sub2(t, magic);
+            fr = sub2(o, fl);
+            uint32_t tL, tR;
+            upk2u(t, tL, tR);
+            aL = KL + (tL << 2);
+            aR = KR + (tR << 2);
+        }
+        if (UL || UR) {  // frames.rs:183-187
+            float f0, f1, u0, u1;
+            upk2(fr_unit, u0, u1);
+            if (UL && UR) { f0 = u0; f1 = u1; }
+            else { upk2(fr, f0, f1); if (UL) f0 = u0; else f1 = u1; }
+            fr = pk2(f0, f1);
+            if (UL) aL = KL + (uint32_t)(128 * j);
+            if (UR) aR = KR + (uint32_t)(128 * j);
+        }
         const u64 a = pk2(lds_f32(aL), lds_f32(aR));      // get_pair (frames.rs:105-123); zeros come from the arena padding
         const u64 b = pk2(lds_f32_4(aL), lds_f32_4(aR));
         const u64 d = sub2(b, a);                          // frame::lerp = a + t * (b - a) (frame.rs:39-41)
@@ -165,47 +195,47 @@ __device__ __forceinline__ void consume_chunk_doppler(u64* __restrict__ acc, con
     }
 }
 
-// Same for the ds ~= 1 path (frames.rs:180-187): constant fract, index base + i.
-template <bool STRICT, bool FULL>
-__device__ __forceinline__ void consume_chunk_unit(u64* __restrict__ acc, const int c, const int lane, const float fbase,
-                                                   const uint32_t AL, const uint32_t AR, const u64 fr, const u64 pgp,
-                                                   const u64 dgp, const int nfr, const u64 nz) {
+template <bool STRICT, bool FULL, bool UL, bool UR>
+__device__ __forceinline__ void consume_source(u64* __restrict__ acc, const int lane, const float lanef, const uint32_t job_sa,
+                                               const uint32_t pcm_b, const uint32_t rows_sa, const int w_start,
+                                               const int nfr, const u64 d1, const u64 d2, const u64 d3, const u64 pgp,
+                                               const u64 dgp, const u64 nz) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j >= nfr) break;
-        const uint32_t aL = AL + (uint32_t)(128 * j), aR = AR + (uint32_t)(128 * j);
-        const u64 a = pk2(lds_f32(aL), lds_f32(aR));
-        const u64 b = pk2(lds_f32_4(aL), lds_f32_4(aR));
-        const u64 d = sub2(b, a);
-        const float fi = fbase + (float)(32 * j);
-        const u64 fi2 = pk2(fi, fi);
-        u64 s, g;
-        if (STRICT) {
-            s = add2(a, mulx(fr, d, nz));
-            g = add2(pgp, mulx(fi2, dgp, nz));
-        } else {
-            s = fma2(fr, d, a);
-            g = fma2(fi2, dgp, pgp);
-        }
-        if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j + lane >= nfr) s = 0ull;
-        if (STRICT) acc[c * 8 + j] = add2(acc[c * 8 + j], mulx(s, g, nz));
-        else acc[c * 8 + j] = fma2(s, g, acc[c * 8 + j]);
+    for (int c = 0; c < ODB_TILE_CHUNKS; c++) {
+        if (!FULL && c * ODB_SPATIAL_CHUNK >= nfr) break;
+        const int baseL = (int)lds_u32(job_sa + (ODB_JW_BASE + c) * 4);
+        const int baseR = (int)lds_u32(job_sa + (ODB_JW_BASE + ODB_TILE_CHUNKS + c) * 4);
+        const uint32_t KL = pcm_b + (uint32_t)((baseL - w_start) * 4) + (UL ? (uint32_t)(lane * 4) : 0u - (ODB_MAGIC_BITS << 2));
+        const uint32_t KR = pcm_b + (uint32_t)((baseR - w_start) * 4) + (UR ? (uint32_t)(lane * 4) : 0u - (ODB_MAGIC_BITS << 2));
+        u64 fr_unit = 0ull;
+        if (UL || UR)
+            fr_unit = pk2(__uint_as_float(lds_u32(job_sa + (ODB_JW_OFF0 + c) * 4)),
+                          __uint_as_float(lds_u32(job_sa + (ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4)));
+        consume_chunk<STRICT, FULL, UL, UR>(acc, c, lane, lanef + (float)(c * ODB_SPATIAL_CHUNK),
+                                            rows_sa + (uint32_t)(c * FAST_ROW_BYTES), KL, KR, d1, d2, d3, fr_unit, pgp, dgp,
+                                            nfr, nz);
     }
 }
 
 template <bool STRICT>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 2) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
+__global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
                                                                   float* __restrict__ partials, const u64 nz) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tl = blockIdx.y;
-    const uint32_t pcm_sa = smem_u32(smem_raw + warp * FAST_WARP_BYTES);
-    const uint32_t offs_sa = pcm_sa + FAST_PCM_BYTES;
-    const uint32_t bar_sa = smem_u32(smem_raw + FAST_WARPS * FAST_WARP_BYTES + warp * 8);
-    if (lane == 0) mbar_init(bar_sa, 1);
+    const uint32_t smem_sa = smem_u32(smem_raw);
+    const uint32_t pcm_sa = smem_sa + (uint32_t)(warp * FAST_WARP_BYTES);
+    const uint32_t offs_sa = pcm_sa + 2 * FAST_PCM_BYTES;
+    const uint32_t jobs_sa = smem_sa + (uint32_t)(FAST_JOBS_OFF + warp * FAST_BATCH * 128);
+    const uint32_t bar_sa = smem_sa + (uint32_t)(FAST_BARS_OFF + warp * 16);
+    if (lane == 0) {
+        mbar_init(bar_sa, 1);
+        mbar_init(bar_sa + 8, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t parity = 0;
+    uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
+    uint32_t buf = 0;     // PCM buffer the next source to consume lands in
 
     u64 acc[ODB_TILE_FRAMES / 32];
 #pragma unroll
@@ -215,88 +245,98 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) k_mix_fast(const OdbJob* _
     const float lanef = (float)(tl * ODB_TILE_FRAMES + lane);
     const int r = lane & 3;
     const OdbJob* tile_jobs = jobs + (size_t)tl * n_sources;
+    const int n_batches = (n_sources + FAST_BATCH - 1) / FAST_BATCH;
 
-    for (int sidx = gw; sidx < n_sources; sidx += GW) {
-        // the job is one 128-byte line: lane l holds word l
-        const uint32_t jw = reinterpret_cast<const uint32_t*>(tile_jobs + sidx)[lane];
-        const uint32_t jf = __shfl_sync(0xffffffffu, jw, ODB_JW_FLAGS);
-        if (jf & (ODB_JF_SKIP | ODB_JF_GENERAL)) continue;
-        const int w_start = (int)__shfl_sync(0xffffffffu, jw, ODB_JW_W_START);
-        const uint32_t w_bytes = __shfl_sync(0xffffffffu, jw, ODB_JW_W_LEN) * 4u;
-        const uint32_t pcm_hi = __shfl_sync(0xffffffffu, jw, ODB_JW_PCM_HI);
-        if (lane == 0) {  // 1. PCM window HBM -> shared, asynchronously
-            const float* pcm = reinterpret_cast<const float*>(((u64)pcm_hi << 32) | (u64)jw);
-            mbar_expect_tx(bar_sa, w_bytes);
-            bulk_g2s(pcm_sa, pcm + w_start, w_bytes, bar_sa);
+    // lane 0: start the bulk copy of source q's PCM window into PCM buffer `b`
+    auto start_copy = [&](int q, uint32_t b) {
+        if (lane == 0) {
+            const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
+            const u64 p = ((u64)lds_u32(job_sa + ODB_JW_PCM_HI * 4) << 32) | (u64)lds_u32(job_sa + ODB_JW_PCM_LO * 4);
+            const int w_start = (int)lds_u32(job_sa + ODB_JW_W_START * 4);
+            const uint32_t bytes = lds_u32(job_sa + ODB_JW_W_LEN * 4) * 4u;
+            mbar_expect_tx(bar_sa + b * 8, bytes);
+            bulk_g2s(pcm_sa + b * FAST_PCM_BYTES, reinterpret_cast<const float*>(p) + w_start, bytes, bar_sa + b * 8);
         }
-        const int nfr = (int)__shfl_sync(0xffffffffu, jw, ODB_JW_N_FRAMES);
-        const bool unit = (jf & ODB_JF_FAST_L) != 0;  // both ears or neither (walk kernel guarantees)
-        const float dsL = __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_DS));
-        const float dsR = __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_DS + 1));
-        const u64 dsp = pk2(dsL, dsR);
-        const float o0L = __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_OFF0 + r));
-        const float o0R = __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_OFF0 + ODB_TILE_CHUNKS + r));
-        if (!unit) {
-            if (lane < ODB_TILE_CHUNKS) {  // 2. literal cursor chains, one lane per chunk, ears packed
-                u64 o = pk2(o0L, o0R);
-                const uint32_t dst = offs_sa + (uint32_t)(lane * FAST_POINTS * 8);
-#pragma unroll 4
-                for (int m = 0; m < FAST_POINTS; m += 2) {
-                    const u64 p0 = o;
-                    o = add2(o, dsp); o = add2(o, dsp); o = add2(o, dsp); o = add2(o, dsp);
-                    const u64 p1 = o;
-                    o = add2(o, dsp); o = add2(o, dsp); o = add2(o, dsp); o = add2(o, dsp);
-                    sts_v2u64(dst + (uint32_t)(m * 8), p0, p1);
+    };
+
+    for (int bi = gw; bi < n_batches; bi += GW) {
+        const int s0 = bi * FAST_BATCH;
+        // 1. stage the batch's job records (one 128-byte line each: lane l moves word l)
+#pragma unroll
+        for (int q = 0; q < FAST_BATCH; q++) {
+            uint32_t w = lane == ODB_JW_FLAGS ? ODB_JF_SKIP : 0u;
+            if (s0 + q < n_sources) w = __ldg(reinterpret_cast<const uint32_t*>(tile_jobs + s0 + q) + lane);
+            sts_u32(jobs_sa + (uint32_t)(q * 128 + lane * 4), w);
+        }
+        __syncwarp();
+        uint32_t act = 0;  // sources of the batch this kernel mixes
+#pragma unroll
+        for (int q = 0; q < FAST_BATCH; q++)
+            if (!(lds_u32(jobs_sa + (uint32_t)(q * 128 + ODB_JW_FLAGS * 4)) & (ODB_JF_SKIP | ODB_JF_GENERAL))) act |= 1u << q;
+        if (act) {
+            start_copy(__ffs(act) - 1, buf);
+            {   // 2. literal cursor chains: lane = (source q, ear e, chunk c)
+                const int q = lane >> 3, e = (lane >> 2) & 1, c = lane & 3;
+                const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
+                const uint32_t jf = lds_u32(job_sa + ODB_JW_FLAGS * 4);
+                if (((act >> q) & 1u) && !(jf & (e ? ODB_JF_FAST_R : ODB_JF_FAST_L))) {
+                    float o = __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c) * 4)));
+                    const float ds = __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_DS + e) * 4)));
+                    const uint32_t dst = offs_sa + (uint32_t)((q * ODB_TILE_CHUNKS + c) * FAST_ROW_BYTES + e * 4);
+#pragma unroll 8
+                    for (int m = 0; m < FAST_POINTS; m++) {
+                        sts_f32(dst + (uint32_t)(m * 8), o);
+                        o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds);
+                    }
                 }
             }
             __syncwarp();
-        }
-        const u64 pgp = pk2(__uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_PG)),
-                            __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_PG + 1)));
-        const u64 dgp = pk2(__uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_DG)),
-                            __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_DG + 1)));
-        const u64 d1 = r >= 1 ? dsp : 0ull, d2 = r >= 2 ? dsp : 0ull, d3 = r >= 3 ? dsp : 0ull;
-        mbar_wait(bar_sa, parity);
-        parity ^= 1u;
-        // 3. consume
-        const bool full = nfr == ODB_TILE_FRAMES;
-#pragma unroll
-        for (int c = 0; c < ODB_TILE_CHUNKS; c++) {
-            if (c * ODB_SPATIAL_CHUNK >= nfr) break;
-            const int baseL = (int)__shfl_sync(0xffffffffu, jw, ODB_JW_BASE + c);
-            const int baseR = (int)__shfl_sync(0xffffffffu, jw, ODB_JW_BASE + ODB_TILE_CHUNKS + c);
-            const float fbase = lanef + (float)(c * ODB_SPATIAL_CHUNK);
-            if (!unit) {
-                const uint32_t KL = pcm_sa + (uint32_t)((baseL - w_start) * 4) - (ODB_MAGIC_BITS << 2);
-                const uint32_t KR = pcm_sa + (uint32_t)((baseR - w_start) * 4) - (ODB_MAGIC_BITS << 2);
-                if (full) consume_chunk_doppler<STRICT, true>(acc, c, lane, fbase, offs_sa, KL, KR, d1, d2, d3, pgp, dgp, nfr, nz);
-                else consume_chunk_doppler<STRICT, false>(acc, c, lane, fbase, offs_sa, KL, KR, d1, d2, d3, pgp, dgp, nfr, nz);
-            } else {
-                const uint32_t AL = pcm_sa + (uint32_t)((baseL - w_start + lane) * 4);
-                const uint32_t AR = pcm_sa + (uint32_t)((baseR - w_start + lane) * 4);
-                const u64 fr = pk2(__uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_OFF0 + c)),
-                                   __uint_as_float(__shfl_sync(0xffffffffu, jw, ODB_JW_OFF0 + ODB_TILE_CHUNKS + c)));
-                if (full) consume_chunk_unit<STRICT, true>(acc, c, lane, fbase, AL, AR, fr, pgp, dgp, nfr, nz);
-                else consume_chunk_unit<STRICT, false>(acc, c, lane, fbase, AL, AR, fr, pgp, dgp, nfr, nz);
+            // 3. consume the batch source by source
+            for (int q = 0; q < FAST_BATCH; q++) {
+                if (!((act >> q) & 1u)) continue;
+                const uint32_t rest = act >> (q + 1);
+                if (rest) start_copy(q + __ffs(rest), buf ^ 1u);  // next window -> the other buffer
+                const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
+                const uint32_t jf = lds_u32(job_sa + ODB_JW_FLAGS * 4);
+                const int nfr = (int)lds_u32(job_sa + ODB_JW_N_FRAMES * 4);
+                const int w_start = (int)lds_u32(job_sa + ODB_JW_W_START * 4);
+                const u64 dsp = lds_u64(job_sa + ODB_JW_DS * 4), pgp = lds_u64(job_sa + ODB_JW_PG * 4),
+                          dgp = lds_u64(job_sa + ODB_JW_DG * 4);
+                const u64 d1 = r >= 1 ? dsp : 0ull, d2 = r >= 2 ? dsp : 0ull, d3 = r >= 3 ? dsp : 0ull;
+                const uint32_t pcm_b = pcm_sa + buf * FAST_PCM_BYTES;
+                const uint32_t rows_sa = offs_sa + (uint32_t)(q * ODB_TILE_CHUNKS * FAST_ROW_BYTES + (lane >> 2) * 8);
+                mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
+                parity ^= 1u << buf;
+                const uint32_t code = (nfr == ODB_TILE_FRAMES ? 4u : 0u) | ((jf & ODB_JF_FAST_L) ? 2u : 0u) | ((jf & ODB_JF_FAST_R) ? 1u : 0u);
+#define ODB_CONSUME(F, L, R) consume_source<STRICT, F, L, R>(acc, lane, lanef, job_sa, pcm_b, rows_sa, w_start, nfr, d1, d2, d3, pgp, dgp, nz)
+                switch (code) {
+                    case 4: ODB_CONSUME(true, false, false); break;
+                    case 7: ODB_CONSUME(true, true, true); break;
+                    case 0: ODB_CONSUME(false, false, false); break;
+                    case 3: ODB_CONSUME(false, true, true); break;
+                    case 6: ODB_CONSUME(true, true, false); break;
+                    case 5: ODB_CONSUME(true, false, true); break;
+                    case 2: ODB_CONSUME(false, true, false); break;
+                    default: ODB_CONSUME(false, false, true); break;
+                }
+#undef ODB_CONSUME
+                __syncwarp();  // every lane is done with this PCM buffer before it is refilled
+                buf ^= 1u;
             }
         }
-        __syncwarp();  // every lane is done with the PCM and cursor buffers before they are refilled
+        __syncwarp();  // ... and with the staged job records and cursor rows
     }
 
     // 4. fold: warp -> CTA (fixed warp order) -> one partial tile per CTA
-    {
-        const uint32_t tile_sa = pcm_sa;
 #pragma unroll
-        for (int j = 0; j < ODB_TILE_FRAMES / 32; j++)
-            asm volatile("st.shared.b64 [%0], %1;" ::"r"(tile_sa + (uint32_t)((32 * j + lane) * 8)), "l"(acc[j]) : "memory");
-    }
+    for (int j = 0; j < ODB_TILE_FRAMES / 32; j++)
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(pcm_sa + (uint32_t)((32 * j + lane) * 8)), "l"(acc[j]) : "memory");
     __syncthreads();
-    const float* all = reinterpret_cast<const float*>(smem_raw);
     float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * (2 * ODB_TILE_FRAMES);
     for (int f = threadIdx.x; f < 2 * ODB_TILE_FRAMES; f += FAST_WARPS * 32) {
         float sum = 0.0f;
 #pragma unroll
-        for (int w = 0; w < FAST_WARPS; w++) sum = sum + all[w * (2 * ODB_TILE_FRAMES) + f];
+        for (int w = 0; w < FAST_WARPS; w++) sum = sum + *reinterpret_cast<const float*>(smem_raw + w * FAST_WARP_BYTES + f * 4);
         dst[f] = sum;
     }
 }
@@ -306,21 +346,15 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) k_mix_fast(const OdbJob* _
 using namespace odbk;
 
 int odb_mix_fast_ctas(int n_sources, int sm_count) {
-    int want = (n_sources + FAST_WARPS - 1) / FAST_WARPS;
-    int cap = sm_count * 2;
-    return want < 1 ? 1 : (want > cap ? cap : want);
+    int want = (n_sources + FAST_WARPS * FAST_BATCH - 1) / (FAST_WARPS * FAST_BATCH);
+    return want < 1 ? 1 : (want > sm_count ? sm_count : want);
 }
 
 cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int strict,
                                 cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_mix_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_mix_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(strict ? k_mix_fast<true> : k_mix_fast<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     dim3 grid(n_ctas, n_tiles);
     if (strict) k_mix_fast<true><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
     else k_mix_fast<false><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mixer_unit(const OdbMixJob* __re
         const float* __restrict__ x = job->pcm + (long long)job->base * CH;
         const float fract = job->off0, fg = job->fixed_gain, g = job->g;
         const int n = job->n_frames;
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < NACC; j++) {
             const int i = 32 * j + lane;
             if (i < n) {

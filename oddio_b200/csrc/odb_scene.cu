@@ -65,7 +65,7 @@ extern "C" int odb_scene_set_epilogue(odb_scene* scene, int epilogue) {
 }
 
 // Builds the device record of FramesSignal::new(frames, start) under the chain's wrappers.
-static int make_source(odb_ctx* ctx, const odb_chain* chain, int want_channels, OdbSource* out, FramesRec* rec) {
+int odb_make_source(odb_ctx* ctx, const odb_chain* chain, int want_channels, OdbSource* out, FramesRec* rec) {
     if (!chain) return odb_fail(ODB_E_INVALID, "chain is NULL");
     ODB_TRY(ctx->frames_ref(chain->frames, rec));
     if (rec->channels != want_channels) {
@@ -100,7 +100,7 @@ extern "C" int odb_scene_play(odb_scene* scene, const odb_chain* chain, const fl
         return odb_fail(ODB_E_UNSUPPORTED, "SpatialSceneControl::play requires Seek; Speed and Gain do not implement it (use play_buffered)");
     OdbSource s;
     FramesRec rec;
-    ODB_TRY(make_source(scene->ctx, chain, 1, &s, &rec));
+    ODB_TRY(odb_make_source(scene->ctx, chain, 1, &s, &rec));
     s.radius = radius;
     for (int k = 0; k < 3; k++) {
         s.pos[k] = position[k]; s.vel[k] = velocity[k];          // Motion, discontinuity: false (:100-104)
@@ -248,7 +248,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             launches++;
         }
         odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_counters.p,
-                          /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, scene->epilogue, st);
+                          /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }
     {   // start the read-back of what walk_set removed; folded in by a later call without waiting

@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
         long long ws = wlo[tl] & ~3ll;
         long long wl = ((whi[tl] - ws + 1) + 3) & ~3ll;
         uint32_t f = jflags[tl];
-        if (fast_e[0] != fast_e[1]) f |= ODB_JF_GENERAL;
         if (wl > ODB_FAST_PCM_CAP || ws < -(long long)ODB_PCM_PAD || ws + wl > (long long)s.len + ODB_PCM_PAD) f |= ODB_JF_GENERAL;
         if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
         if (cb.force_general) f |= ODB_JF_GENERAL;
@@ -270,28 +269,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
 __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* __restrict__ pa, int na,
                                                                  const float* __restrict__ pb, int nb,
                                                                  const uint32_t* __restrict__ counters, int b_is_general,
-                                                                 float* __restrict__ out, int n_frames, int epilogue) {
+                                                                 float* __restrict__ out, int n_frames, int channels,
+                                                                 int epilogue) {
     __shared__ float fold[RED_GROUPS][32];
     const int tl = blockIdx.y;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int f = blockIdx.x * 32 + lane;  // float index inside the tile
     if (b_is_general && counters[ODB_CNT_GENERAL] == 0) nb = 0;
     float sum = 0.0f;
-    const float* p = pa + (size_t)tl * na * (2 * ODB_TILE_FRAMES) + f;
-    for (int i = grp; i < na; i += RED_GROUPS) sum = sum + p[(size_t)i * (2 * ODB_TILE_FRAMES)];
-    const float* q = pb + (size_t)tl * nb * (2 * ODB_TILE_FRAMES) + f;
-    for (int i = grp; i < nb; i += RED_GROUPS) sum = sum + q[(size_t)i * (2 * ODB_TILE_FRAMES)];
+    const size_t tile_floats = (size_t)ODB_TILE_FRAMES * channels;
+    const float* p = pa + (size_t)tl * na * tile_floats + f;
+    for (int i = grp; i < na; i += RED_GROUPS) sum = sum + p[(size_t)i * tile_floats];
+    const float* q = pb + (size_t)tl * nb * tile_floats + f;
+    for (int i = grp; i < nb; i += RED_GROUPS) sum = sum + q[(size_t)i * tile_floats];
     fold[grp][lane] = sum;
     __syncthreads();
     if (grp != 0) return;
     sum = 0.0f;
 #pragma unroll
     for (int g = 0; g < RED_GROUPS; g++) sum = sum + fold[g][lane];
-    const int frame = tl * ODB_TILE_FRAMES + (f >> 1);
+    const int frame = tl * ODB_TILE_FRAMES + f / channels;
     if (frame >= n_frames) return;
     if (epilogue == 1) sum = tanhf(sum);
     else if (epilogue == 2) sum = sum / (1.0f + fabsf(sum));
-    out[(size_t)frame * 2 + (f & 1)] = sum;
+    out[(size_t)tl * tile_floats + f] = sum;
 }
 
 }  // namespace odbk
@@ -339,8 +340,8 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
     return cudaGetLastError();
 }
 void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const uint32_t* counters, int b_is_general,
-                       float* out, int n_frames, int n_tiles, int epilogue, cudaStream_t st) {
+                       float* out, int n_frames, int n_tiles, int channels, int epilogue, cudaStream_t st) {
     if (n_frames <= 0) return;
-    dim3 grid(2 * ODB_TILE_FRAMES / 32, n_tiles);
-    k_reduce_tiles<<<grid, 32 * RED_GROUPS, 0, st>>>(pa, na, pb, nb, counters, b_is_general, out, n_frames, epilogue);
+    dim3 grid(channels * ODB_TILE_FRAMES / 32, n_tiles);
+    k_reduce_tiles<<<grid, 32 * RED_GROUPS, 0, st>>>(pa, na, pb, nb, counters, b_is_general, out, n_frames, channels, epilogue);
 }

@@ -81,10 +81,26 @@ struct __attribute__((aligned(16))) OdbJob {
 #define ODB_JW_OFF0 20
 #define ODB_JW_W_START 28
 #define ODB_JW_W_LEN 29
+// What one (source, 1024-frame chunk) pass of the mixer kernels needs. 64 bytes.
+struct __attribute__((aligned(16))) OdbMixJob {
+    const float* pcm;
+    int len;          // frames
+    uint32_t flags;   // ODB_JF_SKIP / ODB_JF_FAST_L (ds ~= 1 path) / ODB_JF_GENERAL / ODB_JF_RAMP
+    int base;         // frames.rs:179, saturated
+    float off0;       // constant fract (ds ~= 1) or initial offset
+    float ds;         // (interval * speed) * rate as f32
+    float fixed_gain; // FixedGain::gain, 1.0 if absent
+    float g;          // Gain at rest: Smoothed::get() with progress == 1; 1.0 if absent
+    float gprev, gnext, gprog, gstep;  // Gain mid-transition (ODB_JF_RAMP): Smoothed state at the chunk start
+    int n_frames;
+    uint32_t pad[2];
+};
+static_assert(sizeof(OdbMixJob) == 64, "OdbMixJob is half a 128-byte line");
 #define ODB_JF_SKIP 0x1u        // source removed/stopped this callback: contributes nothing
 #define ODB_JF_FAST_L 0x2u      // |ds-1| <= EPSILON for the left ear (frames.rs:180)
 #define ODB_JF_FAST_R 0x4u
 #define ODB_JF_FIXED_GAIN 0x8u
+#define ODB_JF_RAMP 0x20u       // mixer: Gain is mid-transition during this chunk (gain.rs:118-121)
 #define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
 
 // Device counters written by the walk kernels each callback (uint32 each).

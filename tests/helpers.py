@@ -112,3 +112,67 @@ def assert_mix_close(dev, ref, ref64, rel=1e-5):
     tol64 = rel * np.maximum(np.abs(ref64), rms) + 1e-30
     bad64 = np.abs(dev - ref64) > tol64
     assert not bad64.any(), f"{bad64.sum()} samples off against the f64 truth"
+
+
+class MixerPair:
+    """An oracle Mixer and a device Mixer fed identical calls. `epilogue` in (None, 'tanh', 'reinhard')."""
+
+    def __init__(self, oracle, odb, ctx, channels, epilogue=None):
+        self.o, self.odb, self.ctx, self.channels = oracle, odb, ctx, channels
+        self.ref_mixer = oracle.Mixer(channels)
+        self.ctl, self.dev_mixer = odb.Mixer.new(channels, ctx)
+        self.ref, self.dev = self.ref_mixer, self.dev_mixer
+        if epilogue == "tanh":
+            self.ref, self.dev = oracle.Tanh(self.ref_mixer), odb.Tanh(self.dev_mixer)
+        elif epilogue == "reinhard":
+            self.ref, self.dev = oracle.Reinhard(self.ref_mixer), odb.Reinhard(self.dev_mixer)
+        self.items = []  # dicts: ref/dev handles and controls per played signal
+        self._frames_cache = {}
+
+    def frames(self, rate, pcm):
+        key = id(pcm)
+        if key not in self._frames_cache:
+            self._frames_cache[key] = (self.o.Frames.from_slice(rate, pcm), self.odb.Frames.from_slice(rate, pcm, self.ctx), pcm)
+        return self._frames_cache[key][:2]
+
+    def play(self, rate, pcm, start=0.0, speed=None, fixed_gain_db=None, gain=None):
+        fo, fd = self.frames(rate, pcm)
+        so = self.o.FramesSignal(fo, start)
+        cd, sd = self.odb.FramesSignal.new(fd, start)
+        it = {"ref_frames_signal": so, "dev_frames_control": cd}
+        io, idv = so, sd
+        if speed is not None:
+            io = self.o.Speed(io); io.set_speed(speed)
+            sc, idv = self.odb.Speed.new(idv); sc.set_speed(speed)
+            it["ref_speed"], it["dev_speed"] = io, sc
+        if fixed_gain_db is not None:
+            io = self.o.FixedGain(io, fixed_gain_db)
+            idv = self.odb.FixedGain(idv, fixed_gain_db)
+        if gain is not None:
+            io = self.o.Gain(io); io.set_amplitude_ratio(gain)
+            gc, idv = self.odb.Gain.new(idv); idv.set_amplitude_ratio(gain)
+            it["ref_gain"], it["dev_gain"] = io, gc
+        it["ref_mixed"] = self.ref_mixer.play(io)
+        it["dev_mixed"] = self.ctl.play(idv)
+        self.items.append(it)
+        return len(self.items) - 1
+
+    def set_speed(self, i, v):
+        self.items[i]["ref_speed"].set_speed(v)
+        self.items[i]["dev_speed"].set_speed(v)
+
+    def set_gain_ratio(self, i, v):
+        self.items[i]["ref_gain"].control_set_amplitude_ratio(v)
+        self.items[i]["dev_gain"].set_amplitude_ratio(v)
+
+    def stop(self, i):
+        self.items[i]["ref_mixed"].stop()
+        self.items[i]["dev_mixed"].stop()
+
+    def step(self, sample_rate, n):
+        ref = self.o.run(self.ref, sample_rate, n)
+        ref64 = self.ref_mixer.out64(n)
+        shape = (n, self.channels) if self.channels > 1 else (n,)
+        out = np.zeros(shape, dtype=F32)
+        self.odb.run(self.dev, sample_rate, out)
+        return ref, ref64, out
