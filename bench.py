@@ -165,6 +165,7 @@ def run_ours(args):
 
     def new_scene():
         ctl, scene = odb.SpatialScene.new(ctx)
+        scene.set_kernel_variant(args.variant)
         handles = []
         for i, g in enumerate(mine):
             handles.append(ctl.play(odb.FramesSignal(frames[i], START_S), odb.SpatialOptions(pos[g], vel[g], 0.1)))
@@ -276,7 +277,8 @@ def run_ours(args):
                        "sources": N, "frames": M, "rate": RATE, "parallelism": f"source-shard x{world}",
                        "l2": "inputs larger than L2: every callback reads fresh PCM "
                              f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
-                       "kernel_variant": "staged, strict (bit-exact per-source contributions)",
+                       "kernel_variant": ("staged, strict (bit-exact per-source contributions)" if args.variant == 0 else
+                                          "staged, value multiply-adds contracted to FMA (cursors and indices bit-exact)"),
                        "jobs_last_callback": counters, "setup_s": round(setup_s, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
@@ -284,7 +286,7 @@ def run_ours(args):
                     "note": "odb_scene_run with a host tile + set_motion on 1/16 of the sources every callback"},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_mix_fast<strict>", "kernel_ms": kernel_ms,
+                         "traffic": None, "kernel": "k_mix_fast<strict>" if args.variant == 0 else "k_mix_fast<fma>", "kernel_ms": kernel_ms,
                          "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "kernel_share_of_step": kernel_ms / (ms / K)},
             "checksum": checksum,
@@ -362,6 +364,7 @@ def main():
     ap.add_argument("--cpu-sources", type=int, default=2048, help="sources in the bounded CPU sample")
     ap.add_argument("--ref-sources", type=int, default=8192, help="sources in the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--variant", type=int, default=0, choices=[0, 2], help="0 = strict staged kernel, 2 = FMA-contracted value ops")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -78,26 +78,13 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds_f32_4(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ u64 lds_u64(uint32_t addr) {
-    u64 v;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
+// Shared-memory loads are plain C++ loads through the shared window (not `asm volatile`, which would pin
+// them in program order and serialise the eight unrolled frames of a chunk): the compiler is free to hoist
+// and interleave them between the barriers, which is where the kernel's instruction-level parallelism comes from.
+__device__ __forceinline__ float lds_f32(uint32_t addr) { return *reinterpret_cast<const float*>(__cvta_shared_to_generic(addr)); }
+__device__ __forceinline__ float lds_f32_4(uint32_t addr) { return *reinterpret_cast<const float*>(__cvta_shared_to_generic(addr + 4u)); }
+__device__ __forceinline__ u64 lds_u64(uint32_t addr) { return *reinterpret_cast<const u64*>(__cvta_shared_to_generic(addr)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(addr)); }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -123,6 +110,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 constexpr int FAST_WARPS = 12;                                              // one CTA per SM
+constexpr int FAST_ILP = 4;                                                 // frames of a chunk a lane processes interleaved
 constexpr int FAST_BATCH = 4;                                               // sources per warp batch: 4 x 2 ears x 4 chunks = 32 chains
 constexpr int FAST_PCM_BYTES = ODB_FAST_PCM_CAP * 4;                        // 5120, two of them per warp
 constexpr int FAST_POINTS = ODB_SPATIAL_CHUNK / 4;                          // every 4th cursor value of a chunk
@@ -147,51 +135,93 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
                                               const u64 d2, const u64 d3, const u64 fr_unit, const u64 pgp,
                                               const u64 dgp, const int nfr, const u64 nz) {
     const u64 magic = pk2(ODB_MAGIC, ODB_MAGIC);
+    // The 8 frames a lane owns in this chunk are independent; they are written stage by stage over groups of
+    // FAST_ILP frames so that the loads and the 4-cycle dependent FP32x2 steps of different frames interleave.
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j >= nfr) break;  // warp-uniform
-        uint32_t aL, aR;
-        u64 fr;
+    for (int j0 = 0; j0 < 8; j0 += FAST_ILP) {
+        if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j0 >= nfr) break;  // warp-uniform
+        uint32_t aL[FAST_ILP], aR[FAST_ILP];
+        u64 fr[FAST_ILP], o[FAST_ILP];
         if (!(UL && UR)) {
             // cursor of frame k = 32j + lane: checkpoint k & ~3, then (k & 3) literal `offset += ds` steps (frames.rs:195)
-            u64 o = lds_u64(row_sa + (uint32_t)(64 * j));
-            o = add2(o, d1);
-            o = add2(o, d2);
-            o = add2(o, d3);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) o[u] = lds_u64(row_sa + (uint32_t)(64 * (j0 + u)));
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) o[u] = add2(o[u], d1);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) o[u] = add2(o[u], d2);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) o[u] = add2(o[u], d3);
             // trunc = offset as isize; fract = offset - trunc as f32 (frames.rs:191-193), offset >= 0 here
-            const u64 t = add2_rm(o, magic);
-            const u64 fl = sub2(t, magic);
-            fr = sub2(o, fl);
-            uint32_t tL, tR;
-            upk2u(t, tL, tR);
-            aL = KL + (tL << 2);
-            aR = KR + (tR << 2);
+            u64 t[FAST_ILP];
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) t[u] = add2_rm(o[u], magic);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) {
+                uint32_t tL, tR;
+                upk2u(t[u], tL, tR);
+                aL[u] = KL + (tL << 2);
+                aR[u] = KR + (tR << 2);
+            }
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) fr[u] = sub2(o[u], sub2(t[u], magic));
         }
         if (UL || UR) {  // frames.rs:183-187
-            float f0, f1, u0, u1;
+            float u0, u1;
             upk2(fr_unit, u0, u1);
-            if (UL && UR) { f0 = u0; f1 = u1; }
-            else { upk2(fr, f0, f1); if (UL) f0 = u0; else f1 = u1; }
-            fr = pk2(f0, f1);
-            if (UL) aL = KL + (uint32_t)(128 * j);
-            if (UR) aR = KR + (uint32_t)(128 * j);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) {
+                float f0, f1;
+                if (UL && UR) { f0 = u0; f1 = u1; }
+                else { upk2(fr[u], f0, f1); if (UL) f0 = u0; else f1 = u1; }
+                fr[u] = pk2(f0, f1);
+                if (UL) aL[u] = KL + (uint32_t)(128 * (j0 + u));
+                if (UR) aR[u] = KR + (uint32_t)(128 * (j0 + u));
+            }
         }
-        const u64 a = pk2(lds_f32(aL), lds_f32(aR));      // get_pair (frames.rs:105-123); zeros come from the arena padding
-        const u64 b = pk2(lds_f32_4(aL), lds_f32_4(aR));
-        const u64 d = sub2(b, a);                          // frame::lerp = a + t * (b - a) (frame.rs:39-41)
-        const float fi = fbase + (float)(32 * j);          // `i as f32` (spatial.rs:459); exact small integer
-        const u64 fi2 = pk2(fi, fi);
-        u64 s, g;
+        u64 a[FAST_ILP], b[FAST_ILP];
+#pragma unroll
+        for (int u = 0; u < FAST_ILP; u++) {   // get_pair (frames.rs:105-123); zeros come from the arena padding
+            a[u] = pk2(lds_f32(aL[u]), lds_f32(aR[u]));
+            b[u] = pk2(lds_f32_4(aL[u]), lds_f32_4(aR[u]));
+        }
+        u64 g[FAST_ILP], s[FAST_ILP];
+#pragma unroll
+        for (int u = 0; u < FAST_ILP; u++) {
+            const float fi = fbase + (float)(32 * (j0 + u));  // `i as f32` (spatial.rs:459); exact small integer
+            const u64 fi2 = pk2(fi, fi);
+            if (STRICT) g[u] = mulx(fi2, dgp, nz);
+            else g[u] = fma2(fi2, dgp, pgp);
+        }
         if (STRICT) {
-            s = add2(a, mulx(fr, d, nz));
-            g = add2(pgp, mulx(fi2, dgp, nz));             // prev_state.gain + i as f32 * d_gain
-        } else {
-            s = fma2(fr, d, a);
-            g = fma2(fi2, dgp, pgp);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) g[u] = add2(pgp, g[u]);  // prev_state.gain + i as f32 * d_gain
         }
-        if (!FULL && c * ODB_SPATIAL_CHUNK + 32 * j + lane >= nfr) s = 0ull;  // frame beyond the tile: contributes +0
-        if (STRICT) acc[c * 8 + j] = add2(acc[c * 8 + j], mulx(s, g, nz));     // o[ear] += s * gain (spatial.rs:460)
-        else acc[c * 8 + j] = fma2(s, g, acc[c * 8 + j]);
+#pragma unroll
+        for (int u = 0; u < FAST_ILP; u++) b[u] = sub2(b[u], a[u]);     // frame::lerp = a + t * (b - a) (frame.rs:39-41)
+        if (STRICT) {
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) s[u] = mulx(fr[u], b[u], nz);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) s[u] = add2(a[u], s[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) s[u] = fma2(fr[u], b[u], a[u]);
+        }
+        if (!FULL) {
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++)
+                if (c * ODB_SPATIAL_CHUNK + 32 * (j0 + u) + lane >= nfr) s[u] = 0ull;  // frame beyond the tile: contributes +0
+        }
+        if (STRICT) {
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) s[u] = mulx(s[u], g[u], nz);
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) acc[c * 8 + j0 + u] = add2(acc[c * 8 + j0 + u], s[u]);  // o[ear] += s * gain (spatial.rs:460)
+        } else {
+#pragma unroll
+            for (int u = 0; u < FAST_ILP; u++) acc[c * 8 + j0 + u] = fma2(s[u], g[u], acc[c * 8 + j0 + u]);
+        }
     }
 }
 

@@ -45,20 +45,13 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 }
 
 // ------------------------------------------------------------------------------------------
-// walk_set for the seek set (spatial.rs:191-265) plus everything of the mix closure
-// (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
-// cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213). One thread per source.
-// Writes one OdbJob per (tile, source) and the source's state for the next callback.
-__global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
-                                                   OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
-                                                   int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cb.n_sources) return;
-    OdbSource* sp = src + order[idx];
-    OdbSource s = *sp;
-    const int n = cb.n_frames;
+// The part of walk_set that is common to both sets (spatial.rs:204-261) for one source: motion refresh,
+// smoothed start / end positions in the listener's frame, State::dt advance, finished_for / stopped
+// bookkeeping and the removal report. Returns false if the source is (now) stopped: it does not mix.
+__device__ __forceinline__ bool walk_common(OdbSource* sp, const OdbSource& s, const OdbCallback& cb, uint32_t slot,
+                                            uint32_t* __restrict__ removed, int removed_cap, V3& prev_position,
+                                            V3& next_position) {
     const float elapsed = cb.elapsed;
-
     // --- motion refresh, spatial.rs:216-226
     V3 pos = {s.pos[0], s.pos[1], s.pos[2]}, vel = {s.vel[0], s.vel[1], s.vel[2]};
     V3 statep = {s.prev_position[0], s.prev_position[1], s.prev_position[2]};
@@ -74,36 +67,58 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
         sp->vel[0] = vel.x; sp->vel[1] = vel.y; sp->vel[2] = vel.z;
     }
     // --- smoothed start/end positions in the listener's frame, spatial.rs:228-235
-    V3 prev_position = q_rotate(cb.prev_rot, smoothed_position(statep, state_dt, 0.0f, pos, vel));
-    V3 next_position = q_rotate(cb.rot, smoothed_position(statep, state_dt, elapsed, pos, vel));
+    prev_position = q_rotate(cb.prev_rot, smoothed_position(statep, state_dt, 0.0f, pos, vel));
+    next_position = q_rotate(cb.rot, smoothed_position(statep, state_dt, elapsed, pos, vel));
     state_dt = state_dt + elapsed;  // :238
     sp->prev_position[0] = statep.x; sp->prev_position[1] = statep.y; sp->prev_position[2] = statep.z;
     sp->state_dt = state_dt;
 
     // --- finished / stopped bookkeeping, spatial.rs:243-261
-    double t = s.t;
-    const double rate = s.rate;
-    bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
+    const bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
     if (!was_stopped) {
         float distance = v_norm(prev_position);
         if (flags & ODB_SF_HAS_FINISHED_FOR) {
             if (s.finished_for > distance / ODB_SPEED_OF_SOUND) flags |= ODB_SF_STOPPED;
             else sp->finished_for = s.finished_for + elapsed;
-        } else if (t >= (double)(s.len - 1) / rate) {  // FramesSignal::is_finished frames.rs:204-206
+        } else if (s.t >= (double)(s.len - 1) / s.rate) {  // inner.is_finished(): frames.rs:204-206 through the wrappers
             flags |= ODB_SF_HAS_FINISHED_FOR;
             sp->finished_for = elapsed;
         }
     }
     sp->flags = flags;
-    const int nt = cb.n_tiles, ns = cb.n_sources;
     if (flags & ODB_SF_STOPPED) {
         if (!was_stopped) {  // set.remove(i): report the slot so the host can swap_remove it from its Vec
             uint32_t k = atomicAdd(removed, 1u);
-            removed[1 + (k & (uint32_t)(removed_cap - 1))] = order[idx];
+            removed[1 + (k & (uint32_t)(removed_cap - 1))] = slot;
         }
+        return false;
+    }
+    return true;
+}
+
+// walk_set for the seek set (spatial.rs:191-265) plus everything of the mix closure
+// (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
+// cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213). One thread per source.
+// Writes one OdbJob per (tile, source) and the source's state for the next callback.
+__global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
+                                                   OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
+                                                   int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cb.n_sources) return;
+    const uint32_t slot = order[idx];
+    OdbSource* sp = src + slot;
+    OdbSource s = *sp;
+    const int n = cb.n_frames;
+    const float elapsed = cb.elapsed;
+    const int nt = cb.n_tiles, ns = cb.n_sources;
+    V3 prev_position, next_position;
+    if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position)) {
         for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
         return;
     }
+    const uint32_t flags = sp->flags;
+    double t = s.t;
+    const double rate = s.rate;
 
     // --- mix closure set-up, spatial.rs:446-468
     const float nf = (float)n;
@@ -178,13 +193,17 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
 }
 
 // ------------------------------------------------------------------------------------------
-// General mix kernel: exact for every parameter combination (any ds incl. <= 0, negative
-// offsets, FixedGain). One warp per (tile, source); lanes 0..7 each walk one (ear, chunk)
-// chain literally as FramesSignal::sample does (frames.rs:184-196) and write the per-frame
-// contribution s * gain (spatial.rs:459-460) into a warp-private smem tile; all 32 lanes then
-// fold the tile into register accumulators (lane l owns frames l, l+32, ...). Every operation
-// is a single unfused IEEE op in the reference's order, so a source's contribution is
-// bit-identical to the reference's.
+// General mix kernel: exact for every parameter combination (any ds incl. <= 0, negative offsets,
+// windows that leave the PCM block or exceed the staged kernel's buffers, FixedGain). One warp per
+// (tile, source):
+//   1. lanes 0..7 each walk one (ear, chunk) cursor chain literally, as FramesSignal::sample does
+//      (frames.rs:189-196), and park all 256 cursor values of their chain in warp-private shared memory;
+//   2. all 32 lanes (lane l owns frames l, l+32, ...) turn cursors into indices (`as isize` truncation)
+//      and fractions, read the sample pair from HBM with get_pair's bounds rules (frames.rs:105-123),
+//      lerp, apply FixedGain (gain.rs:35) and the per-frame gain (spatial.rs:459-460) and accumulate in
+//      registers.
+// Every operation is a single unfused IEEE op in the reference's order, so a source's contribution
+// is bit-identical to the reference's.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __restrict__ jobs, int n_sources,
                                                             float* __restrict__ partials, int only_flagged,
@@ -193,7 +212,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
     // nothing flagged for this kernel: leave at once; k_reduce_tiles reads the same counter and skips our tiles
     if (only_flagged && counters[ODB_CNT_GENERAL] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = smem + warp * (2 * ODB_TILE_FRAMES);
+    float* tile = smem + warp * (2 * ODB_TILE_FRAMES);  // cursors [ear][1024] while mixing, the partial tile at the end
     const int tl = blockIdx.y;
     const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
     float2 acc[ODB_TILE_FRAMES / 32];
@@ -205,45 +224,53 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
         const uint32_t jf = job->flags;
         if (jf & ODB_JF_SKIP) continue;
         if (only_flagged && !(jf & ODB_JF_GENERAL)) continue;
+        const int nfr = job->n_frames;
         if (lane < 2 * ODB_TILE_CHUNKS) {
             const int e = lane & 1, c = lane >> 1;
-            const float* __restrict__ pcm = job->pcm;
-            const int len = job->len;
-            const int m = max(0, min(ODB_SPATIAL_CHUNK, job->n_frames - c * ODB_SPATIAL_CHUNK));
-            const float ds = job->ds[e], pg = job->pg[e], dg = job->dg[e], fg = job->fixed_gain;
-            const long long base = job->base[e][c];
-            const bool fast = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
-            const bool has_fg = (jf & ODB_JF_FIXED_GAIN) != 0;
-            float offset = job->off0[e][c];
-            float fi = (float)(tl * ODB_TILE_FRAMES + c * ODB_SPATIAL_CHUNK);  // exact: small integers
-            for (int k = 0; k < ODB_SPATIAL_CHUNK; k++) {
-                float contrib = 0.0f;
-                if (k < m) {
-                    float a, b, fract;
-                    if (fast) {                                            // frames.rs:183-187
-                        get_pair_mono(pcm, len, base + k, a, b);
-                        fract = offset;
-                    } else {                                               // frames.rs:189-196
-                        long long tr = (long long)offset;
-                        get_pair_mono(pcm, len, base + tr, a, b);
-                        fract = offset - (float)tr;
-                        offset = offset + ds;
-                    }
-                    float smp = a + fract * (b - a);                       // frame.rs:39-41
-                    if (has_fg) smp = smp * fg;                            // gain.rs:35
-                    float gain = pg + fi * dg;                             // spatial.rs:459
-                    contrib = smp * gain;                                  // spatial.rs:460
-                    fi = fi + 1.0f;
+            const bool unit = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
+            if (!unit) {
+                const float ds = job->ds[e];
+                float offset = job->off0[e][c];
+                float* dst = tile + e * ODB_TILE_FRAMES + c * ODB_SPATIAL_CHUNK;
+                for (int k = 0; k < ODB_SPATIAL_CHUNK; k++) {
+                    dst[k] = offset;
+                    offset = offset + ds;                                  // frames.rs:195
                 }
-                tile[(c * ODB_SPATIAL_CHUNK + k) * 2 + e] = contrib;
             }
         }
         __syncwarp();
+        const float* __restrict__ pcm = job->pcm;
+        const int len = job->len;
+        const float fg = job->fixed_gain;
+        const bool has_fg = (jf & ODB_JF_FIXED_GAIN) != 0;
 #pragma unroll
-        for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) {
-            float2 v = *reinterpret_cast<const float2*>(tile + (32 * j + lane) * 2);
-            acc[j].x = acc[j].x + v.x;
-            acc[j].y = acc[j].y + v.y;
+        for (int e = 0; e < 2; e++) {
+            const bool unit = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
+            const float pg = job->pg[e], dg = job->dg[e];
+#pragma unroll
+            for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) {
+                const int c = j >> 3;
+                const int k = 32 * (j & 7) + lane, i = 32 * j + lane;
+                if (i < nfr) {
+                    const long long base = job->base[e][c];
+                    float a, b, fract;
+                    if (unit) {                                            // frames.rs:183-187
+                        get_pair_mono(pcm, len, base + k, a, b);
+                        fract = job->off0[e][c];
+                    } else {                                               // frames.rs:191-193
+                        const float offset = tile[e * ODB_TILE_FRAMES + i];
+                        const long long tr = (long long)offset;
+                        get_pair_mono(pcm, len, base + tr, a, b);
+                        fract = offset - (float)tr;
+                    }
+                    float smp = a + fract * (b - a);                       // frame.rs:39-41
+                    if (has_fg) smp = smp * fg;                            // gain.rs:35
+                    const float gain = pg + (float)(tl * ODB_TILE_FRAMES + i) * dg;  // spatial.rs:459
+                    const float contrib = smp * gain;                      // spatial.rs:460
+                    if (e == 0) acc[j].x = acc[j].x + contrib;
+                    else acc[j].y = acc[j].y + contrib;
+                }
+            }
         }
         __syncwarp();
     }
