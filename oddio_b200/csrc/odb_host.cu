@@ -344,6 +344,11 @@ int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait) {
         sh.motion_idx = sh.speed_idx = sh.gain_idx = -1;
         if (sh.frames) ctx->frames_unref(sh.frames);
         sh.frames = 0;
+        if (sh.ring_block >= 0) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->arena_unref(sh.ring_block);
+            sh.ring_block = -1;
+        }
         free_slots.push_back(slot);
     }
     order_dirty = true;
@@ -351,8 +356,13 @@ int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait) {
 }
 
 void SourceSet::release_all(odb_ctx* ctx) {
-    for (auto& sh : slots)
+    for (auto& sh : slots) {
         if (sh.in_use && sh.frames) ctx->frames_unref(sh.frames);
+        if (sh.in_use && sh.ring_block >= 0) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->arena_unref(sh.ring_block);
+        }
+    }
     slots.clear();
     d_src.release(); d_order.release(); d_stage_src.release(); d_stage_slot.release();
     d_motions.release(); d_params.release(); d_removed.release();

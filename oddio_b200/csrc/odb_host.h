@@ -117,6 +117,7 @@ struct SlotHost {
     bool stopped = false;   // Spatial::is_finished / Mixed::is_stopped as seen by the control side
     bool stop_requested = false;  // Mixed::stop() was called (mixer.rs:34-36); visible to is_stopped at once
     uint32_t chain_flags = 0;
+    int ring_block = -1;    // arena block of a buffered source's delay ring, -1 if none
     uint64_t n_frames = 0;  // FramesSignalControl::samples
     double rate = 0.0;
     // latest-wins de-duplication of queued control messages (swap.rs semantics): index into the

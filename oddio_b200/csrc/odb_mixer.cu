@@ -147,7 +147,7 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
             if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mixer_general launch failed: %s", cudaGetErrorString(e));
             launches++;
         }
-        odb_launch_reduce(mixer->d_partials_unit.p, n_unit, mixer->d_partials_gen.p, n_gen, mixer->d_counters.p,
+        odb_launch_reduce(mixer->d_partials_unit.p, n_unit, mixer->d_partials_gen.p, n_gen, nullptr, 0, mixer->d_counters.p,
                           n_unit > 0 ? 1 : 0, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
         launches++;
     }

@@ -24,6 +24,9 @@ struct odb_scene {
     DevBuf<float> d_partials;
     DevBuf<float> d_partials_fast;
     DevBuf<uint32_t> d_counters;
+    DevBuf<OdbRingJob> d_ring_jobs;
+    DevBuf<OdbRingWrite> d_ring_writes;
+    DevBuf<float> d_partials_ring;
     DevBuf<float> d_out;
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -50,6 +53,7 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     scene->seek.release_all(scene->ctx);
     scene->buffered.release_all(scene->ctx);
     scene->d_jobs.release(); scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_counters.release();
+    scene->d_ring_jobs.release(); scene->d_ring_writes.release(); scene->d_partials_ring.release();
     scene->d_out.release();
     scene->h_out.release();
     if (scene->ev0) { cudaEventDestroy(scene->ev0); cudaEventDestroy(scene->ev1); }
@@ -118,12 +122,66 @@ extern "C" int odb_scene_play(odb_scene* scene, const odb_chain* chain, const fl
     return ODB_OK;
 }
 
+// SpatialSceneControl::play_buffered (spatial.rs:314-340) + SpatialSignalBuffered::new (:30-56)
 extern "C" int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain, const float position[3],
                                        const float velocity[3], float radius, float max_distance, uint32_t rate,
                                        float buffer_duration, odb_source* out) {
     ODB_TRY(scene_check(scene));
-    (void)chain; (void)position; (void)velocity; (void)radius; (void)max_distance; (void)rate; (void)buffer_duration; (void)out;
-    return odb_fail(ODB_E_UNSUPPORTED, "play_buffered: device ring path not built yet");
+    if (!chain || !position || !velocity || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    if (rate == 0) return odb_fail(ODB_E_INVALID, "rate must be nonzero");
+    odb_ctx* ctx = scene->ctx;
+    OdbSource s;
+    FramesRec rec;
+    ODB_TRY(odb_make_source(ctx, chain, 1, &s, &rec));
+    s.radius = radius;
+    for (int k = 0; k < 3; k++) {
+        s.pos[k] = position[k]; s.vel[k] = velocity[k];
+        s.ppos[k] = position[k]; s.pvel[k] = velocity[k];
+        s.prev_position[k] = position[k];
+    }
+    s.state_dt = 0.0f;
+    const float max_delay = max_distance / 343.0f + buffer_duration;             // spatial.rs:330
+    const float capf = ceilf(max_delay * (float)rate);                           // spatial.rs:39
+    if (!(capf >= 1.0f) || capf > 268435456.0f) {
+        ctx->frames_unref(chain->frames);
+        return odb_fail(ODB_E_INVALID, "delay ring of %g samples is out of range", (double)capf);
+    }
+    const int cap = (int)capf + 1;
+    // Ring::new (ring.rs:10-15): zeroed buffer in HBM
+    float* ring = nullptr;
+    int block = -1;
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        rc = ctx->arena_alloc((size_t)cap * sizeof(float), &ring, &block);
+    }
+    if (rc != ODB_OK) {
+        ctx->frames_unref(chain->frames);
+        return rc;
+    }
+    ODB_CUDA(cudaMemsetAsync(ring, 0, (size_t)cap * sizeof(float), ctx->stream));
+    // queue.delay(rate, (norm(position) / SPEED_OF_SOUND).min(max_delay))   spatial.rs:40-43, ring.rs:45-47
+    float acc = 0.0f;
+    acc = acc + position[0] * position[0];
+    acc = acc + position[1] * position[1];
+    acc = acc + position[2] * position[2];
+    const float dist = sqrtf(acc);                                               // math/mod.rs:33-35
+    const float dt0 = fminf(dist / 343.0f, max_delay);
+    s.ring = ring;
+    s.ring_cap = cap;
+    s.ring_write = fmodf(0.0f + (float)rate * dt0, (float)cap);                  // ring.rs:46
+    s.max_delay = max_delay;
+    s.ring_rate = rate;
+    std::lock_guard<std::mutex> lk(scene->mu);
+    uint32_t slot = scene->buffered.alloc_slot();
+    SlotHost& sh = scene->buffered.slots[slot];
+    sh.frames = chain->frames; sh.chain_flags = chain->flags; sh.n_frames = rec.n_frames; sh.rate = (double)rec.rate;
+    sh.ring_block = block;
+    scene->buffered.ins_src.push_back(s);
+    scene->buffered.ins_slot.push_back(slot);
+    *out = scene->buffered.handle_of(slot, ODB_TAG_BUFFERED);
+    return ODB_OK;
 }
 
 // SpatialSceneControl::set_listener_rotation, spatial.rs:345-349 (stores the conjugate, math/mod.rs:62-67)
@@ -204,6 +262,8 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         std::lock_guard<std::mutex> lk(scene->mu);
         // removals reported by earlier callbacks whose read-back has landed (never waits for the device)
         ODB_TRY(scene->seek.fold_removed(ctx, st, false));
+        ODB_TRY(scene->buffered.fold_removed(ctx, st, false));
+        ODB_TRY(scene->buffered.apply(ctx, st, &launches));                 // set.update(), spatial.rs:379
         ODB_TRY(scene->seek.apply(ctx, st, &launches));                     // set.update(), spatial.rs:437
         cb.prev_rot = scene->rot_received;                                 // spatial.rs:382-386
         if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
@@ -224,6 +284,26 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs.p, scene->seek.d_removed.p,
                              (int)scene->seek.removed_cap, scene->d_counters.p, cb, st);
         launches++;
+    }
+    // buffered set first (spatial.rs:395-433): walk, extend the delay rings, mix from the rings
+    const int nb = (int)scene->buffered.order.size();
+    int n_ring = 0;
+    if (nb > 0) {
+        OdbCallback cbb = cb;
+        cbb.n_sources = nb;
+        ODB_TRY(scene->d_ring_jobs.ensure((size_t)nb * (nt > 0 ? nt : 1), st, false));
+        ODB_TRY(scene->d_ring_writes.ensure((size_t)nb, st, false));
+        odb_launch_walk_buffered(scene->buffered.d_src.p, scene->buffered.d_order.p, scene->d_ring_jobs.p,
+                                 scene->d_ring_writes.p, scene->buffered.d_removed.p, (int)scene->buffered.removed_cap, cbb, st);
+        odb_launch_ring_write(scene->d_ring_writes.p, nb, st);
+        launches += 2;
+        if (nt > 0) {
+            n_ring = odb_mix_ring_ctas(nb, ctx->sm_count);
+            ODB_TRY(scene->d_partials_ring.ensure((size_t)nt * n_ring * 2 * ODB_TILE_FRAMES, st, false));
+            cudaError_t e = odb_launch_mix_ring(scene->d_ring_jobs.p, nb, nt, scene->d_partials_ring.p, n_ring, st);
+            if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_ring launch failed: %s", cudaGetErrorString(e));
+            launches++;
+        }
     }
     if (nt > 0) {
         int n_fast = 0, n_gen = 0;
@@ -247,13 +327,15 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_general launch failed: %s", cudaGetErrorString(e));
             launches++;
         }
-        odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_counters.p,
+        odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_partials_ring.p, n_ring,
+                          scene->d_counters.p,
                           /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }
     {   // start the read-back of what walk_set removed; folded in by a later call without waiting
         std::lock_guard<std::mutex> lk(scene->mu);
         ODB_TRY(scene->seek.post_callback(ctx, st));
+        ODB_TRY(scene->buffered.post_callback(ctx, st));
     }
     scene->last_launches = launches;
     ODB_CUDA(cudaGetLastError());
@@ -273,6 +355,7 @@ extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, ui
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
     std::lock_guard<std::mutex> lk(scene->mu);
+    ODB_TRY(scene->buffered.fold_removed(ctx, ctx->stream, true));
     return scene->seek.fold_removed(ctx, ctx->stream, true);  // like the reference, removals are visible when sample returns
 }
 // oddio::run, lib.rs:90-93

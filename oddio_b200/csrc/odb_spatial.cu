@@ -45,57 +45,6 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 }
 
 // ------------------------------------------------------------------------------------------
-// The part of walk_set that is common to both sets (spatial.rs:204-261) for one source: motion refresh,
-// smoothed start / end positions in the listener's frame, State::dt advance, finished_for / stopped
-// bookkeeping and the removal report. Returns false if the source is (now) stopped: it does not mix.
-__device__ __forceinline__ bool walk_common(OdbSource* sp, const OdbSource& s, const OdbCallback& cb, uint32_t slot,
-                                            uint32_t* __restrict__ removed, int removed_cap, V3& prev_position,
-                                            V3& next_position) {
-    const float elapsed = cb.elapsed;
-    // --- motion refresh, spatial.rs:216-226
-    V3 pos = {s.pos[0], s.pos[1], s.pos[2]}, vel = {s.vel[0], s.vel[1], s.vel[2]};
-    V3 statep = {s.prev_position[0], s.prev_position[1], s.prev_position[2]};
-    float state_dt = s.state_dt;
-    uint32_t flags = s.flags;
-    if (flags & ODB_SF_MOTION_FRESH) {
-        V3 npos = {s.ppos[0], s.ppos[1], s.ppos[2]}, nvel = {s.pvel[0], s.pvel[1], s.pvel[2]};
-        statep = (flags & ODB_SF_PENDING_DISC) ? npos : smoothed_position(statep, state_dt, 0.0f, pos, vel);
-        state_dt = 0.0f;
-        pos = npos; vel = nvel;
-        flags &= ~ODB_SF_MOTION_FRESH;
-        sp->pos[0] = pos.x; sp->pos[1] = pos.y; sp->pos[2] = pos.z;
-        sp->vel[0] = vel.x; sp->vel[1] = vel.y; sp->vel[2] = vel.z;
-    }
-    // --- smoothed start/end positions in the listener's frame, spatial.rs:228-235
-    prev_position = q_rotate(cb.prev_rot, smoothed_position(statep, state_dt, 0.0f, pos, vel));
-    next_position = q_rotate(cb.rot, smoothed_position(statep, state_dt, elapsed, pos, vel));
-    state_dt = state_dt + elapsed;  // :238
-    sp->prev_position[0] = statep.x; sp->prev_position[1] = statep.y; sp->prev_position[2] = statep.z;
-    sp->state_dt = state_dt;
-
-    // --- finished / stopped bookkeeping, spatial.rs:243-261
-    const bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
-    if (!was_stopped) {
-        float distance = v_norm(prev_position);
-        if (flags & ODB_SF_HAS_FINISHED_FOR) {
-            if (s.finished_for > distance / ODB_SPEED_OF_SOUND) flags |= ODB_SF_STOPPED;
-            else sp->finished_for = s.finished_for + elapsed;
-        } else if (s.t >= (double)(s.len - 1) / s.rate) {  // inner.is_finished(): frames.rs:204-206 through the wrappers
-            flags |= ODB_SF_HAS_FINISHED_FOR;
-            sp->finished_for = elapsed;
-        }
-    }
-    sp->flags = flags;
-    if (flags & ODB_SF_STOPPED) {
-        if (!was_stopped) {  // set.remove(i): report the slot so the host can swap_remove it from its Vec
-            uint32_t k = atomicAdd(removed, 1u);
-            removed[1 + (k & (uint32_t)(removed_cap - 1))] = slot;
-        }
-        return false;
-    }
-    return true;
-}
-
 // walk_set for the seek set (spatial.rs:191-265) plus everything of the mix closure
 // (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
 // cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213). One thread per source.
@@ -128,7 +77,6 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     long long wlo[4], whi[4];           // per tile: PCM index range both ears can touch
     for (int tl = 0; tl < 4; tl++) { wlo[tl] = (1ll << 40); whi[tl] = -(1ll << 40); }
     long long sample_t = s.sample_t;
-    bool fast_e[2];
     for (int e = 0; e < 2; e++) {
         EarSt ps = ear_state(prev_position, e, s.radius);
         EarSt nx = ear_state(next_position, e, s.radius);
@@ -138,7 +86,6 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
         float d_gain = (nx.gain - ps.gain) / nf;                      // :453
         float ds = dt * ratef;                                        // frames.rs:178
         bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
-        fast_e[e] = fast;
         bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
         for (int cg = 0; cg < n_chunks; cg++) {
             int tl = cg / ODB_TILE_CHUNKS, c = cg % ODB_TILE_CHUNKS;
@@ -295,6 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
 #define RED_GROUPS 8
 __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* __restrict__ pa, int na,
                                                                  const float* __restrict__ pb, int nb,
+                                                                 const float* __restrict__ pc, int nc,
                                                                  const uint32_t* __restrict__ counters, int b_is_general,
                                                                  float* __restrict__ out, int n_frames, int channels,
                                                                  int epilogue) {
@@ -309,6 +257,8 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
     for (int i = grp; i < na; i += RED_GROUPS) sum = sum + p[(size_t)i * tile_floats];
     const float* q = pb + (size_t)tl * nb * tile_floats + f;
     for (int i = grp; i < nb; i += RED_GROUPS) sum = sum + q[(size_t)i * tile_floats];
+    const float* r = pc + (size_t)tl * nc * tile_floats + f;
+    for (int i = grp; i < nc; i += RED_GROUPS) sum = sum + r[(size_t)i * tile_floats];
     fold[grp][lane] = sum;
     __syncthreads();
     if (grp != 0) return;
@@ -366,9 +316,9 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
     k_mix_general<GEN_WARPS><<<grid, GEN_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged, counters);
     return cudaGetLastError();
 }
-void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const uint32_t* counters, int b_is_general,
-                       float* out, int n_frames, int n_tiles, int channels, int epilogue, cudaStream_t st) {
+void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const float* pc, int nc, const uint32_t* counters,
+                       int b_is_general, float* out, int n_frames, int n_tiles, int channels, int epilogue, cudaStream_t st) {
     if (n_frames <= 0) return;
     dim3 grid(channels * ODB_TILE_FRAMES / 32, n_tiles);
-    k_reduce_tiles<<<grid, 32 * RED_GROUPS, 0, st>>>(pa, na, pb, nb, counters, b_is_general, out, n_frames, channels, epilogue);
+    k_reduce_tiles<<<grid, 32 * RED_GROUPS, 0, st>>>(pa, na, pb, nb, pc, nc, counters, b_is_general, out, n_frames, channels, epilogue);
 }

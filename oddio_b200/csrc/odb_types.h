@@ -96,11 +96,38 @@ struct __attribute__((aligned(16))) OdbMixJob {
     uint32_t pad[2];
 };
 static_assert(sizeof(OdbMixJob) == 64, "OdbMixJob is half a 128-byte line");
+// Buffered (play_buffered) sources: what one (source, 1024-frame tile) pass of k_mix_ring needs. 128 bytes.
+struct __attribute__((aligned(16))) OdbRingJob {
+    const float* ring;              // Ring::buffer (ring.rs:5)
+    int cap;                        // buffer.len()
+    uint32_t flags;                 // ODB_JF_SKIP
+    float ds[2];                    // per ear: dt * rate as f32 (ring.rs:58)
+    float pg[2];                    // prev_state.gain
+    float dg[2];                    // d_gain (spatial.rs:418)
+    float off0[2][ODB_TILE_CHUNKS]; // per ear, per 256-chunk: (write + t * rate).rem_euclid(len) (ring.rs:57)
+    int n_frames;
+    uint32_t pad[13];
+};
+static_assert(sizeof(OdbRingJob) == 128, "OdbRingJob is one 128-byte line");
+// What Ring::write (ring.rs:18-41) hands to inner.sample() for one buffered source and callback: one or two spans.
+struct __attribute__((aligned(16))) OdbRingWrite {
+    float* ring;
+    const float* pcm;
+    int cap, len;
+    uint32_t flags;       // ODB_JF_SKIP / ODB_JF_FAST_L (ds ~= 1 path) / ODB_JF_RAMP (span 0) / ODB_JF_RAMP1 (span 1)
+    float ds;             // (interval * speed) * pcm rate as f32, interval = 1 / ring rate
+    float fixed_gain, gstep;
+    int start[2], n[2], base[2];
+    float off0[2];
+    float g[2];
+    float gprev[2], gnext[2], gprog[2];
+};
 #define ODB_JF_SKIP 0x1u        // source removed/stopped this callback: contributes nothing
 #define ODB_JF_FAST_L 0x2u      // |ds-1| <= EPSILON for the left ear (frames.rs:180)
 #define ODB_JF_FAST_R 0x4u
 #define ODB_JF_FIXED_GAIN 0x8u
 #define ODB_JF_RAMP 0x20u       // mixer: Gain is mid-transition during this chunk (gain.rs:118-121)
+#define ODB_JF_RAMP1 0x40u      // ring write: Gain is mid-transition during the second span
 #define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
 
 // Device counters written by the walk kernels each callback (uint32 each).
