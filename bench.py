@@ -17,8 +17,11 @@ the sources every callback, H2D inside the timed region); `roofline` = algorithm
 staged mix kernel / its device time against the measured HBM peak; `cpu_baseline` = the CPU oracle
 (the only runnable statement of the Rust reference here) on a bounded sample of the same workload.
 
-N > 1: sources are sharded round-robin over the ranks (strong scaling: the 65 536 sources are the
-job); each callback ends with one NCCL all-reduce (sum) of the 8 KiB stereo tile.
+N > 1: one process per GPU; every rank mixes its own shard of the scene's sources and each callback ends
+with a sum all-reduce of the 8 KiB stereo tile. The sum is linear, so `--reduce-every R` (default 8, the offline
+rendering shape of examples/offline.rs) exchanges R tiles in one NCCL all-reduce issued on a second stream that
+overlaps the next callbacks' mixes; the timed region ends after the last all-reduce. R = 1 is live playback. Default `--scaling weak`: 65 536 sources per GPU (the scene grows with
+the box); `--scaling strong`: the 65 536 sources are split over the ranks.
 """
 from __future__ import annotations
 
@@ -138,9 +141,12 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = odb.Context(local, stream=stream.cuda_stream)  # our kernels and NCCL share one stream: no extra events
 
-    N, M, K, W = args.sources, args.frames, args.steps, args.warmup
+    from oddio_b200.sharding import shard_sources
+
+    M, K, W = args.frames, args.steps, args.warmup
+    N = args.sources * world if args.scaling == "weak" else args.sources  # sources of the whole job
     pos, vel, freq, phase = scene_geometry(N)
-    mine = np.arange(rank, N, world)  # round-robin shard
+    mine = shard_sources(N, rank, world)  # round-robin shard
     n_local = len(mine)
     L = pcm_len(M, K + W)
 
@@ -172,12 +178,43 @@ def run_ours(args):
         return ctl, scene, handles
 
     interval = float(np.float32(1.0) / np.float32(RATE))  # oddio::run, lib.rs:91
-    tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+    # Offline rendering batches R consecutive callbacks per exchange: the sum over ranks is linear, so one
+    # all-reduce of R tiles equals R all-reduces of one tile. R = 1 is the live-playback shape.
+    R = max(1, args.reduce_every) if world > 1 else 1
+    groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(2)]
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    mixed = [torch.cuda.Event() for _ in range(2)]
+    reduced = [torch.cuda.Event() for _ in range(2)]
+    step_no = [0]
 
     def step_device(scene):
-        scene.sample_device(interval, tile.data_ptr(), M)
+        """One callback: mix this rank's shard into slot k%R of group (k/R)%2 on `stream`; after R callbacks
+        the NCCL sum of the group runs on `comm` and overlaps the next group's mixes."""
+        k = step_no[0]
+        step_no[0] += 1
+        g, slot = (k // R) % 2, k % R
+        if world > 1 and slot == 0:
+            stream.wait_event(reduced[g])  # the group buffer is free again once its previous all-reduce is done
+        scene.sample_device(interval, groups[g][slot].data_ptr(), M)
+        if world > 1 and slot == R - 1:
+            mixed[g].record(stream)
+            comm.wait_event(mixed[g])
+            with torch.cuda.stream(comm):
+                dist.all_reduce(groups[g])
+                reduced[g].record(comm)
+
+    def drain():
         if world > 1:
-            dist.all_reduce(tile)  # one NCCL sum of the 8 KiB tile per callback
+            k = step_no[0]
+            if k % R:  # flush a partial group
+                g = (k // R) % 2
+                mixed[g].record(stream)
+                comm.wait_event(mixed[g])
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(groups[g])
+                    reduced[g].record(comm)
+                step_no[0] += R - k % R
+            stream.wait_stream(comm)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -191,6 +228,7 @@ def run_ours(args):
         setup_s = time.time() - t_setup
         for _ in range(W):
             step_device(scene)
+        drain()
         launches_per_step = scene.last_launch_count() + (1 if world > 1 else 0)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -198,6 +236,7 @@ def run_ours(args):
             e0.record(stream)
             for _ in range(K):
                 step_device(scene)
+            drain()
             e1.record(stream)
             barrier()
         ms = e0.elapsed_time(e1)
@@ -205,7 +244,7 @@ def run_ours(args):
         # the rare source with exactly one ear on FramesSignal's ds ~= 1 path takes the literal kernel
         assert counters["general"] <= max(1, n_local // 1000), f"{counters['general']} jobs fell back to the general kernel"
         assert scene.len() == n_local, "a source finished during the timed region"
-        checksum = float(tile.abs().sum().item())
+        checksum = float(groups[((step_no[0] - 1) // R) % 2][(step_no[0] - 1) % R].abs().sum().item())
         scene.close()
 
         # ---- (2) mix-kernel device time for the roofline (separate pass: events around the kernel) ------------
@@ -216,6 +255,7 @@ def run_ours(args):
             step_device(scene)
             if i >= W:
                 kms.append(scene.last_mix_kernel_ms())
+        drain()
         scene.close()
 
         # ---- (3) end to end through the host-buffer call --------------------------------------------------------
@@ -262,19 +302,20 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = peaks()
         # algorithmic bytes: the PCM window, once per source per callback: 4 B * M * mean(ds)
-        r = pos / np.linalg.norm(pos, axis=1, keepdims=True)
-        ds_mean = float(np.mean(1.0 - np.sum(vel * r, axis=1) / 343.0))
+        r = pos[mine] / np.linalg.norm(pos[mine], axis=1, keepdims=True)
+        ds_mean = float(np.mean(1.0 - np.sum(vel[mine] * r, axis=1) / 343.0))
         alg_bytes = 4.0 * M * ds_mean * n_local
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         value = N * M / (ms / K * 1e-3)
         out = {
             "metric": "source-frames/sec (N sources x buffer frames) spatial mix",
             "value": value, "unit": "source-frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
                                    f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
-                       "sources": N, "frames": M, "rate": RATE, "parallelism": f"source-shard x{world}",
+                       "sources": N, "sources_per_gpu": n_local, "frames": M, "rate": RATE,
+                       "parallelism": f"source-shard x{world}" + (f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes" if world > 1 else ""),
                        "l2": "inputs larger than L2: every callback reads fresh PCM "
                              f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
                        "kernel_variant": ("staged, strict (bit-exact per-source contributions)" if args.variant == 0 else
@@ -337,11 +378,12 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     t0 = time.time()
     base = cpu_baseline(args, threads=threads, n=args.ref_sources, reps=args.steps, warm=args.warmup)
-    N, M = args.sources, args.frames
+    M = args.frames
+    N = args.sources * args.gpus if args.scaling == "weak" else args.sources
     line = {
         "impl": "reference", "metric": "source-frames/sec (N sources x buffer frames) spatial mix",
         "value": base["value"], "unit": "source-frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": N * M / base["value"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": N * M / base["value"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
                                f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
@@ -364,6 +406,9 @@ def main():
     ap.add_argument("--cpu-sources", type=int, default=2048, help="sources in the bounded CPU sample")
     ap.add_argument("--ref-sources", type=int, default=8192, help="sources in the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --sources per GPU (default), strong = --sources in total")
+    ap.add_argument("--reduce-every", type=int, default=8, help="N > 1: callbacks per all-reduce (1 = live playback)")
     ap.add_argument("--variant", type=int, default=0, choices=[0, 2], help="0 = strict staged kernel, 2 = FMA-contracted value ops")
     args = ap.parse_args()
     if args.warmup < 3:
