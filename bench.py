@@ -47,6 +47,28 @@ SPEED_MAX = 50.0       # m/s  (examples/offline.rs:4 uses 50 m/s)
 DS_MAX = 1.0 + SPEED_MAX / 343.0 + 0.01
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    f = _REAL_STDOUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
+def ncu_traffic(kernel: str, n_local: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/),
+    scaled to this run's source count; None if no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f).get(kernel)
+    if not t:
+        return None
+    return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n_local / 65536.0
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -234,9 +256,11 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
             e0.record(stream)
+            h0 = time.perf_counter()
             for _ in range(K):
                 step_device(scene)
             drain()
+            host_enqueue_us = (time.perf_counter() - h0) / K * 1e6  # CPU time to queue one callback (GPU runs behind)
             e1.record(stream)
             barrier()
         ms = e0.elapsed_time(e1)
@@ -320,21 +344,22 @@ def run_ours(args):
                              f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
                        "kernel_variant": ("staged, strict (bit-exact per-source contributions)" if args.variant == 0 else
                                           "staged, value multiply-adds contracted to FMA (cursors and indices bit-exact)"),
-                       "jobs_last_callback": counters, "setup_s": round(setup_s, 1)},
+                       "jobs_last_callback": counters, "host_enqueue_us_per_step": round(host_enqueue_us, 1),
+                       "setup_s": round(setup_s, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
                     "h2d_bytes_per_step": n_upd * 32, "d2h_bytes_per_step": M * 8 + 4,
                     "note": "odb_scene_run with a host tile + set_motion on 1/16 of the sources every callback"},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_mix_fast<strict>" if args.variant == 0 else "k_mix_fast<fma>", "kernel_ms": kernel_ms,
+                         "traffic": ncu_traffic("k_mix_fast", n_local), "kernel": "k_mix_fast<strict>" if args.variant == 0 else "k_mix_fast<fma>", "kernel_ms": kernel_ms,
                          "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "kernel_share_of_step": kernel_ms / (ms / K)},
             "checksum": checksum,
         }
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, threads=1, n=args.cpu_sources)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -392,10 +417,16 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": "source-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(time.time() - t0, 1),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # Exactly one JSON line may reach stdout: libraries that print there (NCCL's version banner) are sent to
+    # stderr by pointing fd 1 at fd 2 for the whole run; the result line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)

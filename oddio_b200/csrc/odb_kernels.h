@@ -36,7 +36,7 @@ int odb_mix_general_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
                                    int only_flagged, const uint32_t* counters, cudaStream_t st);
 int odb_mix_fast_ctas(int n_sources, int sm_count);
-cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int strict,
+cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int mode,
                                 cudaStream_t st);
 void odb_launch_walk_mixer(OdbSource* src, const uint32_t* order, OdbMixJob* jobs, uint32_t* removed, int removed_cap,
                            uint32_t* counters, const OdbCallback& cb, cudaStream_t st);

@@ -153,6 +153,8 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
 #pragma unroll
             for (int u = 0; u < FAST_ILP; u++) o[u] = add2(o[u], d3);
             // trunc = offset as isize; fract = offset - trunc as f32 (frames.rs:191-193), offset >= 0 here
+            // all-FP32 index split: a round-down add of 2^23 leaves trunc(offset) in the low mantissa bits. (An
+            // F2I.TRUNC / I2FP split was measured 8 % slower: the conversions are not full rate on sm_100a.)
             u64 t[FAST_ILP];
 #pragma unroll
             for (int u = 0; u < FAST_ILP; u++) t[u] = add2_rm(o[u], magic);
@@ -165,6 +167,7 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
             }
 #pragma unroll
             for (int u = 0; u < FAST_ILP; u++) fr[u] = sub2(o[u], sub2(t[u], magic));
+
         }
         if (UL || UR) {  // frames.rs:183-187
             float u0, u1;
@@ -247,8 +250,10 @@ __device__ __forceinline__ void consume_source(u64* __restrict__ acc, const int 
     }
 }
 
+// 152 registers x 384 threads leave room in the register file for one 64-thread walk CTA per SM, so the next
+// callback's k_walk_seek can run underneath this kernel.
 template <bool STRICT>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
+__global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
                                                                   float* __restrict__ partials, const u64 nz) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -380,13 +385,18 @@ int odb_mix_fast_ctas(int n_sources, int sm_count) {
     return want < 1 ? 1 : (want > sm_count ? sm_count : want);
 }
 
-cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int strict,
-                                cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(strict ? k_mix_fast<true> : k_mix_fast<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+template <bool STRICT>
+static cudaError_t launch_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_mix_fast<STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     dim3 grid(n_ctas, n_tiles);
-    if (strict) k_mix_fast<true><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
-    else k_mix_fast<false><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
+    k_mix_fast<STRICT><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
     return cudaGetLastError();
+}
+
+// mode bit 0: value multiply-adds contracted to FMA
+cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int mode,
+                                cudaStream_t st) {
+    return (mode & 1) ? launch_fast<false>(jobs, n_sources, n_tiles, partials, n_ctas, st)
+                      : launch_fast<true>(jobs, n_sources, n_tiles, partials, n_ctas, st);
 }

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cb.n_sources) return;
     OdbSource* sp = src + order[idx];
-    OdbSource s = *sp;
+    OdbSource s;
+    load_source(s, sp);
     const int ns = cb.n_sources, nt = cb.n_tiles;
     uint32_t flags = s.flags;
     const bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
     const double rate = s.rate;
     // mixer.rs:102: `signal.stop.load() || signal.inner.is_finished()`; is_finished forwards through
     // Gain / FixedGain / Speed (gain.rs:39-41,:124-126, speed.rs:37-39) to frames.rs:204-206
-    if (was_stopped || (flags & ODB_SF_STOP_REQ) || t >= (double)(s.len - 1) / rate) {
+    if (was_stopped || (flags & ODB_SF_STOP_REQ) || t >= s.t_end) {
         if (!was_stopped) {
             uint32_t k = atomicAdd(removed, 1u);
             removed[1 + (k & (uint32_t)(removed_cap - 1))] = order[idx];

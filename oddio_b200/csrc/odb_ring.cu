@@ -26,16 +26,17 @@ __global__ void __launch_bounds__(128) k_walk_buffered(OdbSource* __restrict__ s
     if (idx >= cb.n_sources) return;
     const uint32_t slot = order[idx];
     OdbSource* sp = src + slot;
-    OdbSource s = *sp;
+    OdbSource s;
+    load_source(s, sp);
     const int n = cb.n_frames, nt = cb.n_tiles, ns = cb.n_sources;
     const float elapsed = cb.elapsed;
     V3 prev_position, next_position;
-    if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position)) {
+    uint32_t flags;
+    if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position, flags)) {
         for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
         writes[idx].flags = ODB_JF_SKIP;
         return;
     }
-    const uint32_t flags = sp->flags;
 
     // --- queue.write(&mut inner, rate, elapsed), ring.rs:18-41
     const float ratef = (float)s.ring_rate;

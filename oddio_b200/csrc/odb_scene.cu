@@ -20,12 +20,18 @@ struct odb_scene {
     int epilogue = ODB_EPILOGUE_NONE;
     int variant = 0;
     uint32_t last_launches = 0;
-    DevBuf<OdbJob> d_jobs;
+    // Two-stage pipeline: the per-source set-up of callback k+1 (control-plane scatter + walk kernels, on the
+    // scene's own `wst` stream) overlaps the mix kernels of callback k (on the context's stream). What the walk
+    // kernels hand to the mix kernels is double-buffered by callback parity.
+    cudaStream_t wst = nullptr;
+    cudaEvent_t ev_walk[2] = {nullptr, nullptr}, ev_mix[2] = {nullptr, nullptr};
+    uint64_t callback_no = 0;
+    DevBuf<OdbJob> d_jobs[2];
+    DevBuf<uint32_t> d_counters[2];
+    DevBuf<OdbRingJob> d_ring_jobs[2];
+    DevBuf<OdbRingWrite> d_ring_writes[2];
     DevBuf<float> d_partials;
     DevBuf<float> d_partials_fast;
-    DevBuf<uint32_t> d_counters;
-    DevBuf<OdbRingJob> d_ring_jobs;
-    DevBuf<OdbRingWrite> d_ring_writes;
     DevBuf<float> d_partials_ring;
     DevBuf<float> d_out;
     bool profiling = false;
@@ -40,8 +46,14 @@ static int scene_check(odb_scene* s) {
 
 extern "C" int odb_scene_create(odb_ctx* ctx, odb_scene** out) {
     if (!ctx || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    ODB_CUDA(cudaSetDevice(ctx->device));
     odb_scene* s = new odb_scene();
     s->ctx = ctx;
+    ODB_CUDA(cudaStreamCreateWithFlags(&s->wst, cudaStreamNonBlocking));
+    for (int p = 0; p < 2; p++) {
+        ODB_CUDA(cudaEventCreateWithFlags(&s->ev_walk[p], cudaEventDisableTiming));
+        ODB_CUDA(cudaEventCreateWithFlags(&s->ev_mix[p], cudaEventDisableTiming));
+    }
     *out = s;
     return ODB_OK;
 }
@@ -49,11 +61,17 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     if (!scene) return ODB_OK;
     ODB_TRY(scene_check(scene));
     cudaSetDevice(scene->ctx->device);
+    cudaStreamSynchronize(scene->wst);
     cudaStreamSynchronize(scene->ctx->stream);
     scene->seek.release_all(scene->ctx);
     scene->buffered.release_all(scene->ctx);
-    scene->d_jobs.release(); scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_counters.release();
-    scene->d_ring_jobs.release(); scene->d_ring_writes.release(); scene->d_partials_ring.release();
+    for (int p = 0; p < 2; p++) {
+        scene->d_jobs[p].release(); scene->d_counters[p].release();
+        scene->d_ring_jobs[p].release(); scene->d_ring_writes[p].release();
+        cudaEventDestroy(scene->ev_walk[p]); cudaEventDestroy(scene->ev_mix[p]);
+    }
+    cudaStreamDestroy(scene->wst);
+    scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_partials_ring.release();
     scene->d_out.release();
     scene->h_out.release();
     if (scene->ev0) { cudaEventDestroy(scene->ev0); cudaEventDestroy(scene->ev1); }
@@ -81,6 +99,7 @@ int odb_make_source(odb_ctx* ctx, const odb_chain* chain, int want_channels, Odb
     s.pcm = rec->dev;
     s.rate = (double)rec->rate;                                   // frames.rs:40
     s.t = chain->start_seconds;                                   // frames.rs:159
+    s.t_end = (double)(rec->n_frames - 1) / s.rate;               // frames.rs:205, evaluated once
     s.sample_t = (long long)(chain->start_seconds * s.rate);      // frames.rs:160
     s.len = (int)rec->n_frames;
     s.channels = rec->channels;
@@ -250,21 +269,35 @@ extern "C" int odb_scene_len(odb_scene* scene, int buffered, uint64_t* out) {
 
 // <SpatialScene as Signal>::sample, spatial.rs:376-471. Leaves the mixed tile in scene->d_out (or
 // `dev_out` when given) on the context's stream.
+// Grows a device buffer that kernels on either stream may still be using: both streams are drained first.
+template <class T>
+static int ensure_idle(odb_scene* scene, DevBuf<T>& buf, size_t n) {
+    if (n <= buf.cap) return ODB_OK;
+    ODB_CUDA(cudaStreamSynchronize(scene->wst));
+    ODB_CUDA(cudaStreamSynchronize(scene->ctx->stream));
+    return buf.ensure(n, scene->ctx->stream, false);
+}
+
 static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames) {
     odb_ctx* ctx = scene->ctx;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->stream, wst = scene->wst;
     if (n_frames > ODB_MAX_FRAMES)
         return odb_fail(ODB_E_UNSUPPORTED, "n_frames %u exceeds the %d frames one callback may render", n_frames, ODB_MAX_FRAMES);
     ODB_CUDA(cudaSetDevice(ctx->device));
     uint32_t launches = 0;
+    const int p = (int)(scene->callback_no & 1);
+    scene->callback_no++;
+    // ---- stage 1 on `wst`: everything that is per source and O(1) per chunk -------------------------------------
+    // this parity's job / counter buffers are free once the mix of two callbacks ago has finished
+    ODB_CUDA(cudaStreamWaitEvent(wst, scene->ev_mix[p], 0));
     OdbCallback cb;
     {
         std::lock_guard<std::mutex> lk(scene->mu);
         // removals reported by earlier callbacks whose read-back has landed (never waits for the device)
-        ODB_TRY(scene->seek.fold_removed(ctx, st, false));
-        ODB_TRY(scene->buffered.fold_removed(ctx, st, false));
-        ODB_TRY(scene->buffered.apply(ctx, st, &launches));                 // set.update(), spatial.rs:379
-        ODB_TRY(scene->seek.apply(ctx, st, &launches));                     // set.update(), spatial.rs:437
+        ODB_TRY(scene->seek.fold_removed(ctx, wst, false));
+        ODB_TRY(scene->buffered.fold_removed(ctx, wst, false));
+        ODB_TRY(scene->buffered.apply(ctx, wst, &launches));                // set.update(), spatial.rs:379
+        ODB_TRY(scene->seek.apply(ctx, wst, &launches));                    // set.update(), spatial.rs:437
         cb.prev_rot = scene->rot_received;                                 // spatial.rs:382-386
         if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
         cb.rot = scene->rot_received;
@@ -276,31 +309,42 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     cb.n_sources = (int)scene->seek.order.size();
     cb.force_general = scene->variant == 1;
     const int ns = cb.n_sources, nt = cb.n_tiles;
-
-    ODB_TRY(scene->d_counters.ensure(ODB_CNT_WORDS, st, false));
-    ODB_CUDA(cudaMemsetAsync(scene->d_counters.p, 0, ODB_CNT_WORDS * sizeof(uint32_t), st));
-    if (ns > 0) {
-        ODB_TRY(scene->d_jobs.ensure((size_t)ns * (nt > 0 ? nt : 1), st, false));
-        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs.p, scene->seek.d_removed.p,
-                             (int)scene->seek.removed_cap, scene->d_counters.p, cb, st);
-        launches++;
-    }
-    // buffered set first (spatial.rs:395-433): walk, extend the delay rings, mix from the rings
     const int nb = (int)scene->buffered.order.size();
-    int n_ring = 0;
-    if (nb > 0) {
+
+    ODB_TRY(ensure_idle(scene, scene->d_counters[p], ODB_CNT_WORDS));
+    uint32_t* counters = scene->d_counters[p].p;
+    ODB_CUDA(cudaMemsetAsync(counters, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
+    if (nb > 0) {  // buffered set first (spatial.rs:395-433)
         OdbCallback cbb = cb;
         cbb.n_sources = nb;
-        ODB_TRY(scene->d_ring_jobs.ensure((size_t)nb * (nt > 0 ? nt : 1), st, false));
-        ODB_TRY(scene->d_ring_writes.ensure((size_t)nb, st, false));
-        odb_launch_walk_buffered(scene->buffered.d_src.p, scene->buffered.d_order.p, scene->d_ring_jobs.p,
-                                 scene->d_ring_writes.p, scene->buffered.d_removed.p, (int)scene->buffered.removed_cap, cbb, st);
-        odb_launch_ring_write(scene->d_ring_writes.p, nb, st);
-        launches += 2;
+        ODB_TRY(ensure_idle(scene, scene->d_ring_jobs[p], (size_t)nb * (nt > 0 ? nt : 1)));
+        ODB_TRY(ensure_idle(scene, scene->d_ring_writes[p], (size_t)nb));
+        odb_launch_walk_buffered(scene->buffered.d_src.p, scene->buffered.d_order.p, scene->d_ring_jobs[p].p,
+                                 scene->d_ring_writes[p].p, scene->buffered.d_removed.p, (int)scene->buffered.removed_cap, cbb, wst);
+        launches++;
+    }
+    if (ns > 0) {
+        ODB_TRY(ensure_idle(scene, scene->d_jobs[p], (size_t)ns * (nt > 0 ? nt : 1)));
+        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs[p].p, scene->seek.d_removed.p,
+                             (int)scene->seek.removed_cap, counters, cb, wst);
+        launches++;
+    }
+    ODB_CUDA(cudaEventRecord(scene->ev_walk[p], wst));
+    {   // start the read-back of what walk_set removed; folded in by a later call without waiting
+        std::lock_guard<std::mutex> lk(scene->mu);
+        ODB_TRY(scene->seek.post_callback(ctx, wst));
+        ODB_TRY(scene->buffered.post_callback(ctx, wst));
+    }
+    // ---- stage 2 on the context's stream: O(sources x frames) ---------------------------------------------------------
+    ODB_CUDA(cudaStreamWaitEvent(st, scene->ev_walk[p], 0));
+    int n_ring = 0;
+    if (nb > 0) {  // extend the delay rings, then mix from them
+        odb_launch_ring_write(scene->d_ring_writes[p].p, nb, st);
+        launches++;
         if (nt > 0) {
             n_ring = odb_mix_ring_ctas(nb, ctx->sm_count);
-            ODB_TRY(scene->d_partials_ring.ensure((size_t)nt * n_ring * 2 * ODB_TILE_FRAMES, st, false));
-            cudaError_t e = odb_launch_mix_ring(scene->d_ring_jobs.p, nb, nt, scene->d_partials_ring.p, n_ring, st);
+            ODB_TRY(ensure_idle(scene, scene->d_partials_ring, (size_t)nt * n_ring * 2 * ODB_TILE_FRAMES));
+            cudaError_t e = odb_launch_mix_ring(scene->d_ring_jobs[p].p, nb, nt, scene->d_partials_ring.p, n_ring, st);
             if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_ring launch failed: %s", cudaGetErrorString(e));
             launches++;
         }
@@ -311,32 +355,27 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             const bool use_fast = scene->variant != 1;
             if (use_fast) {  // staged kernel for everything the walk kernel did not flag
                 n_fast = odb_mix_fast_ctas(ns, ctx->sm_count);
-                ODB_TRY(scene->d_partials_fast.ensure((size_t)nt * n_fast * 2 * ODB_TILE_FRAMES, st, false));
+                ODB_TRY(ensure_idle(scene, scene->d_partials_fast, (size_t)nt * n_fast * 2 * ODB_TILE_FRAMES));
                 if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev0, st));
-                cudaError_t e = odb_launch_mix_fast(scene->d_jobs.p, ns, nt, scene->d_partials_fast.p, n_fast,
-                                                    /*strict=*/scene->variant != 2, st);
+                cudaError_t e = odb_launch_mix_fast(scene->d_jobs[p].p, ns, nt, scene->d_partials_fast.p, n_fast,
+                                                    /*mode=*/scene->variant == 2 ? 1 : 0, st);
                 if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_fast launch failed: %s", cudaGetErrorString(e));
                 if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev1, st));
                 launches++;
             }
             // literal kernel for the flagged rest (exits at once when the walk kernel flagged nothing)
             n_gen = odb_mix_general_ctas(use_fast ? (ns < 2048 ? ns : 2048) : ns, ctx->sm_count);
-            ODB_TRY(scene->d_partials.ensure((size_t)nt * n_gen * 2 * ODB_TILE_FRAMES, st, false));
-            cudaError_t e = odb_launch_mix_general(scene->d_jobs.p, ns, nt, scene->d_partials.p, n_gen,
-                                                   /*only_flagged=*/use_fast ? 1 : 0, scene->d_counters.p, st);
+            ODB_TRY(ensure_idle(scene, scene->d_partials, (size_t)nt * n_gen * 2 * ODB_TILE_FRAMES));
+            cudaError_t e = odb_launch_mix_general(scene->d_jobs[p].p, ns, nt, scene->d_partials.p, n_gen,
+                                                   /*only_flagged=*/use_fast ? 1 : 0, counters, st);
             if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_general launch failed: %s", cudaGetErrorString(e));
             launches++;
         }
         odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_partials_ring.p, n_ring,
-                          scene->d_counters.p,
-                          /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, 2, scene->epilogue, st);
+                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }
-    {   // start the read-back of what walk_set removed; folded in by a later call without waiting
-        std::lock_guard<std::mutex> lk(scene->mu);
-        ODB_TRY(scene->seek.post_callback(ctx, st));
-        ODB_TRY(scene->buffered.post_callback(ctx, st));
-    }
+    ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
     scene->last_launches = launches;
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
@@ -355,8 +394,8 @@ extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, ui
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
     std::lock_guard<std::mutex> lk(scene->mu);
-    ODB_TRY(scene->buffered.fold_removed(ctx, ctx->stream, true));
-    return scene->seek.fold_removed(ctx, ctx->stream, true);  // like the reference, removals are visible when sample returns
+    ODB_TRY(scene->buffered.fold_removed(ctx, scene->wst, true));
+    return scene->seek.fold_removed(ctx, scene->wst, true);  // like the reference, removals are visible when sample returns
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {
@@ -386,8 +425,11 @@ static int read_source(void* owner, odb_source src, OdbSource* out, bool* stale,
     }
     for (size_t i = 0; i < set->ins_slot.size(); i++)
         if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
-    ODB_CUDA(cudaMemcpyAsync(out, set->d_src.p + slot, sizeof(OdbSource), cudaMemcpyDeviceToHost, ctx->stream));
-    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the source table is written on the scene's walk stream (on the context's stream for a mixer)
+    cudaStream_t rs = ctx->stream;
+    if (*(uint32_t*)owner == ODB_KIND_SCENE) rs = ((odb_scene*)owner)->wst;
+    ODB_CUDA(cudaMemcpyAsync(out, set->d_src.p + slot, sizeof(OdbSource), cudaMemcpyDeviceToHost, rs));
+    ODB_CUDA(cudaStreamSynchronize(rs));
     return ODB_OK;
 }
 
@@ -493,9 +535,11 @@ extern "C" int odb_last_job_counters(void* owner, uint32_t out[4]) {
     if (kind != ODB_KIND_SCENE) return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
     odb_scene* sc = (odb_scene*)owner;
     for (int i = 0; i < 4; i++) out[i] = 0;
-    if (!sc->d_counters.p) return ODB_OK;
+    const int p = (int)((sc->callback_no + 1) & 1);  // parity of the last callback
+    if (sc->callback_no == 0 || !sc->d_counters[p].p) return ODB_OK;
     ODB_CUDA(cudaSetDevice(sc->ctx->device));
-    ODB_CUDA(cudaMemcpyAsync(out, sc->d_counters.p, ODB_CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    ODB_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    ODB_CUDA(cudaMemcpyAsync(out, sc->d_counters[p].p, ODB_CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
     ODB_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return ODB_OK;
 }

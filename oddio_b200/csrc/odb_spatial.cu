@@ -49,23 +49,24 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 // (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
 // cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213). One thread per source.
 // Writes one OdbJob per (tile, source) and the source's state for the next callback.
-__global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(32) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                    OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
                                                    int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cb.n_sources) return;
     const uint32_t slot = order[idx];
     OdbSource* sp = src + slot;
-    OdbSource s = *sp;
+    OdbSource s;
+    load_source(s, sp);
     const int n = cb.n_frames;
     const float elapsed = cb.elapsed;
     const int nt = cb.n_tiles, ns = cb.n_sources;
     V3 prev_position, next_position;
-    if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position)) {
+    uint32_t flags;
+    if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position, flags)) {
         for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
         return;
     }
-    const uint32_t flags = sp->flags;
     double t = s.t;
     const double rate = s.rate;
 
@@ -74,9 +75,11 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     const float ratef = (float)rate;  // `self.data.rate as f32` frames.rs:178
     const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
     uint32_t jflags[4] = {0, 0, 0, 0};  // per tile (n_tiles <= 4 enforced by the host)
-    long long wlo[4], whi[4];           // per tile: PCM index range both ears can touch
-    for (int tl = 0; tl < 4; tl++) { wlo[tl] = (1ll << 40); whi[tl] = -(1ll << 40); }
-    long long sample_t = s.sample_t;
+    int wlo[4], whi[4];                 // per tile: PCM index range both ears can touch (32-bit: |base| <= 2^29 or general)
+#pragma unroll
+    for (int tl = 0; tl < 4; tl++) { wlo[tl] = 0x7fffffff; whi[tl] = -0x7fffffff; }
+    double t_sampled = t;
+#pragma unroll
     for (int e = 0; e < 2; e++) {
         EarSt ps = ear_state(prev_position, e, s.radius);
         EarSt nx = ear_state(next_position, e, s.radius);
@@ -87,51 +90,69 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
         float ds = dt * ratef;                                        // frames.rs:178
         bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
         bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
-        for (int cg = 0; cg < n_chunks; cg++) {
-            int tl = cg / ODB_TILE_CHUNKS, c = cg % ODB_TILE_CHUNKS;
-            int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
-            double s0 = t * rate;                                     // frames.rs:177
-            long long base = (long long)s0;                           // frames.rs:179
-            float off0 = (float)(s0 - (double)base);                  // frames.rs:183 / :189
-            if (off0 < 0.0f) general = true;                          // negative-fract quirk
-            if (base > (1ll << 29) || base < -(1ll << 29)) general = true;
-            OdbJob* j = jobs + (size_t)tl * ns + idx;
-            j->base[e][c] = sat_i32(base);
-            j->off0[e][c] = off0;
-            // PCM indices this chain can read: [base, base + trunc(offset_{m-1}) + 1]; the f32 chain stays
-            // within 1e-2 of off0 + (m-1)*ds for m <= 256, so +3 is a safe upper bound.
-            long long last = fast ? base + m : base + (long long)((double)off0 + (double)(m - 1) * (double)ds) + 3;
-            wlo[tl] = base < wlo[tl] ? base : wlo[tl];
-            whi[tl] = last > whi[tl] ? last : whi[tl];
-            t = t + (double)dt * (double)m;                           // frames.rs:198
-            sample_t = (long long)(t * rate);                         // frames.rs:199-200
+#pragma unroll
+        for (int tl = 0; tl < 4; tl++) {  // tiles and chunks unrolled: the per-tile window bounds stay in registers
+            if (tl < nt) {
+#pragma unroll
+                for (int c = 0; c < ODB_TILE_CHUNKS; c++) {
+                    const int cg = tl * ODB_TILE_CHUNKS + c;
+                    if (cg < n_chunks) {
+                        int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
+                        double s0 = t * rate;                                     // frames.rs:177
+                        // frames.rs:179 `s0 as isize`: 32-bit conversion (saturating); any |s0| >= 2^29 is far
+                        // outside every Frames block and only ever yields zeros, which the general kernel produces
+                        int base = __double2int_rz(s0);
+                        float off0 = (float)(s0 - (double)base);                  // frames.rs:183 / :189
+                        if (off0 < 0.0f) general = true;                          // negative-fract quirk
+                        if (base > (1 << 29) || base < -(1 << 29)) { general = true; base = base > 0 ? (1 << 30) : -(1 << 30); }
+                        OdbJob* j = jobs + (size_t)tl * ns + idx;
+                        j->base[e][c] = base;
+                        j->off0[e][c] = off0;
+                        // PCM indices this chain can read: [base, base + trunc(offset_{m-1}) + 1]; the f32 chain stays
+                        // within 1e-2 of off0 + (m-1)*ds for m <= 256, so +4 on the f32 estimate is a safe upper bound.
+                        const float span = general ? 0.0f : __fmaf_rn((float)(m - 1), ds, off0);
+                        const int last = fast ? base + m : base + __float2int_rz(span) + 4;
+                        wlo[tl] = min(wlo[tl], base);
+                        whi[tl] = max(whi[tl], last);
+                        t = t + (double)dt * (double)m;                           // frames.rs:198
+                        t_sampled = t;
+                    }
+                }
+            }
         }
         t = t + (double)(-eff - ps.offset);                           // :465
-        for (int tl = 0; tl < nt; tl++) {
-            OdbJob* j = jobs + (size_t)tl * ns + idx;
-            j->ds[e] = ds; j->pg[e] = ps.gain; j->dg[e] = d_gain;
-            jflags[tl] |= (fast ? (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R) : 0u) | (general ? ODB_JF_GENERAL : 0u);
+#pragma unroll
+        for (int tl = 0; tl < 4; tl++) {
+            if (tl < nt) {
+                OdbJob* j = jobs + (size_t)tl * ns + idx;
+                j->ds[e] = ds; j->pg[e] = ps.gain; j->dg[e] = d_gain;
+                jflags[tl] |= (fast ? (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R) : 0u) | (general ? ODB_JF_GENERAL : 0u);
+            }
         }
     }
     t = t + (double)elapsed;                                          // :468
     sp->t = t;
-    sp->sample_t = sample_t;
+    // frames.rs:199-200 stores (t * rate) as isize at the end of every sample() call; only the last store (right
+    // ear, last chunk) is observable, and the seeks that follow do not touch sample_t
+    if (n_chunks > 0) sp->sample_t = (long long)(t_sampled * rate);
     uint32_t n_general = 0, n_fast = 0;
-    for (int tl = 0; tl < nt; tl++) {
+#pragma unroll
+    for (int tl = 0; tl < 4; tl++) {
+        if (tl >= nt) break;
         OdbJob* j = jobs + (size_t)tl * ns + idx;
         j->pcm = s.pcm; j->len = s.len;
         j->fixed_gain = s.fixed_gain;
         j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
         // window for the staged (fast) mix kernel: 16-byte aligned start, whole float4s, inside the
         // zero-padded Frames block; anything else goes to the general kernel
-        long long ws = wlo[tl] & ~3ll;
-        long long wl = ((whi[tl] - ws + 1) + 3) & ~3ll;
+        const int ws = wlo[tl] & ~3;
+        const int wl = ((whi[tl] - ws + 1) + 3) & ~3;
         uint32_t f = jflags[tl];
-        if (wl > ODB_FAST_PCM_CAP || ws < -(long long)ODB_PCM_PAD || ws + wl > (long long)s.len + ODB_PCM_PAD) f |= ODB_JF_GENERAL;
+        if (!(f & ODB_JF_GENERAL) && (wl > ODB_FAST_PCM_CAP || ws < -ODB_PCM_PAD || ws + wl > s.len + ODB_PCM_PAD)) f |= ODB_JF_GENERAL;
         if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
         if (cb.force_general) f |= ODB_JF_GENERAL;
-        j->w_start = (int)ws;
-        j->w_len = (f & ODB_JF_GENERAL) ? 0 : (int)wl;
+        j->w_start = ws;
+        j->w_len = (f & ODB_JF_GENERAL) ? 0 : wl;
         j->flags = f;
         if (f & ODB_JF_GENERAL) n_general++; else n_fast++;
     }
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
 // b: general kernel) in a fixed order (deterministic), applies the optional Tanh / Reinhard wrapper
 // (tanh.rs:24-28, reinhard.rs:30-34) and writes the interleaved stereo output. Each block owns 32
 // consecutive output floats; its 8 warps take every 8th partial tile, then fold through shared memory.
-#define RED_GROUPS 8
+#define RED_GROUPS 16
 __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* __restrict__ pa, int na,
                                                                  const float* __restrict__ pb, int nb,
                                                                  const float* __restrict__ pc, int nc,
@@ -254,7 +275,15 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
     float sum = 0.0f;
     const size_t tile_floats = (size_t)ODB_TILE_FRAMES * channels;
     const float* p = pa + (size_t)tl * na * tile_floats + f;
-    for (int i = grp; i < na; i += RED_GROUPS) sum = sum + p[(size_t)i * tile_floats];
+    {   // the dominant set: loads issued four at a time, summed in index order
+        int i = grp;
+        for (; i + 3 * RED_GROUPS < na; i += 4 * RED_GROUPS) {
+            const float v0 = p[(size_t)i * tile_floats], v1 = p[(size_t)(i + RED_GROUPS) * tile_floats];
+            const float v2 = p[(size_t)(i + 2 * RED_GROUPS) * tile_floats], v3 = p[(size_t)(i + 3 * RED_GROUPS) * tile_floats];
+            sum = sum + v0; sum = sum + v1; sum = sum + v2; sum = sum + v3;
+        }
+        for (; i < na; i += RED_GROUPS) sum = sum + p[(size_t)i * tile_floats];
+    }
     const float* q = pb + (size_t)tl * nb * tile_floats + f;
     for (int i = grp; i < nb; i += RED_GROUPS) sum = sum + q[(size_t)i * tile_floats];
     const float* r = pc + (size_t)tl * nc * tile_floats + f;
@@ -294,7 +323,14 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
                           uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
-    k_walk_seek<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
+    // Same shared-memory carve-out as k_mix_fast (which takes all of it): an SM only runs kernels of one
+    // carve-out configuration at a time, and this kernel is meant to run underneath the previous callback's mix.
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(k_walk_seek, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
+    k_walk_seek<<<(cb.n_sources + 31) / 32, 32, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
 }
 
 static const int GEN_WARPS = 8;

@@ -25,6 +25,7 @@ struct __attribute__((aligned(16))) OdbSource {
     const float* pcm;      // first sample of the Frames block (ODB_PCM_PAD zeros on both sides)
     double rate;           // Frames::rate (frames.rs:20)
     double t;              // FramesSignal::t (frames.rs:145)
+    double t_end;          // (len - 1) as f64 / rate, the right-hand side of FramesSignal::is_finished (frames.rs:205)
     long long sample_t;    // FramesSignal::sample_t (frames.rs:149)
     int len;               // frames in the Frames block
     int channels;          // 1 or 2
