@@ -440,7 +440,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --sources per GPU (default), strong = --sources in total")
     ap.add_argument("--reduce-every", type=int, default=8, help="N > 1: callbacks per all-reduce (1 = live playback)")
-    ap.add_argument("--variant", type=int, default=0, choices=[0, 2], help="0 = strict staged kernel, 2 = FMA-contracted value ops")
+    ap.add_argument("--variant", type=int, default=2, choices=[0, 2],
+                    help="2 (default) = staged kernel with FMA-contracted value ops, 0 = strict (bit-exact per-source contributions)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

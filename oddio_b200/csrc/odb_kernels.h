@@ -7,9 +7,10 @@
 // Largest per-frame source advance (samples per output frame) the fast mix kernel stages in
 // shared memory; sources outside (0, ODB_FAST_DS_MAX] take the general kernel.
 #define ODB_FAST_DS_MAX 2.0f
-// Floats of PCM the staged kernel can hold per source and tile (two such buffers per warp): a full 1024-frame
-// tile fits up to ds = 1.21 (1024 * 1.21 + ear skew + slack), shorter callbacks up to ODB_FAST_DS_MAX.
-#define ODB_FAST_PCM_CAP 1280
+// Floats of PCM the staged kernel can hold per source and 512-frame half tile (two such buffers per warp): a
+// full half fits up to ds = 1.17 (512 * 1.17 + ear skew + slack), shorter callbacks up to ODB_FAST_DS_MAX.
+#define ODB_FAST_PCM_CAP 640
+#define ODB_FAST_HALF_CHUNKS 2
 
 struct OdbMotionMsg {  // Spatial::set_motion payload (spatial.rs:137-149)
     uint32_t slot;

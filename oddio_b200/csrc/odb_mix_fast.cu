@@ -109,19 +109,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr int FAST_WARPS = 12;                                              // one CTA per SM
+constexpr int FAST_WARPS = 16;                                              // one CTA per SM: 8 warp pairs, one warp per half tile
 constexpr int FAST_ILP = 4;                                                 // frames of a chunk a lane processes interleaved
-constexpr int FAST_BATCH = 4;                                               // sources per warp batch: 4 x 2 ears x 4 chunks = 32 chains
-constexpr int FAST_PCM_BYTES = ODB_FAST_PCM_CAP * 4;                        // 5120, two of them per warp
+constexpr int FAST_SPLIT = 2;                                               // a 1024-frame tile is mixed as 2 halves of 512 frames
+constexpr int FAST_HCHUNKS = ODB_TILE_CHUNKS / FAST_SPLIT;                  // 256-frame chunks per half: 2
+constexpr int FAST_NACC = FAST_HCHUNKS * 8;                                 // packed (L, R) accumulators per lane: 512 frames / 32
+constexpr int FAST_BATCH = 8;                                               // sources per warp batch: 8 x 2 ears x 2 chunks = 32 chains
+constexpr int FAST_PCM_BYTES = ODB_FAST_PCM_CAP * 4;                        // 2560, two of them per warp
 constexpr int FAST_POINTS = ODB_SPATIAL_CHUNK / 4;                          // every 4th cursor value of a chunk
 constexpr int FAST_ROW_BYTES = FAST_POINTS * 8 + 8;                         // one (source, chunk) row of (L, R) cursors; +8 skews the banks
-constexpr int FAST_OFFS_BYTES = FAST_BATCH * ODB_TILE_CHUNKS * FAST_ROW_BYTES;  // 8320
-constexpr int FAST_WARP_BYTES = 2 * FAST_PCM_BYTES + FAST_OFFS_BYTES;       // 18560
-static_assert(FAST_WARP_BYTES >= 2 * ODB_TILE_FRAMES * 4, "the warp region doubles as its partial tile");
+constexpr int FAST_OFFS_BYTES = FAST_BATCH * FAST_HCHUNKS * FAST_ROW_BYTES; // 8320
+constexpr int FAST_WARP_BYTES = 2 * FAST_PCM_BYTES + FAST_OFFS_BYTES;       // 13440
+static_assert(FAST_WARP_BYTES >= 2 * ODB_TILE_FRAMES * 4 / FAST_SPLIT, "the warp region doubles as its partial half tile");
 static_assert(FAST_WARP_BYTES % 16 == 0, "TMA destinations are 16-byte aligned");
-constexpr int FAST_JOBS_OFF = FAST_WARPS * FAST_WARP_BYTES;                 // staged job records: 4 x 128 B per warp
+constexpr int FAST_JOBS_OFF = FAST_WARPS * FAST_WARP_BYTES;                 // staged job records: 8 x 128 B per warp
 constexpr int FAST_BARS_OFF = FAST_JOBS_OFF + FAST_WARPS * FAST_BATCH * 128;
 constexpr int FAST_SMEM_BYTES = FAST_BARS_OFF + FAST_WARPS * 16;
+static_assert(FAST_SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
 #define ODB_MAGIC 8388608.0f          // 2^23: ulp 1, so x +rd 2^23 = 2^23 + floor(x)
 #define ODB_MAGIC_BITS 0x4B000000u
 
@@ -130,7 +134,7 @@ constexpr int FAST_SMEM_BYTES = FAST_BARS_OFF + FAST_WARPS * 16;
 // inside the tile. KL / KR: doppler ear = shared address of PCM index `base` minus the magic bits,
 // unit ear = shared address of PCM index base + lane.
 template <bool STRICT, bool FULL, bool UL, bool UR>
-__device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c, const int lane, const float fbase,
+__device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int cc, const int c, const int lane, const float fbase,
                                               const uint32_t row_sa, const uint32_t KL, const uint32_t KR, const u64 d1,
                                               const u64 d2, const u64 d3, const u64 fr_unit, const u64 pgp,
                                               const u64 dgp, const int nfr, const u64 nz) {
@@ -220,43 +224,43 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
 #pragma unroll
             for (int u = 0; u < FAST_ILP; u++) s[u] = mulx(s[u], g[u], nz);
 #pragma unroll
-            for (int u = 0; u < FAST_ILP; u++) acc[c * 8 + j0 + u] = add2(acc[c * 8 + j0 + u], s[u]);  // o[ear] += s * gain (spatial.rs:460)
+            for (int u = 0; u < FAST_ILP; u++) acc[cc * 8 + j0 + u] = add2(acc[cc * 8 + j0 + u], s[u]);  // o[ear] += s * gain (spatial.rs:460)
         } else {
 #pragma unroll
-            for (int u = 0; u < FAST_ILP; u++) acc[c * 8 + j0 + u] = fma2(s[u], g[u], acc[c * 8 + j0 + u]);
+            for (int u = 0; u < FAST_ILP; u++) acc[cc * 8 + j0 + u] = fma2(s[u], g[u], acc[cc * 8 + j0 + u]);
         }
     }
 }
 
 template <bool STRICT, bool FULL, bool UL, bool UR>
-__device__ __forceinline__ void consume_source(u64* __restrict__ acc, const int lane, const float lanef, const uint32_t job_sa,
-                                               const uint32_t pcm_b, const uint32_t rows_sa, const int w_start,
-                                               const int nfr, const u64 d1, const u64 d2, const u64 d3, const u64 pgp,
-                                               const u64 dgp, const u64 nz) {
+__device__ __forceinline__ void consume_source(u64* __restrict__ acc, const int lane, const float lanef, const int half,
+                                               const uint32_t job_sa, const uint32_t pcm_b, const uint32_t rows_sa,
+                                               const int w_start, const int nfr, const u64 d1, const u64 d2, const u64 d3,
+                                               const u64 pgp, const u64 dgp, const u64 nz) {
 #pragma unroll
-    for (int c = 0; c < ODB_TILE_CHUNKS; c++) {
+    for (int cc = 0; cc < FAST_HCHUNKS; cc++) {
+        const int c = half * FAST_HCHUNKS + cc;  // chunk of the tile
         if (!FULL && c * ODB_SPATIAL_CHUNK >= nfr) break;
-        const int baseL = (int)lds_u32(job_sa + (ODB_JW_BASE + c) * 4);
-        const int baseR = (int)lds_u32(job_sa + (ODB_JW_BASE + ODB_TILE_CHUNKS + c) * 4);
+        const int baseL = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_BASE + c) * 4));
+        const int baseR = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_BASE + ODB_TILE_CHUNKS + c) * 4));
         const uint32_t KL = pcm_b + (uint32_t)((baseL - w_start) * 4) + (UL ? (uint32_t)(lane * 4) : 0u - (ODB_MAGIC_BITS << 2));
         const uint32_t KR = pcm_b + (uint32_t)((baseR - w_start) * 4) + (UR ? (uint32_t)(lane * 4) : 0u - (ODB_MAGIC_BITS << 2));
         u64 fr_unit = 0ull;
         if (UL || UR)
-            fr_unit = pk2(__uint_as_float(lds_u32(job_sa + (ODB_JW_OFF0 + c) * 4)),
-                          __uint_as_float(lds_u32(job_sa + (ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4)));
-        consume_chunk<STRICT, FULL, UL, UR>(acc, c, lane, lanef + (float)(c * ODB_SPATIAL_CHUNK),
-                                            rows_sa + (uint32_t)(c * FAST_ROW_BYTES), KL, KR, d1, d2, d3, fr_unit, pgp, dgp,
+            fr_unit = pk2(__uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + c) * 4))),
+                          __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4))));
+        consume_chunk<STRICT, FULL, UL, UR>(acc, cc, c, lane, lanef + (float)(c * ODB_SPATIAL_CHUNK),
+                                            rows_sa + (uint32_t)(cc * FAST_ROW_BYTES), KL, KR, d1, d2, d3, fr_unit, pgp, dgp,
                                             nfr, nz);
     }
 }
 
-// 152 registers x 384 threads leave room in the register file for one 64-thread walk CTA per SM, so the next
-// callback's k_walk_seek can run underneath this kernel.
 template <bool STRICT>
-__global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
+__global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* __restrict__ jobs, int n_sources,
                                                                   float* __restrict__ partials, const u64 nz) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = warp & 1, pair = warp >> 1;  // the two warps of a pair mix the two halves of the same sources
     const int tl = blockIdx.y;
     const uint32_t smem_sa = smem_u32(smem_raw);
     const uint32_t pcm_sa = smem_sa + (uint32_t)(warp * FAST_WARP_BYTES);
@@ -272,29 +276,30 @@ __global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int
     uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
     uint32_t buf = 0;     // PCM buffer the next source to consume lands in
 
-    u64 acc[ODB_TILE_FRAMES / 32];
+    u64 acc[FAST_NACC];
 #pragma unroll
-    for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) acc[j] = 0ull;
+    for (int j = 0; j < FAST_NACC; j++) acc[j] = 0ull;
 
-    const int gw = blockIdx.x * FAST_WARPS + warp, GW = gridDim.x * FAST_WARPS;
+    const int gp = blockIdx.x * (FAST_WARPS / FAST_SPLIT) + pair, GP = gridDim.x * (FAST_WARPS / FAST_SPLIT);
     const float lanef = (float)(tl * ODB_TILE_FRAMES + lane);
     const int r = lane & 3;
     const OdbJob* tile_jobs = jobs + (size_t)tl * n_sources;
     const int n_batches = (n_sources + FAST_BATCH - 1) / FAST_BATCH;
+    const int first_frame = half * (ODB_TILE_FRAMES / FAST_SPLIT);
 
-    // lane 0: start the bulk copy of source q's PCM window into PCM buffer `b`
+    // lane 0: start the bulk copy of source q's PCM window of this half into PCM buffer `b`
     auto start_copy = [&](int q, uint32_t b) {
         if (lane == 0) {
             const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
             const u64 p = ((u64)lds_u32(job_sa + ODB_JW_PCM_HI * 4) << 32) | (u64)lds_u32(job_sa + ODB_JW_PCM_LO * 4);
-            const int w_start = (int)lds_u32(job_sa + ODB_JW_W_START * 4);
-            const uint32_t bytes = lds_u32(job_sa + ODB_JW_W_LEN * 4) * 4u;
+            const int w_start = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_WINDOW + 2 * half) * 4));
+            const uint32_t bytes = lds_u32(job_sa + (uint32_t)((ODB_JW_WINDOW + 2 * half + 1) * 4)) * 4u;
             mbar_expect_tx(bar_sa + b * 8, bytes);
             bulk_g2s(pcm_sa + b * FAST_PCM_BYTES, reinterpret_cast<const float*>(p) + w_start, bytes, bar_sa + b * 8);
         }
     };
 
-    for (int bi = gw; bi < n_batches; bi += GW) {
+    for (int bi = gp; bi < n_batches; bi += GP) {
         const int s0 = bi * FAST_BATCH;
         // 1. stage the batch's job records (one 128-byte line each: lane l moves word l)
 #pragma unroll
@@ -304,20 +309,25 @@ __global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int
             sts_u32(jobs_sa + (uint32_t)(q * 128 + lane * 4), w);
         }
         __syncwarp();
-        uint32_t act = 0;  // sources of the batch this kernel mixes
+        uint32_t act = 0;  // sources of the batch this warp mixes: staged, and with frames in this half
 #pragma unroll
-        for (int q = 0; q < FAST_BATCH; q++)
-            if (!(lds_u32(jobs_sa + (uint32_t)(q * 128 + ODB_JW_FLAGS * 4)) & (ODB_JF_SKIP | ODB_JF_GENERAL))) act |= 1u << q;
+        for (int q = 0; q < FAST_BATCH; q++) {
+            const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
+            if (!(lds_u32(job_sa + ODB_JW_FLAGS * 4) & (ODB_JF_SKIP | ODB_JF_GENERAL)) &&
+                (int)lds_u32(job_sa + ODB_JW_N_FRAMES * 4) > first_frame)
+                act |= 1u << q;
+        }
         if (act) {
             start_copy(__ffs(act) - 1, buf);
-            {   // 2. literal cursor chains: lane = (source q, ear e, chunk c)
-                const int q = lane >> 3, e = (lane >> 2) & 1, c = lane & 3;
+            {   // 2. literal cursor chains: lane = (source q, ear e, chunk cc of this half)
+                const int q = lane >> 2, e = (lane >> 1) & 1, cc = lane & 1;
+                const int c = half * FAST_HCHUNKS + cc;
                 const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
                 const uint32_t jf = lds_u32(job_sa + ODB_JW_FLAGS * 4);
                 if (((act >> q) & 1u) && !(jf & (e ? ODB_JF_FAST_R : ODB_JF_FAST_L))) {
                     float o = __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c) * 4)));
                     const float ds = __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_DS + e) * 4)));
-                    const uint32_t dst = offs_sa + (uint32_t)((q * ODB_TILE_CHUNKS + c) * FAST_ROW_BYTES + e * 4);
+                    const uint32_t dst = offs_sa + (uint32_t)((q * FAST_HCHUNKS + cc) * FAST_ROW_BYTES + e * 4);
 #pragma unroll 8
                     for (int m = 0; m < FAST_POINTS; m++) {
                         sts_f32(dst + (uint32_t)(m * 8), o);
@@ -334,16 +344,16 @@ __global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int
                 const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
                 const uint32_t jf = lds_u32(job_sa + ODB_JW_FLAGS * 4);
                 const int nfr = (int)lds_u32(job_sa + ODB_JW_N_FRAMES * 4);
-                const int w_start = (int)lds_u32(job_sa + ODB_JW_W_START * 4);
+                const int w_start = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_WINDOW + 2 * half) * 4));
                 const u64 dsp = lds_u64(job_sa + ODB_JW_DS * 4), pgp = lds_u64(job_sa + ODB_JW_PG * 4),
                           dgp = lds_u64(job_sa + ODB_JW_DG * 4);
                 const u64 d1 = r >= 1 ? dsp : 0ull, d2 = r >= 2 ? dsp : 0ull, d3 = r >= 3 ? dsp : 0ull;
                 const uint32_t pcm_b = pcm_sa + buf * FAST_PCM_BYTES;
-                const uint32_t rows_sa = offs_sa + (uint32_t)(q * ODB_TILE_CHUNKS * FAST_ROW_BYTES + (lane >> 2) * 8);
+                const uint32_t rows_sa = offs_sa + (uint32_t)(q * FAST_HCHUNKS * FAST_ROW_BYTES + (lane >> 2) * 8);
                 mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
                 parity ^= 1u << buf;
                 const uint32_t code = (nfr == ODB_TILE_FRAMES ? 4u : 0u) | ((jf & ODB_JF_FAST_L) ? 2u : 0u) | ((jf & ODB_JF_FAST_R) ? 1u : 0u);
-#define ODB_CONSUME(F, L, R) consume_source<STRICT, F, L, R>(acc, lane, lanef, job_sa, pcm_b, rows_sa, w_start, nfr, d1, d2, d3, pgp, dgp, nz)
+#define ODB_CONSUME(F, L, R) consume_source<STRICT, F, L, R>(acc, lane, lanef, half, job_sa, pcm_b, rows_sa, w_start, nfr, d1, d2, d3, pgp, dgp, nz)
                 switch (code) {
                     case 4: ODB_CONSUME(true, false, false); break;
                     case 7: ODB_CONSUME(true, true, true); break;
@@ -364,14 +374,17 @@ __global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int
 
     // 4. fold: warp -> CTA (fixed warp order) -> one partial tile per CTA
 #pragma unroll
-    for (int j = 0; j < ODB_TILE_FRAMES / 32; j++)
+    for (int j = 0; j < FAST_NACC; j++)
         asm volatile("st.shared.b64 [%0], %1;" ::"r"(pcm_sa + (uint32_t)((32 * j + lane) * 8)), "l"(acc[j]) : "memory");
     __syncthreads();
     float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * (2 * ODB_TILE_FRAMES);
+    constexpr int HALF_FLOATS = 2 * ODB_TILE_FRAMES / FAST_SPLIT;
     for (int f = threadIdx.x; f < 2 * ODB_TILE_FRAMES; f += FAST_WARPS * 32) {
+        const int h = f / HALF_FLOATS, fh = f - h * HALF_FLOATS;
         float sum = 0.0f;
 #pragma unroll
-        for (int w = 0; w < FAST_WARPS; w++) sum = sum + *reinterpret_cast<const float*>(smem_raw + w * FAST_WARP_BYTES + f * 4);
+        for (int w = 0; w < FAST_WARPS / FAST_SPLIT; w++)
+            sum = sum + *reinterpret_cast<const float*>(smem_raw + (w * FAST_SPLIT + h) * FAST_WARP_BYTES + fh * 4);
         dst[f] = sum;
     }
 }
@@ -381,7 +394,8 @@ __global__ void __maxnreg__(152) k_mix_fast(const OdbJob* __restrict__ jobs, int
 using namespace odbk;
 
 int odb_mix_fast_ctas(int n_sources, int sm_count) {
-    int want = (n_sources + FAST_WARPS * FAST_BATCH - 1) / (FAST_WARPS * FAST_BATCH);
+    const int per_cta = (FAST_WARPS / FAST_SPLIT) * FAST_BATCH;
+    int want = (n_sources + per_cta - 1) / per_cta;
     return want < 1 ? 1 : (want > sm_count ? sm_count : want);
 }
 

@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(32) k_walk_seek(OdbSource* __restrict__ src, c
     const float ratef = (float)rate;  // `self.data.rate as f32` frames.rs:178
     const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
     uint32_t jflags[4] = {0, 0, 0, 0};  // per tile (n_tiles <= 4 enforced by the host)
-    int wlo[4], whi[4];                 // per tile: PCM index range both ears can touch (32-bit: |base| <= 2^29 or general)
+    int wlo[8], whi[8];                 // per 512-frame half tile: PCM index range both ears can touch (|base| <= 2^29 or general)
 #pragma unroll
-    for (int tl = 0; tl < 4; tl++) { wlo[tl] = 0x7fffffff; whi[tl] = -0x7fffffff; }
+    for (int h = 0; h < 8; h++) { wlo[h] = 0x7fffffff; whi[h] = -0x7fffffff; }
     double t_sampled = t;
 #pragma unroll
     for (int e = 0; e < 2; e++) {
@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(32) k_walk_seek(OdbSource* __restrict__ src, c
                         // within 1e-2 of off0 + (m-1)*ds for m <= 256, so +4 on the f32 estimate is a safe upper bound.
                         const float span = general ? 0.0f : __fmaf_rn((float)(m - 1), ds, off0);
                         const int last = fast ? base + m : base + __float2int_rz(span) + 4;
-                        wlo[tl] = min(wlo[tl], base);
-                        whi[tl] = max(whi[tl], last);
+                        wlo[2 * tl + c / ODB_FAST_HALF_CHUNKS] = min(wlo[2 * tl + c / ODB_FAST_HALF_CHUNKS], base);
+                        whi[2 * tl + c / ODB_FAST_HALF_CHUNKS] = max(whi[2 * tl + c / ODB_FAST_HALF_CHUNKS], last);
                         t = t + (double)dt * (double)m;                           // frames.rs:198
                         t_sampled = t;
                     }
@@ -145,14 +145,25 @@ __global__ void __launch_bounds__(32) k_walk_seek(OdbSource* __restrict__ src, c
         j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
         // window for the staged (fast) mix kernel: 16-byte aligned start, whole float4s, inside the
         // zero-padded Frames block; anything else goes to the general kernel
-        const int ws = wlo[tl] & ~3;
-        const int wl = ((whi[tl] - ws + 1) + 3) & ~3;
         uint32_t f = jflags[tl];
-        if (!(f & ODB_JF_GENERAL) && (wl > ODB_FAST_PCM_CAP || ws < -ODB_PCM_PAD || ws + wl > s.len + ODB_PCM_PAD)) f |= ODB_JF_GENERAL;
+        int ws[2], wl[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            ws[h] = 0; wl[h] = 0;
+            if (whi[2 * tl + h] >= wlo[2 * tl + h]) {  // the half has frames
+                ws[h] = wlo[2 * tl + h] & ~3;
+                wl[h] = ((whi[2 * tl + h] - ws[h] + 1) + 3) & ~3;
+                if (!(f & ODB_JF_GENERAL) && (wl[h] > ODB_FAST_PCM_CAP || ws[h] < -ODB_PCM_PAD || ws[h] + wl[h] > s.len + ODB_PCM_PAD))
+                    f |= ODB_JF_GENERAL;
+            }
+        }
         if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
         if (cb.force_general) f |= ODB_JF_GENERAL;
-        j->w_start = ws;
-        j->w_len = (f & ODB_JF_GENERAL) ? 0 : wl;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            j->window[h][0] = ws[h];
+            j->window[h][1] = (f & ODB_JF_GENERAL) ? 0 : wl[h];
+        }
         j->flags = f;
         if (f & ODB_JF_GENERAL) n_general++; else n_fast++;
     }

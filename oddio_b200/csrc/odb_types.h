@@ -65,9 +65,8 @@ struct __attribute__((aligned(16))) OdbJob {
     int n_frames;                   // word 11: frames of this tile (<= ODB_TILE_FRAMES)
     int base[2][ODB_TILE_CHUNKS];   // words 12-19: per ear, per 256-chunk `base` (frames.rs:179), saturated to int32
     float off0[2][ODB_TILE_CHUNKS]; // words 20-27: initial `offset` / constant `fract` (frames.rs:183,189)
-    int w_start;                    // word 28: first PCM index the tile can touch, rounded down to a multiple of 4
-    int w_len;                      // word 29: floats from w_start that cover every index of both ears (multiple of 4)
-    uint32_t pad[2];
+    int window[2][2];               // words 28-31: per 512-frame half {first PCM index it can touch (multiple of 4),
+                                    // floats from there covering every index of both ears (multiple of 4; 0 = unused)}
 };
 #define ODB_JW_PCM_LO 0
 #define ODB_JW_PCM_HI 1
@@ -80,8 +79,7 @@ struct __attribute__((aligned(16))) OdbJob {
 #define ODB_JW_N_FRAMES 11
 #define ODB_JW_BASE 12
 #define ODB_JW_OFF0 20
-#define ODB_JW_W_START 28
-#define ODB_JW_W_LEN 29
+#define ODB_JW_WINDOW 28
 // What one (source, 1024-frame chunk) pass of the mixer kernels needs. 64 bytes.
 struct __attribute__((aligned(16))) OdbMixJob {
     const float* pcm;
