@@ -175,7 +175,8 @@ int odb_last_mix_kernel_ms(void* owner, float* out_ms);
 /* Selects the mix-kernel variant: 0 = default (staged kernel, strict arithmetic: a source's
  * contribution is bit-identical to the reference's; general kernel per source as fallback), 1 = force the
  * literal general kernel for every source (slow, used to cross-check), 2 = staged kernel with the three
- * value multiply-adds contracted to FMA (cursors and indices still bit-exact). */
+ * value multiply-adds contracted to FMA (cursors and indices still bit-exact). Adding 0x100 runs a scene's
+ * per-source set-up kernels on a second stream so that they overlap the previous callback's mix. */
 int odb_set_kernel_variant(void* owner, int variant);
 
 #ifdef __cplusplus

@@ -12,6 +12,23 @@
 #define ODB_FAST_PCM_CAP 640
 #define ODB_FAST_HALF_CHUNKS 2
 
+// Launches `kernel` so that it may overlap the tail of the previous kernel in `st` (programmatic dependent
+// launch); the kernel must call odbk::pdl_wait() before it touches anything the previous kernel wrote.
+template <class... KArgs, class... Args>
+static inline cudaError_t odb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct OdbMotionMsg {  // Spatial::set_motion payload (spatial.rs:137-149)
     uint32_t slot;
     float pos[3];
@@ -54,5 +71,7 @@ cudaError_t odb_launch_mix_ring(const OdbRingJob* jobs, int n_sources, int n_til
 // Sums partial tiles of `tile_floats` floats each (1024 frames x channels) into the interleaved output.
 // Up to three partial sets: a (staged / streaming kernel), b (general kernel; skipped when the walk kernel
 // counted no general job and b_is_general is set), c (ring kernel).
+// `zero_counters` (may be NULL): ODB_CNT_WORDS counters the kernel resets for the next callback.
 void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const float* pc, int nc, const uint32_t* counters,
-                       int b_is_general, float* out, int n_frames, int n_tiles, int channels, int epilogue, cudaStream_t st);
+                       int b_is_general, uint32_t* zero_counters, float* out, int n_frames, int n_tiles, int channels,
+                       int epilogue, cudaStream_t st);

@@ -7,6 +7,13 @@
 
 namespace odbk {
 
+// Programmatic dependent launch (sm_90+): the kernels of one callback are launched back to back with the
+// programmatic-stream-serialization attribute. `pdl_launch_dependents` lets the next kernel of the stream be
+// set up while this one still runs; `pdl_wait` blocks until everything the previous kernel wrote is visible.
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct V3 { float x, y, z; };
 
 // math/mod.rs:33-35  norm = sqrt(((0 + x*x) + y*y) + z*z)

@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();           // the job records come from the walk kernel launched just before
     uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
     uint32_t buf = 0;     // PCM buffer the next source to consume lands in
 
@@ -404,8 +406,8 @@ static cudaError_t launch_fast(const OdbJob* jobs, int n_sources, int n_tiles, f
     cudaError_t e = cudaFuncSetAttribute(k_mix_fast<STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     dim3 grid(n_ctas, n_tiles);
-    k_mix_fast<STRICT><<<grid, FAST_WARPS * 32, FAST_SMEM_BYTES, st>>>(jobs, n_sources, partials, 0x8000000080000000ull);
-    return cudaGetLastError();
+    return odb_launch_pdl(k_mix_fast<STRICT>, grid, dim3(FAST_WARPS * 32), (size_t)FAST_SMEM_BYTES, st, jobs, n_sources, partials,
+                          0x8000000080000000ull);
 }
 
 // mode bit 0: value multiply-adds contracted to FMA

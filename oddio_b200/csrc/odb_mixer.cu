@@ -148,7 +148,7 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
             launches++;
         }
         odb_launch_reduce(mixer->d_partials_unit.p, n_unit, mixer->d_partials_gen.p, n_gen, nullptr, 0, mixer->d_counters.p,
-                          n_unit > 0 ? 1 : 0, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
+                          n_unit > 0 ? 1 : 0, nullptr, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
         launches++;
     }
     {

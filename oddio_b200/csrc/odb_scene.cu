@@ -20,9 +20,13 @@ struct odb_scene {
     int epilogue = ODB_EPILOGUE_NONE;
     int variant = 0;
     uint32_t last_launches = 0;
-    // Two-stage pipeline: the per-source set-up of callback k+1 (control-plane scatter + walk kernels, on the
-    // scene's own `wst` stream) overlaps the mix kernels of callback k (on the context's stream). What the walk
-    // kernels hand to the mix kernels is double-buffered by callback parity.
+    // Optional two-stage pipeline (odb_set_kernel_variant bit 8): the per-source set-up of callback k+1
+    // (control-plane scatter + walk kernels, on the scene's own `wst` stream) overlaps the mix kernels of
+    // callback k (on the context's stream). Measured on C3 it hides only ~4 us of the 15 us walk kernel (the mix
+    // kernel leaves it no registers or issue slots), so the default is one stream with programmatic dependent
+    // launches between the kernels of a callback. What the walk kernels hand to the mix kernels is
+    // double-buffered by callback parity either way.
+    bool pipelined = false;
     cudaStream_t wst = nullptr;
     cudaEvent_t ev_walk[2] = {nullptr, nullptr}, ev_mix[2] = {nullptr, nullptr};
     uint64_t callback_no = 0;
@@ -280,7 +284,7 @@ static int ensure_idle(odb_scene* scene, DevBuf<T>& buf, size_t n) {
 
 static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames) {
     odb_ctx* ctx = scene->ctx;
-    cudaStream_t st = ctx->stream, wst = scene->wst;
+    cudaStream_t st = ctx->stream, wst = scene->pipelined ? scene->wst : ctx->stream;
     if (n_frames > ODB_MAX_FRAMES)
         return odb_fail(ODB_E_UNSUPPORTED, "n_frames %u exceeds the %d frames one callback may render", n_frames, ODB_MAX_FRAMES);
     ODB_CUDA(cudaSetDevice(ctx->device));
@@ -289,7 +293,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     scene->callback_no++;
     // ---- stage 1 on `wst`: everything that is per source and O(1) per chunk -------------------------------------
     // this parity's job / counter buffers are free once the mix of two callbacks ago has finished
-    ODB_CUDA(cudaStreamWaitEvent(wst, scene->ev_mix[p], 0));
+    if (scene->pipelined) ODB_CUDA(cudaStreamWaitEvent(wst, scene->ev_mix[p], 0));
     OdbCallback cb;
     {
         std::lock_guard<std::mutex> lk(scene->mu);
@@ -311,9 +315,19 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     const int ns = cb.n_sources, nt = cb.n_tiles;
     const int nb = (int)scene->buffered.order.size();
 
-    ODB_TRY(ensure_idle(scene, scene->d_counters[p], ODB_CNT_WORDS));
+    for (int q = 0; q < 2; q++) {  // job counters: zeroed at creation, afterwards by k_reduce_tiles of the previous callback
+        if (!scene->d_counters[q].p) {
+            ODB_TRY(ensure_idle(scene, scene->d_counters[q], ODB_CNT_WORDS));
+            ODB_CUDA(cudaMemsetAsync(scene->d_counters[q].p, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
+        }
+    }
     uint32_t* counters = scene->d_counters[p].p;
-    ODB_CUDA(cudaMemsetAsync(counters, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
+    if (scene->pipelined) {  // the next walk may overlap this callback's reduce: reset on the walk stream instead
+        ODB_CUDA(cudaMemsetAsync(counters, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
+    } else if (nt == 0) {    // no reduce kernel will run for this callback
+        ODB_CUDA(cudaMemsetAsync(scene->d_counters[0].p, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
+        ODB_CUDA(cudaMemsetAsync(scene->d_counters[1].p, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
+    }
     if (nb > 0) {  // buffered set first (spatial.rs:395-433)
         OdbCallback cbb = cb;
         cbb.n_sources = nb;
@@ -329,14 +343,11 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
                              (int)scene->seek.removed_cap, counters, cb, wst);
         launches++;
     }
-    ODB_CUDA(cudaEventRecord(scene->ev_walk[p], wst));
-    {   // start the read-back of what walk_set removed; folded in by a later call without waiting
-        std::lock_guard<std::mutex> lk(scene->mu);
-        ODB_TRY(scene->seek.post_callback(ctx, wst));
-        ODB_TRY(scene->buffered.post_callback(ctx, wst));
+    if (scene->pipelined) {
+        ODB_CUDA(cudaEventRecord(scene->ev_walk[p], wst));
+        // ---- stage 2 on the context's stream: O(sources x frames) -----------------------------------------------------
+        ODB_CUDA(cudaStreamWaitEvent(st, scene->ev_walk[p], 0));
     }
-    // ---- stage 2 on the context's stream: O(sources x frames) ---------------------------------------------------------
-    ODB_CUDA(cudaStreamWaitEvent(st, scene->ev_walk[p], 0));
     int n_ring = 0;
     if (nb > 0) {  // extend the delay rings, then mix from them
         odb_launch_ring_write(scene->d_ring_writes[p].p, nb, st);
@@ -372,10 +383,16 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             launches++;
         }
         odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_partials_ring.p, n_ring,
-                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0, dev_out, (int)n_frames, nt, 2, scene->epilogue, st);
+                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0, /*zero_counters=*/scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p, dev_out,
+                          (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }
-    ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
+    if (scene->pipelined) ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
+    {   // start the read-back of what walk_set removed; folded in by a later call without waiting
+        std::lock_guard<std::mutex> lk(scene->mu);
+        ODB_TRY(scene->seek.post_callback(ctx, wst));
+        ODB_TRY(scene->buffered.post_callback(ctx, wst));
+    }
     scene->last_launches = launches;
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
@@ -394,8 +411,9 @@ extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, ui
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
     std::lock_guard<std::mutex> lk(scene->mu);
-    ODB_TRY(scene->buffered.fold_removed(ctx, scene->wst, true));
-    return scene->seek.fold_removed(ctx, scene->wst, true);  // like the reference, removals are visible when sample returns
+    cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
+    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true));
+    return scene->seek.fold_removed(ctx, ws, true);  // like the reference, removals are visible when sample returns
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {
@@ -427,7 +445,7 @@ static int read_source(void* owner, odb_source src, OdbSource* out, bool* stale,
         if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
     // the source table is written on the scene's walk stream (on the context's stream for a mixer)
     cudaStream_t rs = ctx->stream;
-    if (*(uint32_t*)owner == ODB_KIND_SCENE) rs = ((odb_scene*)owner)->wst;
+    if (*(uint32_t*)owner == ODB_KIND_SCENE && ((odb_scene*)owner)->pipelined) rs = ((odb_scene*)owner)->wst;
     ODB_CUDA(cudaMemcpyAsync(out, set->d_src.p + slot, sizeof(OdbSource), cudaMemcpyDeviceToHost, rs));
     ODB_CUDA(cudaStreamSynchronize(rs));
     return ODB_OK;
@@ -546,7 +564,14 @@ extern "C" int odb_last_job_counters(void* owner, uint32_t out[4]) {
 extern "C" int odb_set_kernel_variant(void* owner, int variant) {
     if (!owner) return odb_fail(ODB_E_INVALID, "NULL argument");
     uint32_t kind = *(uint32_t*)owner;
-    if (kind == ODB_KIND_SCENE) { ((odb_scene*)owner)->variant = variant; return ODB_OK; }
+    if (kind == ODB_KIND_SCENE) {
+        odb_scene* sc = (odb_scene*)owner;
+        cudaStreamSynchronize(sc->wst);
+        cudaStreamSynchronize(sc->ctx->stream);
+        sc->variant = variant & 0xFF;
+        sc->pipelined = (variant & 0x100) != 0;
+        return ODB_OK;
+    }
     if (kind == ODB_KIND_MIXER) return odb_mixer_set_variant(owner, variant);
     return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
 }

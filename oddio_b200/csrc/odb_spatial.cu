@@ -52,6 +52,7 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 __global__ void __launch_bounds__(32) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                    OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
                                                    int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+    pdl_launch_dependents();  // the mix kernel may be set up now; it waits for this grid before reading jobs
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cb.n_sources) return;
     const uint32_t slot = order[idx];
@@ -188,6 +189,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
                                                             float* __restrict__ partials, int only_flagged,
                                                             const uint32_t* __restrict__ counters) {
     extern __shared__ float smem[];
+    pdl_launch_dependents();
+    pdl_wait();  // jobs and counters come from the walk kernel (two launches back in the stream)
     // nothing flagged for this kernel: leave at once; k_reduce_tiles reads the same counter and skips our tiles
     if (only_flagged && counters[ODB_CNT_GENERAL] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,9 +279,14 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
                                                                  const float* __restrict__ pb, int nb,
                                                                  const float* __restrict__ pc, int nc,
                                                                  const uint32_t* __restrict__ counters, int b_is_general,
+                                                                 uint32_t* __restrict__ zero_counters,
                                                                  float* __restrict__ out, int n_frames, int channels,
                                                                  int epilogue) {
     __shared__ float fold[RED_GROUPS][32];
+    pdl_wait();  // partial tiles come from the mix kernels launched just before
+    // reset the other parity's job counters for the next callback (keeps the stream free of memset nodes
+    // between the kernels, which programmatic dependent launch needs)
+    if (zero_counters && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < ODB_CNT_WORDS) zero_counters[threadIdx.x] = 0u;
     const int tl = blockIdx.y;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int f = blockIdx.x * 32 + lane;  // float index inside the tile
@@ -334,13 +342,6 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
                           uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
-    // Same shared-memory carve-out as k_mix_fast (which takes all of it): an SM only runs kernels of one
-    // carve-out configuration at a time, and this kernel is meant to run underneath the previous callback's mix.
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        cudaFuncSetAttribute(k_walk_seek, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-    }
     k_walk_seek<<<(cb.n_sources + 31) / 32, 32, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
 }
 
@@ -360,12 +361,14 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
         attr_set = true;
     }
     dim3 grid(n_ctas, n_tiles);
-    k_mix_general<GEN_WARPS><<<grid, GEN_WARPS * 32, smem, st>>>(jobs, n_sources, partials, only_flagged, counters);
-    return cudaGetLastError();
+    return odb_launch_pdl(k_mix_general<GEN_WARPS>, grid, dim3(GEN_WARPS * 32), (size_t)smem, st, jobs, n_sources, partials, only_flagged,
+                          counters);
 }
 void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const float* pc, int nc, const uint32_t* counters,
-                       int b_is_general, float* out, int n_frames, int n_tiles, int channels, int epilogue, cudaStream_t st) {
+                       int b_is_general, uint32_t* zero_counters, float* out, int n_frames, int n_tiles, int channels,
+                       int epilogue, cudaStream_t st) {
     if (n_frames <= 0) return;
     dim3 grid(channels * ODB_TILE_FRAMES / 32, n_tiles);
-    k_reduce_tiles<<<grid, 32 * RED_GROUPS, 0, st>>>(pa, na, pb, nb, pc, nc, counters, b_is_general, out, n_frames, channels, epilogue);
+    odb_launch_pdl(k_reduce_tiles, grid, dim3(32 * RED_GROUPS), 0, st, pa, na, pb, nb, pc, nc, counters, b_is_general, zero_counters, out, n_frames,
+                   channels, epilogue);
 }
