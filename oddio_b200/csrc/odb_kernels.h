@@ -11,6 +11,12 @@
 // full half fits up to ds = 1.17 (512 * 1.17 + ear skew + slack), shorter callbacks up to ODB_FAST_DS_MAX.
 #define ODB_FAST_PCM_CAP 640
 #define ODB_FAST_HALF_CHUNKS 2
+// k_walk_seek runs 2 * ODB_WALK_CHUNK_SPLIT threads per source (ear x chunk group); measured on C3:
+// one thread per source 15.0 us, 2 threads (split 1) 13.6 us, 4 threads 18.0 us, 8 threads 20.4 us - the shared part
+// (motion smoothing, rotation) is evaluated redundantly by every thread of a source.
+#ifndef ODB_WALK_CHUNK_SPLIT
+#define ODB_WALK_CHUNK_SPLIT 1
+#endif
 
 // Launches `kernel` so that it may overlap the tail of the previous kernel in `st` (programmatic dependent
 // launch); the kernel must call odbk::pdl_wait() before it touches anything the previous kernel wrote.

@@ -122,7 +122,7 @@ __device__ __forceinline__ void load_source(OdbSource& dst, const OdbSource* __r
 // bookkeeping and the removal report. Returns false if the source is (now) stopped: it does not mix.
 __device__ __forceinline__ bool walk_common(OdbSource* sp, const OdbSource& s, const OdbCallback& cb, uint32_t slot,
                                             uint32_t* __restrict__ removed, int removed_cap, V3& prev_position,
-                                            V3& next_position, uint32_t& flags_out) {
+                                            V3& next_position, uint32_t& flags_out, const bool write = true) {
     const float elapsed = cb.elapsed;
     // --- motion refresh, spatial.rs:216-226
     V3 pos = {s.pos[0], s.pos[1], s.pos[2]}, vel = {s.vel[0], s.vel[1], s.vel[2]};
@@ -135,15 +135,19 @@ __device__ __forceinline__ bool walk_common(OdbSource* sp, const OdbSource& s, c
         state_dt = 0.0f;
         pos = npos; vel = nvel;
         flags &= ~ODB_SF_MOTION_FRESH;
-        sp->pos[0] = pos.x; sp->pos[1] = pos.y; sp->pos[2] = pos.z;
-        sp->vel[0] = vel.x; sp->vel[1] = vel.y; sp->vel[2] = vel.z;
+        if (write) {
+            sp->pos[0] = pos.x; sp->pos[1] = pos.y; sp->pos[2] = pos.z;
+            sp->vel[0] = vel.x; sp->vel[1] = vel.y; sp->vel[2] = vel.z;
+        }
     }
     // --- smoothed start/end positions in the listener's frame, spatial.rs:228-235
     prev_position = q_rotate(cb.prev_rot, smoothed_position(statep, state_dt, 0.0f, pos, vel));
     next_position = q_rotate(cb.rot, smoothed_position(statep, state_dt, elapsed, pos, vel));
     state_dt = state_dt + elapsed;  // :238
-    sp->prev_position[0] = statep.x; sp->prev_position[1] = statep.y; sp->prev_position[2] = statep.z;
-    sp->state_dt = state_dt;
+    if (write) {
+        sp->prev_position[0] = statep.x; sp->prev_position[1] = statep.y; sp->prev_position[2] = statep.z;
+        sp->state_dt = state_dt;
+    }
 
     // --- finished / stopped bookkeeping, spatial.rs:243-261
     const bool was_stopped = (flags & ODB_SF_STOPPED) != 0;
@@ -151,16 +155,16 @@ __device__ __forceinline__ bool walk_common(OdbSource* sp, const OdbSource& s, c
         float distance = v_norm(prev_position);
         if (flags & ODB_SF_HAS_FINISHED_FOR) {
             if (s.finished_for > distance / ODB_SPEED_OF_SOUND) flags |= ODB_SF_STOPPED;
-            else sp->finished_for = s.finished_for + elapsed;
+            else if (write) sp->finished_for = s.finished_for + elapsed;
         } else if (s.t >= s.t_end) {  // inner.is_finished(): frames.rs:204-206 through the wrappers
             flags |= ODB_SF_HAS_FINISHED_FOR;
-            sp->finished_for = elapsed;
+            if (write) sp->finished_for = elapsed;
         }
     }
-    sp->flags = flags;
+    if (write) sp->flags = flags;
     flags_out = flags;
     if (flags & ODB_SF_STOPPED) {
-        if (!was_stopped) {  // set.remove(i): report the slot so the host can swap_remove it from its Vec
+        if (!was_stopped && write) {  // set.remove(i): report the slot so the host can swap_remove it from its Vec
             uint32_t k = atomicAdd(removed, 1u);
             removed[1 + (k & (uint32_t)(removed_cap - 1))] = slot;
         }

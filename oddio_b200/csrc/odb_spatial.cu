@@ -47,126 +47,162 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 // ------------------------------------------------------------------------------------------
 // walk_set for the seek set (spatial.rs:191-265) plus everything of the mix closure
 // (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
-// cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213). One thread per source.
-// Writes one OdbJob per (tile, source) and the source's state for the next callback.
-__global__ void __launch_bounds__(32) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
-                                                   OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
-                                                   int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+// cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213).
+// 2*CS threads per source - one per (ear, group of 4/CS chunks of a tile) - because the work of one source
+// is a long chain of dependent high-latency operations (IEEE divides and square roots, f64 conversions):
+// with one thread per source the kernel took 15 us at 15 % issue utilisation. The threads of a source
+// evaluate the shared part (motion smoothing, listener rotation) redundantly and bit-identically; thread
+// (ear 0, group 0) writes the source's state. A thread reproduces the f64 cursor at the start of each of its
+// chunks with the reference's own sequence of additions (seek(prev.offset), then `t += f64(dt) * f64(m)` per
+// earlier chunk, the rewinding seek between the ears), so every (base, offset) pair is the one the serial
+// code computes. Writes one OdbJob per (tile, source) and the source's state for the next callback.
+template <int CS>
+__global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
+                                                    OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
+                                                    int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+    constexpr int TPS = 2 * CS;                  // threads per source
+    constexpr int CPT = ODB_TILE_CHUNKS / CS;    // chunks of a tile per thread
     pdl_launch_dependents();  // the mix kernel may be set up now; it waits for this grid before reading jobs
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cb.n_sources) return;
-    const uint32_t slot = order[idx];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = gtid / TPS, sub = threadIdx.x % TPS;
+    const int e = sub / CS, grp = sub % CS;  // this thread's ear and chunk group
+    const bool live = idx < cb.n_sources;    // dead lanes still take part in the shuffles below
+    const uint32_t slot = order[live ? idx : 0];
     OdbSource* sp = src + slot;
     OdbSource s;
     load_source(s, sp);
     const int n = cb.n_frames;
     const float elapsed = cb.elapsed;
     const int nt = cb.n_tiles, ns = cb.n_sources;
+    const bool leader = live && sub == 0;
     V3 prev_position, next_position;
     uint32_t flags;
-    if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position, flags)) {
+    const bool mixing = walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position, flags, leader);
+    if (!mixing && leader)
         for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
-        return;
-    }
-    double t = s.t;
+    const bool emit = mixing && live;
     const double rate = s.rate;
 
-    // --- mix closure set-up, spatial.rs:446-468
+    // --- mix closure set-up, spatial.rs:446-468: this thread's ear
     const float nf = (float)n;
     const float ratef = (float)rate;  // `self.data.rate as f32` frames.rs:178
     const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
-    uint32_t jflags[4] = {0, 0, 0, 0};  // per tile (n_tiles <= 4 enforced by the host)
-    int wlo[8], whi[8];                 // per 512-frame half tile: PCM index range both ears can touch (|base| <= 2^29 or general)
-#pragma unroll
-    for (int h = 0; h < 8; h++) { wlo[h] = 0x7fffffff; whi[h] = -0x7fffffff; }
-    double t_sampled = t;
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        EarSt ps = ear_state(prev_position, e, s.radius);
-        EarSt nx = ear_state(next_position, e, s.radius);
-        t = t + (double)ps.offset;                                    // :449 seek(prev.offset)
-        float eff = (elapsed + nx.offset) - ps.offset;                // :451
-        float dt = eff / nf;                                          // :452
-        float d_gain = (nx.gain - ps.gain) / nf;                      // :453
-        float ds = dt * ratef;                                        // frames.rs:178
-        bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
-        bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
-#pragma unroll
-        for (int tl = 0; tl < 4; tl++) {  // tiles and chunks unrolled: the per-tile window bounds stay in registers
-            if (tl < nt) {
-#pragma unroll
-                for (int c = 0; c < ODB_TILE_CHUNKS; c++) {
-                    const int cg = tl * ODB_TILE_CHUNKS + c;
-                    if (cg < n_chunks) {
-                        int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
-                        double s0 = t * rate;                                     // frames.rs:177
-                        // frames.rs:179 `s0 as isize`: 32-bit conversion (saturating); any |s0| >= 2^29 is far
-                        // outside every Frames block and only ever yields zeros, which the general kernel produces
-                        int base = __double2int_rz(s0);
-                        float off0 = (float)(s0 - (double)base);                  // frames.rs:183 / :189
-                        if (off0 < 0.0f) general = true;                          // negative-fract quirk
-                        if (base > (1 << 29) || base < -(1 << 29)) { general = true; base = base > 0 ? (1 << 30) : -(1 << 30); }
-                        OdbJob* j = jobs + (size_t)tl * ns + idx;
-                        j->base[e][c] = base;
-                        j->off0[e][c] = off0;
-                        // PCM indices this chain can read: [base, base + trunc(offset_{m-1}) + 1]; the f32 chain stays
-                        // within 1e-2 of off0 + (m-1)*ds for m <= 256, so +4 on the f32 estimate is a safe upper bound.
-                        const float span = general ? 0.0f : __fmaf_rn((float)(m - 1), ds, off0);
-                        const int last = fast ? base + m : base + __float2int_rz(span) + 4;
-                        wlo[2 * tl + c / ODB_FAST_HALF_CHUNKS] = min(wlo[2 * tl + c / ODB_FAST_HALF_CHUNKS], base);
-                        whi[2 * tl + c / ODB_FAST_HALF_CHUNKS] = max(whi[2 * tl + c / ODB_FAST_HALF_CHUNKS], last);
-                        t = t + (double)dt * (double)m;                           // frames.rs:198
-                        t_sampled = t;
-                    }
-                }
-            }
+    const EarSt ps = ear_state(prev_position, e, s.radius);
+    const EarSt nx = ear_state(next_position, e, s.radius);
+    const float eff = (elapsed + nx.offset) - ps.offset;                // :451
+    const float dt = eff / nf;                                          // :452
+    const float d_gain = (nx.gain - ps.gain) / nf;                      // :453
+    const float ds = dt * ratef;                                        // frames.rs:178
+    const bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
+    const bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
+    // the left ear's scalars, needed by the right ear's threads to replay the cursor up to their own start
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, src_lane0 = lane - sub;
+    const float ps_off_l = __shfl_sync(full, ps.offset, src_lane0);
+    const float eff_l = __shfl_sync(full, eff, src_lane0);
+    const float dt_l = __shfl_sync(full, dt, src_lane0);
+    // cursor at the start of this thread's ear
+    double t = s.t;
+    if (e == 1) {  // left ear first: seek(prev.offset), all chunks, seek(-eff - prev.offset)  (:449-465)
+        t = t + (double)ps_off_l;
+        for (int cg = 0; cg < n_chunks; cg++) {
+            const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
+            t = t + (double)dt_l * (double)m;                           // frames.rs:198
         }
-        t = t + (double)(-eff - ps.offset);                           // :465
+        t = t + (double)(-eff_l - ps_off_l);
+    }
+    t = t + (double)ps.offset;                                          // :449 seek(prev.offset)
+    // this thread's chunks of every tile
+    double tc = t;                                                      // cursor at the start of chunk `cg_done`
+    int cg_done = 0;
+    uint32_t gen_tiles = 0;                                             // bit tl: something of tile tl needs the general kernel
+    int wlo[4][2], whi[4][2];                                           // per tile and 512-frame half
 #pragma unroll
-        for (int tl = 0; tl < 4; tl++) {
-            if (tl < nt) {
-                OdbJob* j = jobs + (size_t)tl * ns + idx;
-                j->ds[e] = ds; j->pg[e] = ps.gain; j->dg[e] = d_gain;
-                jflags[tl] |= (fast ? (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R) : 0u) | (general ? ODB_JF_GENERAL : 0u);
+    for (int tl = 0; tl < 4; tl++) {
+        wlo[tl][0] = wlo[tl][1] = 0x7fffffff;
+        whi[tl][0] = whi[tl][1] = -0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int c = grp * CPT + k, cg = tl * ODB_TILE_CHUNKS + c;
+            if (tl < nt && cg < n_chunks) {
+                for (; cg_done < cg; cg_done++) tc = tc + (double)dt * (double)ODB_SPATIAL_CHUNK;  // earlier chunks are full ones
+                const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
+                const double s0 = tc * rate;                            // frames.rs:177
+                // frames.rs:179 `s0 as isize`: 32-bit conversion (saturating); any |s0| >= 2^29 is far outside every
+                // Frames block and only ever yields zeros, which the general kernel produces
+                int base = __double2int_rz(s0);
+                const float off0 = (float)(s0 - (double)base);          // frames.rs:183 / :189
+                bool g = general || off0 < 0.0f;                        // negative-fract quirk
+                if (base > (1 << 29) || base < -(1 << 29)) { g = true; base = base > 0 ? (1 << 30) : -(1 << 30); }
+                if (emit) {
+                    OdbJob* j = jobs + (size_t)tl * ns + idx;
+                    j->base[e][c] = base;
+                    j->off0[e][c] = off0;
+                }
+                // PCM indices this chain can read: [base, base + trunc(offset_{m-1}) + 1]; the f32 chain stays within
+                // 1e-2 of off0 + (m-1)*ds for m <= 256, so +4 on the f32 estimate is a safe upper bound.
+                const float span = g ? 0.0f : __fmaf_rn((float)(m - 1), ds, off0);
+                const int last = fast ? base + m : base + __float2int_rz(span) + 4;
+                const int h = c / ODB_FAST_HALF_CHUNKS;
+                wlo[tl][h] = min(wlo[tl][h], base);
+                whi[tl][h] = max(whi[tl][h], last);
+                if (g) gen_tiles |= 1u << tl;
             }
         }
     }
-    t = t + (double)elapsed;                                          // :468
-    sp->t = t;
-    // frames.rs:199-200 stores (t * rate) as isize at the end of every sample() call; only the last store (right
-    // ear, last chunk) is observable, and the seeks that follow do not touch sample_t
-    if (n_chunks > 0) sp->sample_t = (long long)(t_sampled * rate);
+    // per tile: ear-level job fields, window per half and flags (reduced over the threads of the source)
     uint32_t n_general = 0, n_fast = 0;
 #pragma unroll
     for (int tl = 0; tl < 4; tl++) {
         if (tl >= nt) break;
-        OdbJob* j = jobs + (size_t)tl * ns + idx;
-        j->pcm = s.pcm; j->len = s.len;
-        j->fixed_gain = s.fixed_gain;
-        j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
-        // window for the staged (fast) mix kernel: 16-byte aligned start, whole float4s, inside the
-        // zero-padded Frames block; anything else goes to the general kernel
-        uint32_t f = jflags[tl];
+        uint32_t f = ((gen_tiles >> tl) & 1u) ? ODB_JF_GENERAL : 0u;
         int ws[2], wl[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            int lo = wlo[tl][h], hi = whi[tl][h];
+#pragma unroll
+            for (int x = 1; x < TPS; x <<= 1) {  // over the ears and chunk groups of this source
+                lo = min(lo, __shfl_xor_sync(full, lo, x));
+                hi = max(hi, __shfl_xor_sync(full, hi, x));
+            }
             ws[h] = 0; wl[h] = 0;
-            if (whi[2 * tl + h] >= wlo[2 * tl + h]) {  // the half has frames
-                ws[h] = wlo[2 * tl + h] & ~3;
-                wl[h] = ((whi[2 * tl + h] - ws[h] + 1) + 3) & ~3;
-                if (!(f & ODB_JF_GENERAL) && (wl[h] > ODB_FAST_PCM_CAP || ws[h] < -ODB_PCM_PAD || ws[h] + wl[h] > s.len + ODB_PCM_PAD))
-                    f |= ODB_JF_GENERAL;
+            if (hi >= lo) {  // the half has frames
+                ws[h] = lo & ~3;
+                wl[h] = ((hi - ws[h] + 1) + 3) & ~3;
+                if (wl[h] > ODB_FAST_PCM_CAP || ws[h] < -ODB_PCM_PAD || ws[h] + wl[h] > s.len + ODB_PCM_PAD) f |= ODB_JF_GENERAL;
             }
         }
+        if (grp == 0) f |= fast ? (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R) : 0u;
+#pragma unroll
+        for (int x = 1; x < TPS; x <<= 1) f |= __shfl_xor_sync(full, f, x);
         if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
         if (cb.force_general) f |= ODB_JF_GENERAL;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            j->window[h][0] = ws[h];
-            j->window[h][1] = (f & ODB_JF_GENERAL) ? 0 : wl[h];
+        if (emit) {
+            OdbJob* j = jobs + (size_t)tl * ns + idx;
+            if (grp == 0) { j->ds[e] = ds; j->pg[e] = ps.gain; j->dg[e] = d_gain; }
+            if (sub == 0) {
+                j->window[0][0] = ws[0]; j->window[0][1] = (f & ODB_JF_GENERAL) ? 0 : wl[0];
+                j->window[1][0] = ws[1]; j->window[1][1] = (f & ODB_JF_GENERAL) ? 0 : wl[1];
+                j->pcm = s.pcm; j->len = s.len;
+                j->fixed_gain = s.fixed_gain;
+                j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
+                j->flags = f;
+                if (f & ODB_JF_GENERAL) n_general++; else n_fast++;
+            }
         }
-        j->flags = f;
-        if (f & ODB_JF_GENERAL) n_general++; else n_fast++;
+    }
+    if (emit && sub == CS) {  // (right ear, group 0): finish the cursor, :465-468
+        double te = t;
+        for (int cg = 0; cg < n_chunks; cg++) {
+            const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
+            te = te + (double)dt * (double)m;
+        }
+        // frames.rs:199-200 stores (t * rate) as isize at the end of every sample() call; only the last store
+        // (right ear, last chunk) is observable, and the seeks that follow do not touch sample_t
+        if (n_chunks > 0) sp->sample_t = (long long)(te * rate);
+        te = te + (double)(-eff - ps.offset);                           // :465
+        te = te + (double)elapsed;                                      // :468
+        sp->t = te;
     }
     if (n_general) atomicAdd(counters + ODB_CNT_GENERAL, n_general);
     if (n_fast) atomicAdd(counters + ODB_CNT_FAST, n_fast);
@@ -275,6 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
 // (tanh.rs:24-28, reinhard.rs:30-34) and writes the interleaved stereo output. Each block owns 32
 // consecutive output floats; its 8 warps take every 8th partial tile, then fold through shared memory.
 #define RED_GROUPS 16
+
 __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* __restrict__ pa, int na,
                                                                  const float* __restrict__ pb, int nb,
                                                                  const float* __restrict__ pc, int nc,
@@ -342,7 +379,8 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
                           uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
-    k_walk_seek<<<(cb.n_sources + 31) / 32, 32, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
+    constexpr int CS = ODB_WALK_CHUNK_SPLIT;
+    k_walk_seek<CS><<<(cb.n_sources * 2 * CS + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
 }
 
 static const int GEN_WARPS = 8;
