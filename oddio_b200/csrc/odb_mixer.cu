@@ -134,7 +134,7 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
             const bool use_unit = mixer->variant != 1;
             cudaError_t e;
             if (use_unit) {
-                n_unit = odb_mixer_ctas(ns, ctx->sm_count, ch == 1 ? 4 : 2);
+                n_unit = odb_mixer_ctas(ns, ctx->sm_count, ch == 1 ? 3 : 1);
                 ODB_TRY(mixer->d_partials_unit.ensure((size_t)nt * n_unit * tile_floats, st, false));
                 e = odb_launch_mixer_unit(mixer->d_jobs.p, ns, nt, ch, mixer->d_partials_unit.p, n_unit, st);
                 if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mixer_unit launch failed: %s", cudaGetErrorString(e));

@@ -6,6 +6,7 @@
 
 #include "odb_kernels.h"
 #include "odb_math.cuh"
+#include "odb_async.cuh"
 
 namespace odbk {
 
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
         }
         // what the streaming kernel may touch: frames [base, base + n] of the zero-padded block
         const long long pad_frames = ODB_PCM_PAD / ch;
-        if (!unit || off0 < 0.0f || base < -(pad_frames - 1) || base + n + 1 > (long long)s.len + pad_frames - 1 ||
+        // (4 frames of slack on both sides: the bulk copy rounds its window to 16-byte boundaries)
+        if (!unit || off0 < 0.0f || base < -(pad_frames - 4) || base + n + 1 > (long long)s.len + pad_frames - 4 ||
             base > (1ll << 29) || base < -(1ll << 29) || cb.force_general)
             jf |= ODB_JF_GENERAL;
         j.flags = jf;
@@ -91,65 +93,108 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
 
 // ------------------------------------------------------------------------------------------
 // Streaming kernel, ds ~= 1 path: out[i] += ((a + fract * (b - a)) * fixed_gain) * g with a = x[base+i],
-// b = x[base+i+1] read straight from HBM (coalesced; the neighbour comes from L1), one warp per
-// (source, tile), lane l owns frames l, l+32, ...; 1024*CH/32 register accumulators per lane.
-// Multiplying by a gain of exactly 1.0 is the identity, so the reference's `if g != 1.0` (gain.rs:111)
-// and the absence of a FixedGain need no branches.
-template <int CH, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_mixer_unit(const OdbMixJob* __restrict__ jobs, int n_sources,
-                                                           float* __restrict__ partials) {
-    extern __shared__ float smem[];
+// b = x[base+i+1]. One warp per (source, chunk); the chunk's PCM - frames [base, base+n], one contiguous
+// block of (n+1)*CH floats - is brought into the warp's shared-memory buffer by one bulk async copy (TMA)
+// while the warp is still consuming the previous source from its other buffer, so HBM sees long contiguous
+// requests with two of them in flight per warp. Lane l owns frames l, l+32, ... (conflict-free LDS) and keeps
+// 1024*CH/32 register accumulators. Multiplying by a gain of exactly 1.0 is the identity, so the reference's
+// `if g != 1.0` (gain.rs:111) and the absence of a FixedGain need no branches.
+template <int CH>
+struct MixerStream {
+    static constexpr int WARPS = CH == 2 ? 12 : 8;                             // stereo: one 12-warp CTA per SM; mono: three 8-warp CTAs
+    static constexpr int BUF_FLOATS = (ODB_MIXER_CHUNK + 1) * CH + 8;          // window + alignment slack, multiple of 4
+    static constexpr int BUF_BYTES = ((BUF_FLOATS * 4 + 127) / 128) * 128;
+    static constexpr int WARP_BYTES = 2 * BUF_BYTES;                            // >= one partial tile (1024*CH*4)
+    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES + WARPS * 16;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(MixerStream<CH>::WARPS * 32) k_mixer_unit(const OdbMixJob* __restrict__ jobs, int n_sources,
+                                                                            float* __restrict__ partials) {
+    typedef MixerStream<CH> C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tl = blockIdx.y;
-    const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    const int gw = blockIdx.x * C::WARPS + warp, GW = gridDim.x * C::WARPS;
+    const uint32_t buf_sa = smem_u32(smem_raw) + (uint32_t)(warp * C::WARP_BYTES);
+    const uint32_t bar_sa = smem_u32(smem_raw) + (uint32_t)(C::WARPS * C::WARP_BYTES + warp * 16);
+    if (lane == 0) {
+        mbar_init(bar_sa, 1);
+        mbar_init(bar_sa + 8, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
     constexpr int NACC = ODB_MIXER_CHUNK / 32;
     float acc[NACC][CH];
 #pragma unroll
     for (int j = 0; j < NACC; j++)
 #pragma unroll
         for (int c = 0; c < CH; c++) acc[j][c] = 0.0f;
+    const OdbMixJob* tile_jobs = jobs + (size_t)tl * n_sources;
 
-    for (int sidx = gw; sidx < n_sources; sidx += GW) {
-        const OdbMixJob* job = jobs + (size_t)tl * n_sources + sidx;
-        const uint32_t jf = job->flags;
-        if (jf & (ODB_JF_SKIP | ODB_JF_GENERAL)) continue;
-        const float* __restrict__ x = job->pcm + (long long)job->base * CH;
+    // next job at or after `from` (stride GW) that this kernel mixes; n_sources if none. Warp-uniform.
+    auto next_job = [&](int from) {
+        for (; from < n_sources; from += GW)
+            if (!(tile_jobs[from].flags & (ODB_JF_SKIP | ODB_JF_GENERAL))) break;
+        return from < n_sources ? from : n_sources;
+    };
+    // lane 0: start the copy of job `j`'s window into buffer `b`. The source address is rounded down to 16 bytes.
+    auto start_copy = [&](int j, uint32_t b) {
+        if (lane == 0) {
+            const OdbMixJob* job = tile_jobs + j;
+            const long long first = (long long)job->base * CH;                 // float index of frame `base`
+            const long long start = first & ~3ll;
+            const uint32_t floats = (uint32_t)((first - start) + (job->n_frames + 1) * CH + 3) & ~3u;
+            mbar_expect_tx(bar_sa + b * 8, floats * 4u);
+            bulk_g2s(buf_sa + b * C::BUF_BYTES, job->pcm + start, floats * 4u, bar_sa + b * 8);
+        }
+    };
+
+    uint32_t parity = 0, buf = 0;
+    int cur = next_job(gw);
+    if (cur < n_sources) start_copy(cur, buf);
+    while (cur < n_sources) {
+        const int nxt = next_job(cur + GW);
+        if (nxt < n_sources) start_copy(nxt, buf ^ 1u);
+        const OdbMixJob* job = tile_jobs + cur;
         const float fract = job->off0, fg = job->fixed_gain, g = job->g;
         const int n = job->n_frames;
+        const uint32_t skew = (uint32_t)(((long long)job->base * CH) & 3ll);   // floats the copy started early
+        const uint32_t x_sa = buf_sa + buf * C::BUF_BYTES + skew * 4u + (uint32_t)(lane * CH * 4);
+        mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
+        parity ^= 1u << buf;
 #pragma unroll
         for (int j = 0; j < NACC; j++) {
-            const int i = 32 * j + lane;
-            if (i < n) {
-                if (CH == 1) {
-                    const float a = x[i], b = x[i + 1];
-                    float v = a + fract * (b - a);      // frame::lerp (frame.rs:39-41)
-                    v = v * fg;                         // FixedGain (gain.rs:35)
-                    v = v * g;                          // Gain, steady state (gain.rs:112-114)
-                    acc[j][0] = acc[j][0] + v;          // frame::mix (frame.rs:44-46, mixer.rs:115)
-                } else {
-                    const float2 a = *reinterpret_cast<const float2*>(x + 2 * i);
-                    const float2 b = *reinterpret_cast<const float2*>(x + 2 * i + 2);
-                    float v0 = a.x + fract * (b.x - a.x), v1 = a.y + fract * (b.y - a.y);
-                    v0 = v0 * fg; v1 = v1 * fg;
-                    v0 = v0 * g; v1 = v1 * g;
-                    acc[j][0] = acc[j][0] + v0;
-                    acc[j][CH - 1] = acc[j][CH - 1] + v1;
-                }
+            if (32 * j >= n) break;  // warp-uniform
+            // a frame past the end of a short callback reads stale but in-bounds shared memory and is masked
+            const uint32_t a_sa = x_sa + (uint32_t)(32 * j * CH * 4);
+            const bool valid = 32 * j + lane < n;
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const float a = lds_f32(a_sa + (uint32_t)(c * 4)), b = lds_f32(a_sa + (uint32_t)((CH + c) * 4));
+                float v = a + fract * (b - a);      // frame::lerp (frame.rs:39-41)
+                v = v * fg;                         // FixedGain (gain.rs:35)
+                v = v * g;                          // Gain, steady state (gain.rs:112-114)
+                if (!valid) v = 0.0f;
+                acc[j][c] = acc[j][c] + v;          // frame::mix (frame.rs:44-46, mixer.rs:115)
             }
         }
+        __syncwarp();  // every lane is done with this buffer before it is refilled
+        buf ^= 1u;
+        cur = nxt;
     }
     // fold: warp -> CTA (fixed order) -> one partial tile per CTA
-    float* tile = smem + warp * (ODB_MIXER_CHUNK * CH);
+    float* tile = reinterpret_cast<float*>(smem_raw + warp * C::WARP_BYTES);
 #pragma unroll
     for (int j = 0; j < NACC; j++)
 #pragma unroll
         for (int c = 0; c < CH; c++) tile[(32 * j + lane) * CH + c] = acc[j][c];
     __syncthreads();
     float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * (ODB_MIXER_CHUNK * CH);
-    for (int f = threadIdx.x; f < ODB_MIXER_CHUNK * CH; f += WARPS * 32) {
+    for (int f = threadIdx.x; f < ODB_MIXER_CHUNK * CH; f += C::WARPS * 32) {
         float sum = 0.0f;
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) sum = sum + smem[w * (ODB_MIXER_CHUNK * CH) + f];
+        for (int w = 0; w < C::WARPS; w++) sum = sum + *reinterpret_cast<const float*>(smem_raw + w * C::WARP_BYTES + f * 4);
         dst[f] = sum;
     }
 }
@@ -262,14 +307,13 @@ static cudaError_t set_smem(K kernel, int bytes) {
 cudaError_t odb_launch_mixer_unit(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
                                   int n_ctas, cudaStream_t st) {
     dim3 grid(n_ctas, n_tiles);
-    const int smem = MIX_WARPS * ODB_MIXER_CHUNK * channels * (int)sizeof(float);
     cudaError_t e;
     if (channels == 1) {
-        if ((e = set_smem(k_mixer_unit<1, MIX_WARPS>, smem)) != cudaSuccess) return e;
-        k_mixer_unit<1, MIX_WARPS><<<grid, MIX_WARPS * 32, smem, st>>>(jobs, n_sources, partials);
+        if ((e = set_smem(k_mixer_unit<1>, MixerStream<1>::SMEM_BYTES)) != cudaSuccess) return e;
+        k_mixer_unit<1><<<grid, MixerStream<1>::WARPS * 32, MixerStream<1>::SMEM_BYTES, st>>>(jobs, n_sources, partials);
     } else {
-        if ((e = set_smem(k_mixer_unit<2, MIX_WARPS>, smem)) != cudaSuccess) return e;
-        k_mixer_unit<2, MIX_WARPS><<<grid, MIX_WARPS * 32, smem, st>>>(jobs, n_sources, partials);
+        if ((e = set_smem(k_mixer_unit<2>, MixerStream<2>::SMEM_BYTES)) != cudaSuccess) return e;
+        k_mixer_unit<2><<<grid, MixerStream<2>::WARPS * 32, MixerStream<2>::SMEM_BYTES, st>>>(jobs, n_sources, partials);
     }
     return cudaGetLastError();
 }
