@@ -11,6 +11,11 @@
 // full half fits up to ds = 1.17 (512 * 1.17 + ear skew + slack), shorter callbacks up to ODB_FAST_DS_MAX.
 #define ODB_FAST_PCM_CAP 640
 #define ODB_FAST_HALF_CHUNKS 2
+// Floats of PCM the staged mixer resampling kernel holds per (source, 1024-frame chunk): mono up to ds = 2.0,
+// stereo up to ds = 1.0 (two such buffers per warp).
+#define ODB_MIXER_RESAMPLE_CAP 2112
+#define ODB_MAGIC 8388608.0f          // 2^23: ulp 1, so x +rd 2^23 = 2^23 + floor(x)
+#define ODB_MAGIC_BITS 0x4B000000u
 // k_walk_seek runs 2 * ODB_WALK_CHUNK_SPLIT threads per source (ear x chunk group); measured on C3:
 // one thread per source 15.0 us, 2 threads (split 1) 13.6 us, 4 threads 18.0 us, 8 threads 20.4 us - the shared part
 // (motion smoothing, rotation) is evaluated redundantly by every thread of a source.
@@ -67,6 +72,9 @@ void odb_launch_walk_mixer(OdbSource* src, const uint32_t* order, OdbMixJob* job
 int odb_mixer_ctas(int n_sources, int sm_count, int per_sm);
 cudaError_t odb_launch_mixer_unit(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
                                   int n_ctas, cudaStream_t st);
+int odb_mixer_resample_ctas(int n_sources, int sm_count);
+cudaError_t odb_launch_mixer_resample(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
+                                      int n_ctas, const uint32_t* counters, cudaStream_t st);
 cudaError_t odb_launch_mixer_general(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
                                      int n_ctas, int only_flagged, const uint32_t* counters, cudaStream_t st);
 void odb_launch_walk_buffered(OdbSource* src, const uint32_t* order, OdbRingJob* jobs, OdbRingWrite* writes,
@@ -77,7 +85,8 @@ cudaError_t odb_launch_mix_ring(const OdbRingJob* jobs, int n_sources, int n_til
 // Sums partial tiles of `tile_floats` floats each (1024 frames x channels) into the interleaved output.
 // Up to three partial sets: a (staged / streaming kernel), b (general kernel; skipped when the walk kernel
 // counted no general job and b_is_general is set), c (ring kernel).
-// `zero_counters` (may be NULL): ODB_CNT_WORDS counters the kernel resets for the next callback.
+// `c_counter` >= 0: set c is skipped when that job counter is zero. `zero_counters` (may be NULL): ODB_CNT_WORDS
+// counters the kernel resets for the next callback.
 void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const float* pc, int nc, const uint32_t* counters,
-                       int b_is_general, uint32_t* zero_counters, float* out, int n_frames, int n_tiles, int channels,
-                       int epilogue, cudaStream_t st);
+                       int b_is_general, int c_counter, uint32_t* zero_counters, float* out, int n_frames, int n_tiles,
+                       int channels, int epilogue, cudaStream_t st);

@@ -93,8 +93,6 @@ constexpr int FAST_JOBS_OFF = FAST_WARPS * FAST_WARP_BYTES;                 // s
 constexpr int FAST_BARS_OFF = FAST_JOBS_OFF + FAST_WARPS * FAST_BATCH * 128;
 constexpr int FAST_SMEM_BYTES = FAST_BARS_OFF + FAST_WARPS * 16;
 static_assert(FAST_SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
-#define ODB_MAGIC 8388608.0f          // 2^23: ulp 1, so x +rd 2^23 = 2^23 + floor(x)
-#define ODB_MAGIC_BITS 0x4B000000u
 
 // One 256-frame chunk of one source. UL / UR: that ear is on the ds ~= 1 path (constant fraction, index
 // base + i); otherwise its cursor comes from the chain checkpoints. FULL: every frame of the chunk is

@@ -15,7 +15,7 @@ struct odb_mixer {
     int variant = 0;
     uint32_t last_launches = 0;
     DevBuf<OdbMixJob> d_jobs;
-    DevBuf<float> d_partials_unit, d_partials_gen;
+    DevBuf<float> d_partials_unit, d_partials_gen, d_partials_res;
     DevBuf<uint32_t> d_counters;
     DevBuf<float> d_out;
     PinBuf<float> h_out;
@@ -42,7 +42,7 @@ extern "C" int odb_mixer_destroy(odb_mixer* mixer) {
     cudaSetDevice(mixer->ctx->device);
     cudaStreamSynchronize(mixer->ctx->stream);
     mixer->set.release_all(mixer->ctx);
-    mixer->d_jobs.release(); mixer->d_partials_unit.release(); mixer->d_partials_gen.release();
+    mixer->d_jobs.release(); mixer->d_partials_unit.release(); mixer->d_partials_gen.release(); mixer->d_partials_res.release();
     mixer->d_counters.release(); mixer->d_out.release(); mixer->h_out.release();
     mixer->kind = 0;
     delete mixer;
@@ -129,10 +129,17 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
         launches++;
     }
     if (nt > 0) {
-        int n_unit = 0, n_gen = 0;
+        int n_unit = 0, n_gen = 0, n_res = 0;
         if (ns > 0) {
             const bool use_unit = mixer->variant != 1;
             cudaError_t e;
+            if (use_unit) {  // staged resampling kernel (leaves at once when the walk kernel counted no such job)
+                n_res = odb_mixer_resample_ctas(ns, ctx->sm_count);
+                ODB_TRY(mixer->d_partials_res.ensure((size_t)nt * n_res * tile_floats, st, false));
+                e = odb_launch_mixer_resample(mixer->d_jobs.p, ns, nt, ch, mixer->d_partials_res.p, n_res, mixer->d_counters.p, st);
+                if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mixer_resample launch failed: %s", cudaGetErrorString(e));
+                launches++;
+            }
             if (use_unit) {
                 n_unit = odb_mixer_ctas(ns, ctx->sm_count, ch == 1 ? 3 : 1);
                 ODB_TRY(mixer->d_partials_unit.ensure((size_t)nt * n_unit * tile_floats, st, false));
@@ -147,8 +154,8 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
             if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mixer_general launch failed: %s", cudaGetErrorString(e));
             launches++;
         }
-        odb_launch_reduce(mixer->d_partials_unit.p, n_unit, mixer->d_partials_gen.p, n_gen, nullptr, 0, mixer->d_counters.p,
-                          n_unit > 0 ? 1 : 0, nullptr, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
+        odb_launch_reduce(mixer->d_partials_unit.p, n_unit, mixer->d_partials_gen.p, n_gen, mixer->d_partials_res.p, n_res,
+                          mixer->d_counters.p, n_unit > 0 ? 1 : 0, n_res > 0 ? ODB_CNT_RESAMPLE : -1, nullptr, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
         launches++;
     }
     {

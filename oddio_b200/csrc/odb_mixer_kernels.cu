@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
     float gprev = s.gain_prev, gnext = s.gain_next, gprog = s.gain_progress;
     const float gstep = cb.interval / ODB_GAIN_SMOOTHING;                           // gain.rs:120
     long long sample_t = s.sample_t;
-    uint32_t n_general = 0, n_fast = 0;
+    uint32_t n_general = 0, n_fast = 0, n_resample = 0;
     for (int tl = 0; tl < nt; tl++) {
         const int n = min(ODB_MIXER_CHUNK, cb.n_frames - tl * ODB_MIXER_CHUNK);
         OdbMixJob j;
@@ -77,18 +77,26 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
         // what the streaming kernel may touch: frames [base, base + n] of the zero-padded block
         const long long pad_frames = ODB_PCM_PAD / ch;
         // (4 frames of slack on both sides: the bulk copy rounds its window to 16-byte boundaries)
-        if (!unit || off0 < 0.0f || base < -(pad_frames - 4) || base + n + 1 > (long long)s.len + pad_frames - 4 ||
-            base > (1ll << 29) || base < -(1ll << 29) || cb.force_general)
-            jf |= ODB_JF_GENERAL;
+        // frames the kernels may touch: unit path [base, base + n], resampling path [base, base + trunc(offset_{n-1}) + 1]
+        // (the f32 cursor stays within 0.1 of off0 + (n-1)*ds over 1024 steps; +4 is a safe bound)
+        const long long reach = unit ? n : (long long)((double)off0 + (double)(n - 1) * (double)ds) + 4;
+        const bool in_block = base >= -(pad_frames - 4) && base + reach + 1 <= (long long)s.len + pad_frames - 4 &&
+                              base < (1ll << 29) && base > -(1ll << 29);
+        if (cb.force_general || off0 < 0.0f || !in_block || (jf & ODB_JF_RAMP)) jf |= ODB_JF_GENERAL;
+        else if (!unit) {
+            if (ds > 0.0f && (reach + 2) * ch + 4 <= ODB_MIXER_RESAMPLE_CAP) jf |= ODB_JF_RESAMPLE;
+            else jf |= ODB_JF_GENERAL;
+        }
         j.flags = jf;
         jobs[(size_t)tl * ns + idx] = j;
-        if (jf & ODB_JF_GENERAL) n_general++; else n_fast++;
+        if (jf & ODB_JF_GENERAL) n_general++; else if (jf & ODB_JF_RESAMPLE) n_resample++; else n_fast++;
     }
     sp->t = t;
     sp->sample_t = sample_t;
     sp->gain_prev = gprev; sp->gain_next = gnext; sp->gain_progress = gprog;
     if (n_general) atomicAdd(counters + ODB_CNT_GENERAL, n_general);
     if (n_fast) atomicAdd(counters + ODB_CNT_FAST, n_fast);
+    if (n_resample) atomicAdd(counters + ODB_CNT_RESAMPLE, n_resample);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(MixerStream<CH>::WARPS * 32) k_mixer_unit(cons
     // next job at or after `from` (stride GW) that this kernel mixes; n_sources if none. Warp-uniform.
     auto next_job = [&](int from) {
         for (; from < n_sources; from += GW)
-            if (!(tile_jobs[from].flags & (ODB_JF_SKIP | ODB_JF_GENERAL))) break;
+            if (!(tile_jobs[from].flags & (ODB_JF_SKIP | ODB_JF_GENERAL | ODB_JF_RESAMPLE))) break;
         return from < n_sources ? from : n_sources;
     };
     // lane 0: start the copy of job `j`'s window into buffer `b`. The source address is rounded down to 16 bytes.
@@ -184,6 +192,151 @@ __global__ void __launch_bounds__(MixerStream<CH>::WARPS * 32) k_mixer_unit(cons
         cur = nxt;
     }
     // fold: warp -> CTA (fixed order) -> one partial tile per CTA
+    float* tile = reinterpret_cast<float*>(smem_raw + warp * C::WARP_BYTES);
+#pragma unroll
+    for (int j = 0; j < NACC; j++)
+#pragma unroll
+        for (int c = 0; c < CH; c++) tile[(32 * j + lane) * CH + c] = acc[j][c];
+    __syncthreads();
+    float* dst = partials + ((size_t)tl * gridDim.x + blockIdx.x) * (ODB_MIXER_CHUNK * CH);
+    for (int f = threadIdx.x; f < ODB_MIXER_CHUNK * CH; f += C::WARPS * 32) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < C::WARPS; w++) sum = sum + *reinterpret_cast<const float*>(smem_raw + w * C::WARP_BYTES + f * 4);
+        dst[f] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Staged resampling kernel: FramesSignal's serial-cursor path (frames.rs:189-196) for chains with ds != 1
+// (Speed, PCM at another rate) and a gain at rest. Same construction as k_mix_fast: a warp takes 8
+// (source, chunk) jobs; lanes 0..7 walk the 1024 literal `offset += ds` steps of one job each and store
+// every 4th cursor value; then the jobs are consumed one by one from double-buffered TMA windows, lane l
+// owning frames l, l+32, ...: checkpoint + <= 3 literal additions, round-down magic add for index and
+// fraction, gather, lerp, FixedGain, Gain, accumulate. Unfused arithmetic: bit-identical per source.
+template <int CH>
+struct MixerResample {
+    static constexpr int WARPS = 8;
+    static constexpr int BATCH = 8;
+    static constexpr int POINTS = ODB_MIXER_CHUNK / 4;
+    static constexpr int ROW_BYTES = POINTS * 4 + 4;                            // +4 skews the banks between the 8 chain lanes
+    static constexpr int BUF_BYTES = ODB_MIXER_RESAMPLE_CAP * 4;                // 8448
+    static constexpr int WARP_BYTES = 2 * BUF_BYTES + ((BATCH * ROW_BYTES + 15) / 16) * 16;  // 25120
+    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES + WARPS * 16;
+    static_assert(WARP_BYTES >= ODB_MIXER_CHUNK * CH * 4, "the warp region doubles as its partial tile");
+};
+
+template <int CH>
+__global__ void __launch_bounds__(MixerResample<CH>::WARPS * 32) k_mixer_resample(const OdbMixJob* __restrict__ jobs, int n_sources,
+                                                                                 float* __restrict__ partials,
+                                                                                 const uint32_t* __restrict__ counters) {
+    typedef MixerResample<CH> C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (counters[ODB_CNT_RESAMPLE] == 0) return;  // k_reduce_tiles reads the same counter and skips our tiles
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tl = blockIdx.y;
+    const uint32_t buf_sa = smem_u32(smem_raw) + (uint32_t)(warp * C::WARP_BYTES);
+    const uint32_t offs_sa = buf_sa + 2 * C::BUF_BYTES;
+    const uint32_t bar_sa = smem_u32(smem_raw) + (uint32_t)(C::WARPS * C::WARP_BYTES + warp * 16);
+    if (lane == 0) {
+        mbar_init(bar_sa, 1);
+        mbar_init(bar_sa + 8, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    constexpr int NACC = ODB_MIXER_CHUNK / 32;
+    float acc[NACC][CH];
+#pragma unroll
+    for (int j = 0; j < NACC; j++)
+#pragma unroll
+        for (int c = 0; c < CH; c++) acc[j][c] = 0.0f;
+    const OdbMixJob* tile_jobs = jobs + (size_t)tl * n_sources;
+    const int gw = blockIdx.x * C::WARPS + warp, GW = gridDim.x * C::WARPS;
+    const int n_batches = (n_sources + C::BATCH - 1) / C::BATCH;
+    const int r = lane & 3;
+    uint32_t parity = 0, buf = 0;
+
+    auto start_copy = [&](int sidx, uint32_t b) {  // lane 0: window of job sidx -> buffer b (16-byte aligned start)
+        if (lane == 0) {
+            const OdbMixJob* job = tile_jobs + sidx;
+            const long long first = (long long)job->base * CH, start = first & ~3ll;
+            const int reach = (int)((double)job->off0 + (double)(job->n_frames - 1) * (double)job->ds) + 4;
+            const uint32_t floats = (uint32_t)((first - start) + (reach + 2) * CH + 3) & ~3u;
+            mbar_expect_tx(bar_sa + b * 8, floats * 4u);
+            bulk_g2s(buf_sa + b * C::BUF_BYTES, job->pcm + start, floats * 4u, bar_sa + b * 8);
+        }
+    };
+
+    for (int bi = gw; bi < n_batches; bi += GW) {
+        const int s0 = bi * C::BATCH;
+        uint32_t act = 0;
+#pragma unroll
+        for (int q = 0; q < C::BATCH; q++)
+            if (s0 + q < n_sources && (tile_jobs[s0 + q].flags & (ODB_JF_SKIP | ODB_JF_GENERAL | ODB_JF_RESAMPLE)) == ODB_JF_RESAMPLE)
+                act |= 1u << q;
+        if (!act) continue;
+        start_copy(s0 + __ffs(act) - 1, buf);
+        if (lane < C::BATCH && ((act >> lane) & 1u)) {  // literal cursor chains, one lane per job
+            const OdbMixJob* job = tile_jobs + s0 + lane;
+            float o = job->off0;
+            const float ds = job->ds;
+            const uint32_t dst = offs_sa + (uint32_t)(lane * C::ROW_BYTES);
+#pragma unroll 8
+            for (int m = 0; m < C::POINTS; m++) {
+                sts_f32(dst + (uint32_t)(m * 4), o);
+                o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds);
+            }
+        }
+        __syncwarp();
+        for (int q = 0; q < C::BATCH; q++) {
+            if (!((act >> q) & 1u)) continue;
+            const uint32_t rest = act >> (q + 1);
+            if (rest) start_copy(s0 + q + __ffs(rest), buf ^ 1u);
+            const OdbMixJob* job = tile_jobs + s0 + q;
+            const float ds = job->ds, fg = job->fixed_gain, g = job->g;
+            const int n = job->n_frames;
+            const uint32_t skew = (uint32_t)(((long long)job->base * CH) & 3ll);
+            // shared address of frame `base`, minus the magic bits the index arrives with
+            const uint32_t K = buf_sa + buf * C::BUF_BYTES + skew * 4u - (ODB_MAGIC_BITS * (uint32_t)(CH * 4));
+            const uint32_t row_sa = offs_sa + (uint32_t)(q * C::ROW_BYTES + (lane >> 2) * 4);
+            const float d1 = r >= 1 ? ds : 0.0f, d2 = r >= 2 ? ds : 0.0f, d3 = r >= 3 ? ds : 0.0f;
+            mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
+            parity ^= 1u << buf;
+            constexpr int ILP = 4;
+#pragma unroll
+            for (int j0 = 0; j0 < NACC; j0 += ILP) {
+                if (32 * j0 >= n) break;  // warp-uniform
+                float o[ILP], fr[ILP];
+                uint32_t ad[ILP];
+#pragma unroll
+                for (int u = 0; u < ILP; u++) o[u] = lds_f32(row_sa + (uint32_t)(32 * (j0 + u)));  // checkpoint (32j + lane) & ~3
+#pragma unroll
+                for (int u = 0; u < ILP; u++) o[u] = __fadd_rn(__fadd_rn(__fadd_rn(o[u], d1), d2), d3);
+#pragma unroll
+                for (int u = 0; u < ILP; u++) {
+                    const float t = __fadd_rd(o[u], ODB_MAGIC);         // 2^23 + trunc(offset), offset >= 0
+                    fr[u] = __fadd_rn(o[u], -__fadd_rn(t, -ODB_MAGIC)); // offset - trunc as f32 (frames.rs:193)
+                    ad[u] = K + __float_as_uint(t) * (uint32_t)(CH * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < ILP; u++) {
+                    const bool valid = 32 * (j0 + u) + lane < n;
+#pragma unroll
+                    for (int c = 0; c < CH; c++) {
+                        const float a = lds_f32(ad[u] + (uint32_t)(c * 4)), b = lds_f32(ad[u] + (uint32_t)((CH + c) * 4));
+                        float v = a + fr[u] * (b - a);  // frame::lerp (frame.rs:39-41)
+                        v = v * fg;                     // FixedGain (gain.rs:35)
+                        v = v * g;                      // Gain at rest (gain.rs:112-114)
+                        if (!valid) v = 0.0f;
+                        acc[j0 + u][c] = acc[j0 + u][c] + v;
+                    }
+                }
+            }
+            __syncwarp();
+            buf ^= 1u;
+        }
+        __syncwarp();
+    }
     float* tile = reinterpret_cast<float*>(smem_raw + warp * C::WARP_BYTES);
 #pragma unroll
     for (int j = 0; j < NACC; j++)
@@ -314,6 +467,24 @@ cudaError_t odb_launch_mixer_unit(const OdbMixJob* jobs, int n_sources, int n_ti
     } else {
         if ((e = set_smem(k_mixer_unit<2>, MixerStream<2>::SMEM_BYTES)) != cudaSuccess) return e;
         k_mixer_unit<2><<<grid, MixerStream<2>::WARPS * 32, MixerStream<2>::SMEM_BYTES, st>>>(jobs, n_sources, partials);
+    }
+    return cudaGetLastError();
+}
+
+int odb_mixer_resample_ctas(int n_sources, int sm_count) {
+    int want = (n_sources + 63) / 64;
+    return want < 1 ? 1 : (want > sm_count ? sm_count : want);
+}
+cudaError_t odb_launch_mixer_resample(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
+                                      int n_ctas, const uint32_t* counters, cudaStream_t st) {
+    dim3 grid(n_ctas, n_tiles);
+    cudaError_t e;
+    if (channels == 1) {
+        if ((e = set_smem(k_mixer_resample<1>, MixerResample<1>::SMEM_BYTES)) != cudaSuccess) return e;
+        k_mixer_resample<1><<<grid, MixerResample<1>::WARPS * 32, MixerResample<1>::SMEM_BYTES, st>>>(jobs, n_sources, partials, counters);
+    } else {
+        if ((e = set_smem(k_mixer_resample<2>, MixerResample<2>::SMEM_BYTES)) != cudaSuccess) return e;
+        k_mixer_resample<2><<<grid, MixerResample<2>::WARPS * 32, MixerResample<2>::SMEM_BYTES, st>>>(jobs, n_sources, partials, counters);
     }
     return cudaGetLastError();
 }

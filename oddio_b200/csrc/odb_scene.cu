@@ -383,7 +383,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             launches++;
         }
         odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_partials_ring.p, n_ring,
-                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0, /*zero_counters=*/scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p, dev_out,
+                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0, /*c_counter=*/-1, /*zero_counters=*/scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p, dev_out,
                           (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }

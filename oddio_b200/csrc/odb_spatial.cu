@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
                                                                  const float* __restrict__ pb, int nb,
                                                                  const float* __restrict__ pc, int nc,
                                                                  const uint32_t* __restrict__ counters, int b_is_general,
-                                                                 uint32_t* __restrict__ zero_counters,
+                                                                 int c_counter, uint32_t* __restrict__ zero_counters,
                                                                  float* __restrict__ out, int n_frames, int channels,
                                                                  int epilogue) {
     __shared__ float fold[RED_GROUPS][32];
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int f = blockIdx.x * 32 + lane;  // float index inside the tile
     if (b_is_general && counters[ODB_CNT_GENERAL] == 0) nb = 0;
+    if (c_counter >= 0 && counters[c_counter] == 0) nc = 0;  // that kernel left at once and wrote no tiles
     float sum = 0.0f;
     const size_t tile_floats = (size_t)ODB_TILE_FRAMES * channels;
     const float* p = pa + (size_t)tl * na * tile_floats + f;
@@ -403,10 +404,10 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
                           counters);
 }
 void odb_launch_reduce(const float* pa, int na, const float* pb, int nb, const float* pc, int nc, const uint32_t* counters,
-                       int b_is_general, uint32_t* zero_counters, float* out, int n_frames, int n_tiles, int channels,
-                       int epilogue, cudaStream_t st) {
+                       int b_is_general, int c_counter, uint32_t* zero_counters, float* out, int n_frames, int n_tiles,
+                       int channels, int epilogue, cudaStream_t st) {
     if (n_frames <= 0) return;
     dim3 grid(channels * ODB_TILE_FRAMES / 32, n_tiles);
-    odb_launch_pdl(k_reduce_tiles, grid, dim3(32 * RED_GROUPS), 0, st, pa, na, pb, nb, pc, nc, counters, b_is_general, zero_counters, out, n_frames,
+    odb_launch_pdl(k_reduce_tiles, grid, dim3(32 * RED_GROUPS), 0, st, pa, na, pb, nb, pc, nc, counters, b_is_general, c_counter, zero_counters, out, n_frames,
                    channels, epilogue);
 }

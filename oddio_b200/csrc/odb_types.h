@@ -127,11 +127,13 @@ struct __attribute__((aligned(16))) OdbRingWrite {
 #define ODB_JF_FIXED_GAIN 0x8u
 #define ODB_JF_RAMP 0x20u       // mixer: Gain is mid-transition during this chunk (gain.rs:118-121)
 #define ODB_JF_RAMP1 0x40u      // ring write: Gain is mid-transition during the second span
+#define ODB_JF_RESAMPLE 0x80u   // mixer: a resampling chain the staged resampling kernel takes (never together with GENERAL)
 #define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
 
 // Device counters written by the walk kernels each callback (uint32 each).
 #define ODB_CNT_GENERAL 0       // jobs flagged ODB_JF_GENERAL
 #define ODB_CNT_FAST 1          // jobs the fast mix kernel takes
+#define ODB_CNT_RESAMPLE 2      // mixer jobs the staged resampling kernel takes
 #define ODB_CNT_WORDS 4
 
 struct OdbQuat { float x, y, z, s; };
