@@ -165,7 +165,7 @@ int odb_source_cursor(void* owner, odb_source src, double* out_t, float* out_rin
 int odb_last_launch_count(void* owner, uint32_t* out);
 /* Per-callback job counters of the last *_sample* call on this owner, out[0] = (source, tile) jobs that
  * took the literal general kernel, out[1] = jobs that took the staged / streaming kernel, out[2] = jobs that took
- * the staged resampling kernel (mixer); out[3] reserved.
+ * the staged resampling kernel (mixer), out[3] = buffered-source jobs that took the literal ring kernel.
  * Synchronises the context's stream. Benchmarks assert out[0] == 0. */
 int odb_last_job_counters(void* owner, uint32_t out[4]);
 /* Kernel timing for roofline reports: when enabled, *_sample* brackets its mix kernel with CUDA events on

@@ -383,10 +383,10 @@ class _Aggregator(Signal):
 
     def last_job_counters(self) -> dict:
         """(source, tile) jobs of the last callback by kernel: literal general kernel, staged / streaming kernel,
-        staged resampling kernel (mixer only)."""
+        staged resampling kernel (mixer only), literal ring kernel (buffered sources whose reads wrap)."""
         out = (C.c_uint32 * 4)()
         check(_lib.load().odb_last_job_counters(self._h, out))
-        return {"general": int(out[0]), "staged": int(out[1]), "resampled": int(out[2])}
+        return {"general": int(out[0]), "staged": int(out[1]), "resampled": int(out[2]), "ring_literal": int(out[3])}
 
     def set_profiling(self, enabled: bool) -> None:
         check(_lib.load().odb_set_profiling(self._h, int(bool(enabled))))

@@ -77,11 +77,13 @@ cudaError_t odb_launch_mixer_resample(const OdbMixJob* jobs, int n_sources, int 
                                       int n_ctas, const uint32_t* counters, cudaStream_t st);
 cudaError_t odb_launch_mixer_general(const OdbMixJob* jobs, int n_sources, int n_tiles, int channels, float* partials,
                                      int n_ctas, int only_flagged, const uint32_t* counters, cudaStream_t st);
-void odb_launch_walk_buffered(OdbSource* src, const uint32_t* order, OdbRingJob* jobs, OdbRingWrite* writes,
-                              uint32_t* removed, int removed_cap, const OdbCallback& cb, cudaStream_t st);
+void odb_launch_walk_buffered(OdbSource* src, const uint32_t* order, OdbRingJob* jobs, OdbJob* fjobs, OdbRingWrite* writes,
+                              uint32_t* removed, int removed_cap, uint32_t* counters, uint32_t* literal_list,
+                              const OdbCallback& cb, cudaStream_t st);
 void odb_launch_ring_write(const OdbRingWrite* writes, int n_sources, cudaStream_t st);
 int odb_mix_ring_ctas(int n_sources, int sm_count);
-cudaError_t odb_launch_mix_ring(const OdbRingJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, cudaStream_t st);
+cudaError_t odb_launch_mix_ring(const OdbRingJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
+                                int only_flagged, const uint32_t* counters, const uint32_t* literal_list, cudaStream_t st);
 // Sums partial tiles of `tile_floats` floats each (1024 frames x channels) into the interleaved output.
 // Up to three partial sets: a (staged / streaming kernel), b (general kernel; skipped when the walk kernel
 // counted no general job and b_is_general is set), c (ring kernel).

@@ -20,8 +20,10 @@ __device__ __forceinline__ float rem_euclidf(float a, float b) {
 
 // One thread per buffered source.
 __global__ void __launch_bounds__(128) k_walk_buffered(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
-                                                       OdbRingJob* __restrict__ jobs, OdbRingWrite* __restrict__ writes,
-                                                       uint32_t* __restrict__ removed, int removed_cap, OdbCallback cb) {
+                                                       OdbRingJob* __restrict__ jobs, OdbJob* __restrict__ fjobs,
+                                                       OdbRingWrite* __restrict__ writes, uint32_t* __restrict__ removed,
+                                                       int removed_cap, uint32_t* __restrict__ counters,
+                                                       uint32_t* __restrict__ literal_list, OdbCallback cb) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cb.n_sources) return;
     const uint32_t slot = order[idx];
@@ -33,7 +35,10 @@ __global__ void __launch_bounds__(128) k_walk_buffered(OdbSource* __restrict__ s
     V3 prev_position, next_position;
     uint32_t flags;
     if (!walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position, flags)) {
-        for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
+        for (int tl = 0; tl < nt; tl++) {
+            jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
+            fjobs[(size_t)tl * cb.job_stride + cb.job_offset + idx].flags = ODB_JF_SKIP | ODB_JF_RING;
+        }
         writes[idx].flags = ODB_JF_SKIP;
         return;
     }
@@ -101,8 +106,14 @@ __global__ void __launch_bounds__(128) k_walk_buffered(OdbSource* __restrict__ s
     sp->ring_write = end;                                                         // ring.rs:40
 
     // --- per ear: clamp into the ring, cursor and gain set-up, spatial.rs:409-431 + ring.rs:57-58
+    // Every (tile, source) gets two records: an OdbRingJob for the literal ring kernel and an OdbJob for the staged
+    // mix kernel, which reads the delay ring exactly like a Frames block whenever the tile's reads do not wrap
+    // around the ring (then Ring::sample's cursor is a plain `offset += ds` chain, ring.rs:59-77 without :67-75).
     const float nf = (float)n;
     const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
+    uint32_t wrap_tiles = 0;      // bit tl: some read of tile tl may wrap, or leaves the staged kernel's envelope
+    int wlo[4][2], whi[4][2];     // per tile and 512-frame half: ring index range both ears can touch
+    for (int tl = 0; tl < 4; tl++) { wlo[tl][0] = wlo[tl][1] = 0x7fffffff; whi[tl][0] = whi[tl][1] = -0x7fffffff; }
     for (int e = 0; e < 2; e++) {
         EarSt ps = ear_state(prev_position, e, s.radius);
         EarSt nx = ear_state(next_position, e, s.radius);
@@ -111,21 +122,61 @@ __global__ void __launch_bounds__(128) k_walk_buffered(OdbSource* __restrict__ s
         const float dt = (next_offset - prev_offset) / nf;                        // :417
         const float d_gain = (nx.gain - ps.gain) / nf;                            // :418
         const float rds = dt * ratef;                                             // ring.rs:58
+        const bool ds_ok = rds > 0.0f && rds <= ODB_FAST_DS_MAX;
         for (int cg = 0; cg < n_chunks; cg++) {
             const int tl = cg / ODB_TILE_CHUNKS, c = cg % ODB_TILE_CHUNKS;
+            const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
             const float tt = prev_offset + (float)(cg * ODB_SPATIAL_CHUNK) * dt;  // :423
-            jobs[(size_t)tl * ns + idx].off0[e][c] = rem_euclidf(end + tt * ratef, capf);  // ring.rs:57 (write is already `end`)
+            const float off0 = rem_euclidf(end + tt * ratef, capf);               // ring.rs:57 (write is already `end`)
+            jobs[(size_t)tl * ns + idx].off0[e][c] = off0;
+            OdbJob* fj = fjobs + (size_t)tl * cb.job_stride + cb.job_offset + idx;
+            fj->base[e][c] = 0;
+            fj->off0[e][c] = off0;
+            const int lo = (int)off0;
+            const int hi = ds_ok ? (int)__fmaf_rn((float)(m - 1), rds, off0) + 4 : 0x7ffffff0;
+            if (!ds_ok || lo < 0 || hi > s.ring_cap - 2) wrap_tiles |= 1u << tl;  // x + 1 must stay below buffer.len()
+            const int h = c / ODB_FAST_HALF_CHUNKS;
+            wlo[tl][h] = min(wlo[tl][h], lo);
+            whi[tl][h] = max(whi[tl][h], hi);
         }
         for (int tl = 0; tl < nt; tl++) {
             OdbRingJob* j = jobs + (size_t)tl * ns + idx;
             j->ds[e] = rds; j->pg[e] = ps.gain; j->dg[e] = d_gain;
+            OdbJob* fj = fjobs + (size_t)tl * cb.job_stride + cb.job_offset + idx;
+            fj->ds[e] = rds; fj->pg[e] = ps.gain; fj->dg[e] = d_gain;
         }
     }
+    uint32_t n_staged = 0;
     for (int tl = 0; tl < nt; tl++) {
+        uint32_t f = ODB_JF_RING;
+        if (((wrap_tiles >> tl) & 1u) || cb.force_general) f |= ODB_JF_GENERAL;
+        int ws[2] = {0, 0}, wl[2] = {0, 0};
+        for (int h = 0; h < 2; h++) {
+            if (whi[tl][h] >= wlo[tl][h] && !(f & ODB_JF_GENERAL)) {
+                ws[h] = wlo[tl][h] & ~3;
+                wl[h] = ((whi[tl][h] - ws[h] + 1) + 3) & ~3;
+                if (wl[h] > ODB_FAST_PCM_CAP || ws[h] + wl[h] > s.ring_cap) f |= ODB_JF_GENERAL;
+            }
+        }
+        OdbJob* fj = fjobs + (size_t)tl * cb.job_stride + cb.job_offset + idx;
+        fj->pcm = s.ring; fj->len = s.ring_cap; fj->fixed_gain = 1.0f;
+        fj->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
+        for (int h = 0; h < 2; h++) {
+            fj->window[h][0] = ws[h];
+            fj->window[h][1] = (f & ODB_JF_GENERAL) ? 0 : wl[h];
+        }
+        fj->flags = f;
         OdbRingJob* j = jobs + (size_t)tl * ns + idx;
-        j->ring = s.ring; j->cap = s.ring_cap; j->flags = 0u;
+        j->ring = s.ring; j->cap = s.ring_cap; j->flags = (f & ODB_JF_GENERAL) ? ODB_JF_GENERAL : 0u;
         j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
+        if (f & ODB_JF_GENERAL) {  // compact list of the jobs k_mix_ring has to take: one warp each, no scanning
+            const uint32_t k = atomicAdd(counters + ODB_CNT_RING_GENERAL, 1u);
+            literal_list[k] = (uint32_t)(tl * ns + idx);
+        } else {
+            n_staged++;
+        }
     }
+    if (n_staged) atomicAdd(counters + ODB_CNT_FAST, n_staged);
 }
 
 // One warp per buffered source: fills the span(s) Ring::write hands to inner.sample().
@@ -143,13 +194,21 @@ __global__ void __launch_bounds__(256) k_ring_write(const OdbRingWrite* __restri
         const long long base = w.base[k];
         if (unit && !ramp) {  // frames.rs:183-187: every frame independent
             const float fract = w.off0[k], fg = w.fixed_gain, g = w.g[k];
-            for (int i = lane; i < m; i += 32) {
-                float a, b;
-                get_pair_mono(w.pcm, w.len, base + i, a, b);
-                float v = a + fract * (b - a);   // frame.rs:39-41
-                v = v * fg;                      // gain.rs:35 (x * 1.0 == x)
-                v = v * g;                       // gain.rs:112-114
-                dst[i] = v;
+            constexpr int U = 8;  // frames per lane whose loads are issued together
+            for (int i0 = lane; i0 < m; i0 += 32 * U) {
+                float a[U], b[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    a[u] = 0.0f; b[u] = 0.0f;
+                    if (i0 + 32 * u < m) get_pair_mono(w.pcm, w.len, base + i0 + 32 * u, a[u], b[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    float v = a[u] + fract * (b[u] - a[u]);   // frame.rs:39-41
+                    v = v * fg;                               // gain.rs:35 (x * 1.0 == x)
+                    v = v * g;                                // gain.rs:112-114
+                    if (i0 + 32 * u < m) dst[i0 + 32 * u] = v;
+                }
             }
         } else if (lane == 0) {  // serial cursor and/or serial gain ramp: literal
             float offset = w.off0[k], gprog = w.gprog[k];
@@ -186,8 +245,14 @@ __global__ void __launch_bounds__(256) k_ring_write(const OdbRingWrite* __restri
 // apply the gain ramp and accumulate in registers (lane l owns frames l, l+32, ...).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_mix_ring(const OdbRingJob* __restrict__ jobs, int n_sources,
-                                                         float* __restrict__ partials) {
+                                                         float* __restrict__ partials, int only_flagged,
+                                                         const uint32_t* __restrict__ counters,
+                                                         const uint32_t* __restrict__ literal_list) {
     extern __shared__ float smem[];
+    pdl_launch_dependents();
+    pdl_wait();
+    // nothing wraps this callback: leave at once; k_reduce_tiles reads the same counter and skips our tiles
+    if (only_flagged && counters[ODB_CNT_RING_GENERAL] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* fr_s = smem + warp * (4 * ODB_TILE_FRAMES);                             // [ear][1024] fractions
     int* ix_s = reinterpret_cast<int*>(fr_s + 2 * ODB_TILE_FRAMES);                // [ear][1024] ring indices
@@ -197,7 +262,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_ring(const OdbRingJob* __res
 #pragma unroll
     for (int j = 0; j < ODB_TILE_FRAMES / 32; j++) acc[j] = make_float2(0.0f, 0.0f);
 
-    for (int sidx = gw; sidx < n_sources; sidx += GW) {
+    // only_flagged: the walk kernel's compact list of (tile, source) jobs whose reads wrap; else every job of the tile
+    const int n_items = only_flagged ? (int)counters[ODB_CNT_RING_GENERAL] : n_sources;
+    for (int it = gw; it < n_items; it += GW) {
+        int sidx = it;
+        if (only_flagged) {
+            const uint32_t lin = literal_list[it];
+            if ((int)(lin / (uint32_t)n_sources) != tl) continue;
+            sidx = (int)(lin % (uint32_t)n_sources);
+        }
         const OdbRingJob* job = jobs + (size_t)tl * n_sources + sidx;
         if (job->flags & ODB_JF_SKIP) continue;
         const int nfr = job->n_frames;
@@ -262,10 +335,12 @@ using namespace odbk;
 
 static const int RING_WARPS = 8;
 
-void odb_launch_walk_buffered(OdbSource* src, const uint32_t* order, OdbRingJob* jobs, OdbRingWrite* writes,
-                              uint32_t* removed, int removed_cap, const OdbCallback& cb, cudaStream_t st) {
+void odb_launch_walk_buffered(OdbSource* src, const uint32_t* order, OdbRingJob* jobs, OdbJob* fjobs, OdbRingWrite* writes,
+                              uint32_t* removed, int removed_cap, uint32_t* counters, uint32_t* literal_list,
+                              const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
-    k_walk_buffered<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, writes, removed, removed_cap, cb);
+    k_walk_buffered<<<(cb.n_sources + 127) / 128, 128, 0, st>>>(src, order, jobs, fjobs, writes, removed, removed_cap, counters,
+                                                               literal_list, cb);
 }
 void odb_launch_ring_write(const OdbRingWrite* writes, int n_sources, cudaStream_t st) {
     if (n_sources <= 0) return;
@@ -275,11 +350,12 @@ int odb_mix_ring_ctas(int n_sources, int sm_count) {
     int want = (n_sources + RING_WARPS - 1) / RING_WARPS;
     return want < 1 ? 1 : (want > sm_count ? sm_count : want);
 }
-cudaError_t odb_launch_mix_ring(const OdbRingJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, cudaStream_t st) {
+cudaError_t odb_launch_mix_ring(const OdbRingJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
+                                int only_flagged, const uint32_t* counters, const uint32_t* literal_list, cudaStream_t st) {
     const int smem = RING_WARPS * 4 * ODB_TILE_FRAMES * (int)sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_mix_ring<RING_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     dim3 grid(n_ctas, n_tiles);
-    k_mix_ring<RING_WARPS><<<grid, RING_WARPS * 32, smem, st>>>(jobs, n_sources, partials);
-    return cudaGetLastError();
+    return odb_launch_pdl(k_mix_ring<RING_WARPS>, grid, dim3(RING_WARPS * 32), (size_t)smem, st, jobs, n_sources, partials, only_flagged,
+                          counters, literal_list);
 }

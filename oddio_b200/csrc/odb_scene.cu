@@ -34,6 +34,7 @@ struct odb_scene {
     DevBuf<uint32_t> d_counters[2];
     DevBuf<OdbRingJob> d_ring_jobs[2];
     DevBuf<OdbRingWrite> d_ring_writes[2];
+    DevBuf<uint32_t> d_ring_list[2];   // (tile, source) jobs the literal ring kernel takes, written by k_walk_buffered
     DevBuf<float> d_partials;
     DevBuf<float> d_partials_fast;
     DevBuf<float> d_partials_ring;
@@ -71,7 +72,7 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     scene->buffered.release_all(scene->ctx);
     for (int p = 0; p < 2; p++) {
         scene->d_jobs[p].release(); scene->d_counters[p].release();
-        scene->d_ring_jobs[p].release(); scene->d_ring_writes[p].release();
+        scene->d_ring_jobs[p].release(); scene->d_ring_writes[p].release(); scene->d_ring_list[p].release();
         cudaEventDestroy(scene->ev_walk[p]); cudaEventDestroy(scene->ev_mix[p]);
     }
     cudaStreamDestroy(scene->wst);
@@ -328,17 +329,25 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         ODB_CUDA(cudaMemsetAsync(scene->d_counters[0].p, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
         ODB_CUDA(cudaMemsetAsync(scene->d_counters[1].p, 0, ODB_CNT_WORDS * sizeof(uint32_t), wst));
     }
+    // One OdbJob array serves both sets: per tile the seek sources' records first, then the buffered sources'
+    // (whose "PCM" is their delay ring); the staged kernel mixes both in one launch.
+    const int ntot = ns + nb;
+    cb.job_stride = ntot;
+    cb.job_offset = 0;
+    if (ntot > 0) ODB_TRY(ensure_idle(scene, scene->d_jobs[p], (size_t)ntot * (nt > 0 ? nt : 1)));
     if (nb > 0) {  // buffered set first (spatial.rs:395-433)
         OdbCallback cbb = cb;
         cbb.n_sources = nb;
+        cbb.job_offset = ns;
         ODB_TRY(ensure_idle(scene, scene->d_ring_jobs[p], (size_t)nb * (nt > 0 ? nt : 1)));
         ODB_TRY(ensure_idle(scene, scene->d_ring_writes[p], (size_t)nb));
-        odb_launch_walk_buffered(scene->buffered.d_src.p, scene->buffered.d_order.p, scene->d_ring_jobs[p].p,
-                                 scene->d_ring_writes[p].p, scene->buffered.d_removed.p, (int)scene->buffered.removed_cap, cbb, wst);
+        ODB_TRY(ensure_idle(scene, scene->d_ring_list[p], (size_t)nb * (nt > 0 ? nt : 1)));
+        odb_launch_walk_buffered(scene->buffered.d_src.p, scene->buffered.d_order.p, scene->d_ring_jobs[p].p, scene->d_jobs[p].p,
+                                 scene->d_ring_writes[p].p, scene->buffered.d_removed.p, (int)scene->buffered.removed_cap,
+                                 counters, scene->d_ring_list[p].p, cbb, wst);
         launches++;
     }
     if (ns > 0) {
-        ODB_TRY(ensure_idle(scene, scene->d_jobs[p], (size_t)ns * (nt > 0 ? nt : 1)));
         odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs[p].p, scene->seek.d_removed.p,
                              (int)scene->seek.removed_cap, counters, cb, wst);
         launches++;
@@ -348,42 +357,48 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         // ---- stage 2 on the context's stream: O(sources x frames) -----------------------------------------------------
         ODB_CUDA(cudaStreamWaitEvent(st, scene->ev_walk[p], 0));
     }
+    const bool use_fast = scene->variant != 1;
     int n_ring = 0;
-    if (nb > 0) {  // extend the delay rings, then mix from them
+    if (nb > 0) {  // extend the delay rings (Ring::write), before anything reads them
         odb_launch_ring_write(scene->d_ring_writes[p].p, nb, st);
         launches++;
-        if (nt > 0) {
-            n_ring = odb_mix_ring_ctas(nb, ctx->sm_count);
-            ODB_TRY(ensure_idle(scene, scene->d_partials_ring, (size_t)nt * n_ring * 2 * ODB_TILE_FRAMES));
-            cudaError_t e = odb_launch_mix_ring(scene->d_ring_jobs[p].p, nb, nt, scene->d_partials_ring.p, n_ring, st);
-            if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_ring launch failed: %s", cudaGetErrorString(e));
-            launches++;
-        }
     }
     if (nt > 0) {
         int n_fast = 0, n_gen = 0;
-        if (ns > 0) {
-            const bool use_fast = scene->variant != 1;
-            if (use_fast) {  // staged kernel for everything the walk kernel did not flag
-                n_fast = odb_mix_fast_ctas(ns, ctx->sm_count);
+        if (ntot > 0) {
+            if (use_fast) {  // staged kernel for everything the walk kernels did not flag
+                n_fast = odb_mix_fast_ctas(ntot, ctx->sm_count);
                 ODB_TRY(ensure_idle(scene, scene->d_partials_fast, (size_t)nt * n_fast * 2 * ODB_TILE_FRAMES));
                 if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev0, st));
-                cudaError_t e = odb_launch_mix_fast(scene->d_jobs[p].p, ns, nt, scene->d_partials_fast.p, n_fast,
+                cudaError_t e = odb_launch_mix_fast(scene->d_jobs[p].p, ntot, nt, scene->d_partials_fast.p, n_fast,
                                                     /*mode=*/scene->variant == 2 ? 1 : 0, st);
                 if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_fast launch failed: %s", cudaGetErrorString(e));
                 if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev1, st));
                 launches++;
             }
-            // literal kernel for the flagged rest (exits at once when the walk kernel flagged nothing)
-            n_gen = odb_mix_general_ctas(use_fast ? (ns < 2048 ? ns : 2048) : ns, ctx->sm_count);
-            ODB_TRY(ensure_idle(scene, scene->d_partials, (size_t)nt * n_gen * 2 * ODB_TILE_FRAMES));
-            cudaError_t e = odb_launch_mix_general(scene->d_jobs[p].p, ns, nt, scene->d_partials.p, n_gen,
-                                                   /*only_flagged=*/use_fast ? 1 : 0, counters, st);
-            if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_general launch failed: %s", cudaGetErrorString(e));
-            launches++;
+            if (ns > 0) {
+                // literal kernel for the flagged rest of the seek set (exits at once when the walk kernel flagged nothing)
+                n_gen = odb_mix_general_ctas(use_fast ? (ns < 2048 ? ns : 2048) : ns, ctx->sm_count);
+                ODB_TRY(ensure_idle(scene, scene->d_partials, (size_t)nt * n_gen * 2 * ODB_TILE_FRAMES));
+                cudaError_t e = odb_launch_mix_general(scene->d_jobs[p].p, ntot, nt, scene->d_partials.p, n_gen,
+                                                       /*only_flagged=*/use_fast ? 1 : 0, counters, st);
+                if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_general launch failed: %s", cudaGetErrorString(e));
+                launches++;
+            }
+            if (nb > 0) {
+                // literal ring kernel for the buffered sources whose reads wrap around their ring this callback
+                n_ring = odb_mix_ring_ctas(use_fast ? (nb < 2048 ? nb : 2048) : nb, ctx->sm_count);
+                ODB_TRY(ensure_idle(scene, scene->d_partials_ring, (size_t)nt * n_ring * 2 * ODB_TILE_FRAMES));
+                cudaError_t e = odb_launch_mix_ring(scene->d_ring_jobs[p].p, nb, nt, scene->d_partials_ring.p, n_ring,
+                                                    /*only_flagged=*/use_fast ? 1 : 0, counters, scene->d_ring_list[p].p, st);
+                if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_ring launch failed: %s", cudaGetErrorString(e));
+                launches++;
+            }
         }
         odb_launch_reduce(scene->d_partials_fast.p, n_fast, scene->d_partials.p, n_gen, scene->d_partials_ring.p, n_ring,
-                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0, /*c_counter=*/-1, /*zero_counters=*/scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p, dev_out,
+                          counters, /*b_is_general=*/n_fast > 0 ? 1 : 0,
+                          /*c_counter=*/(n_fast > 0 && n_ring > 0) ? ODB_CNT_RING_GENERAL : -1,
+                          /*zero_counters=*/scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p, dev_out,
                           (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }

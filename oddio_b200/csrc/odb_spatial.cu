@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     load_source(s, sp);
     const int n = cb.n_frames;
     const float elapsed = cb.elapsed;
-    const int nt = cb.n_tiles, ns = cb.n_sources;
+    const int nt = cb.n_tiles, ns = cb.job_stride;
     const bool leader = live && sub == 0;
     V3 prev_position, next_position;
     uint32_t flags;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
     for (int sidx = gw; sidx < n_sources; sidx += GW) {
         const OdbJob* job = jobs + (size_t)tl * n_sources + sidx;
         const uint32_t jf = job->flags;
-        if (jf & ODB_JF_SKIP) continue;
+        if (jf & (ODB_JF_SKIP | ODB_JF_RING)) continue;  // flagged buffered-source jobs belong to k_mix_ring
         if (only_flagged && !(jf & ODB_JF_GENERAL)) continue;
         const int nfr = job->n_frames;
         if (lane < 2 * ODB_TILE_CHUNKS) {

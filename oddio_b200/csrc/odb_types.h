@@ -128,12 +128,14 @@ struct __attribute__((aligned(16))) OdbRingWrite {
 #define ODB_JF_RAMP 0x20u       // mixer: Gain is mid-transition during this chunk (gain.rs:118-121)
 #define ODB_JF_RAMP1 0x40u      // ring write: Gain is mid-transition during the second span
 #define ODB_JF_RESAMPLE 0x80u   // mixer: a resampling chain the staged resampling kernel takes (never together with GENERAL)
+#define ODB_JF_RING 0x100u      // the job belongs to a buffered source: pcm is its delay ring, flagged ones go to k_mix_ring
 #define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
 
 // Device counters written by the walk kernels each callback (uint32 each).
 #define ODB_CNT_GENERAL 0       // jobs flagged ODB_JF_GENERAL
 #define ODB_CNT_FAST 1          // jobs the fast mix kernel takes
 #define ODB_CNT_RESAMPLE 2      // mixer jobs the staged resampling kernel takes
+#define ODB_CNT_RING_GENERAL 3   // buffered-source jobs the literal ring kernel takes (the read wraps around the ring)
 #define ODB_CNT_WORDS 4
 
 struct OdbQuat { float x, y, z, s; };
@@ -147,6 +149,8 @@ struct OdbCallback {
     int n_tiles;
     int n_sources;           // entries of the active list
     int force_general;       // kernel variant 1: every job takes the general (literal) kernel
+    int job_stride;          // OdbJob records per tile: seek sources first, then buffered sources
+    int job_offset;          // index of this set's first source inside a tile's records
 };
 
 static_assert(sizeof(OdbSource) % 16 == 0, "OdbSource is moved in 16-byte words");

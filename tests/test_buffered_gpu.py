@@ -30,19 +30,25 @@ def cursors_equal(pair):
         assert t == so.t, f"f64 cursor differs: {t!r} vs {so.t!r}"
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("kw", [{}, {"gain": 0.4}, {"fixed_gain_db": -3.0}, {"speed": 1.3}, {"speed": 0.7, "gain": 1.7}])
-def test_single_buffered_source_bit_exact(oracle, odb, ctx, kw):
+def test_single_buffered_source_bit_exact(oracle, odb, ctx, kw, variant):
     rng = np.random.default_rng(60)
     rate = 48000
-    pcm = synth_pcm(rng, 90000, rate)
+    pcm = synth_pcm(rng, 140000, rate)
     pair = ScenePair(oracle, odb, ctx)
+    pair.dev.set_kernel_variant(variant)  # 0: staged kernel reads the ring (literal ring kernel when a read wraps); 1: literal only
     pair.play_buffered(rate, pcm, 0.0, [30.0, 5.0, -12.0], [12.0, -3.0, 4.0], 0.2, max_distance=200.0, ring_rate=rate,
                        buffer_duration=0.1, **kw)
-    for n in (256, 1024, 480, 1024, 2048, 100):
+    kinds = set()
+    for n in (256, 1024, 480, 1024, 2048, 100) * 6:  # ~0.6 s: the 0.68 s ring wraps along the way
         ref, _, out = pair.step(rate, n)
         np.testing.assert_array_equal(out, ref)
         cursors_equal(pair)
+        cnt = pair.dev.last_job_counters()
+        kinds.add("staged" if cnt["staged"] else "literal")
     assert np.abs(out).max() > 0  # the sound has arrived (30 m ~ 87 ms)
+    assert kinds == ({"staged", "literal"} if variant == 0 else {"literal"})
 
 
 def test_many_buffered_and_seek_sources_together(oracle, odb, ctx):
@@ -75,6 +81,8 @@ def test_many_buffered_and_seek_sources_together(oracle, odb, ctx):
         cursors_equal(pair)
     assert pair.dev.len(True) == pair.ref.len(True) == 40
     assert pair.dev.len(False) == pair.ref.len(False) == 30
+    cnt = pair.dev.last_job_counters()  # buffered sources ride the staged kernel unless their reads wrap this callback
+    assert cnt["staged"] + cnt["general"] + cnt["ring_literal"] == 70 and cnt["staged"] >= 60
 
 
 def test_buffered_ring_wrap_and_finish(oracle, odb, ctx):

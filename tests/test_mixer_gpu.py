@@ -72,7 +72,7 @@ def test_c4_like_static_stereo_gain_tanh(oracle, odb, ctx, variant, epilogue):
         close(out, ref, ref64, epilogue)
         check_cursors(pair)
     cnt = pair.dev_mixer.last_job_counters()
-    assert cnt == ({"general": 0, "staged": n_src, "resampled": 0} if variant == 0 else {"general": n_src, "staged": 0, "resampled": 0})
+    assert cnt == ({"general": 0, "staged": n_src, "resampled": 0, "ring_literal": 0} if variant == 0 else {"general": n_src, "staged": 0, "resampled": 0, "ring_literal": 0})
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -90,7 +90,7 @@ def test_c5_like_speed_sweep(oracle, odb, ctx, variant):
         close(out, ref, ref64, None)
         check_cursors(pair)
     cnt = pair.dev_mixer.last_job_counters()  # 64 sources x 4 chunks: all on the staged resampling kernel
-    assert cnt == ({"general": 0, "staged": 0, "resampled": 256} if variant == 0 else {"general": 256, "staged": 0, "resampled": 0})
+    assert cnt == ({"general": 0, "staged": 0, "resampled": 256, "ring_literal": 0} if variant == 0 else {"general": 256, "staged": 0, "resampled": 0, "ring_literal": 0})
 
 
 @pytest.mark.parametrize("variant", [0, 1])
