@@ -300,21 +300,18 @@ def run_ours(args):
         # The reference's architecture has two threads: a control ("game") thread that calls set_motion and the
         # audio thread that calls run (README, examples/realtime.rs). Same here: the control thread queues the
         # updates of callback s while the audio thread is inside odb_scene_run of callback s (ctypes releases the GIL).
-        gate = threading.Barrier(2)
-        ctl_err = []
+        # The audio thread paces the control thread with a semaphore (one batch of updates per callback) and never
+        # waits for it.
+        go = threading.Semaphore(0)
 
         def control_thread():
-            try:
-                for s in range(W + K):
-                    gate.wait()
-                    ids, p, v = upd[s]
-                    ctl.set_motion_ids(ids, n_upd, p, v)
-            except Exception as e:  # pragma: no cover
-                ctl_err.append(e)
-                gate.abort()
+            for s in range(W + K):
+                go.acquire()
+                ids, p, v = upd[s]
+                ctl.set_motion_ids(ids, n_upd, p, v)
 
         def step_e2e(s):
-            gate.wait()
+            go.release()
             odb.run(scene, RATE, host_out)  # host tile: H2D of the queued updates and D2H of the result inside
             if world > 1:
                 t = torch.from_numpy(host_out).to(dev, non_blocking=False)
