@@ -12,4 +12,6 @@ from .api import (  # noqa: F401
     default_context, flatten_stereo, frame_stereo, init, run,
 )
 
+from . import wavio  # noqa: F401,E402
+
 Sample = "f32"  # lib.rs:85
