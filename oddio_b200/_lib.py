@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "liboddio_b200.so")
+SO_PATH = os.environ.get("ODB_SO") or os.path.join(HERE, "liboddio_b200.so")
 
 ODB_OK = 0
 ODB_E_INVALID = -1

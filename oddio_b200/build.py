@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "liboddio_b200.so")
+SO = os.environ.get("ODB_SO") or os.path.join(HERE, "liboddio_b200.so")  # ODB_SO / ODB_NVCC_EXTRA: developer experiments
 SOURCES = ["odb_host.cu", "odb_scene.cu", "odb_mixer.cu", "odb_spatial.cu", "odb_mix_fast.cu", "odb_mixer_kernels.cu", "odb_ring.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,12 +51,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return SO
     objs = []
-    bdir = os.path.join(HERE, "build")
+    bdir = os.path.join(HERE, "build", os.path.basename(SO).replace(".so", ""))
+    extra = os.environ.get("ODB_NVCC_EXTRA", "").split()
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

@@ -89,8 +89,9 @@ constexpr int FAST_OFFS_BYTES = FAST_BATCH * FAST_HCHUNKS * FAST_ROW_BYTES; // 8
 constexpr int FAST_WARP_BYTES = 2 * FAST_PCM_BYTES + FAST_OFFS_BYTES;       // 13440
 static_assert(FAST_WARP_BYTES >= 2 * ODB_TILE_FRAMES * 4 / FAST_SPLIT, "the warp region doubles as its partial half tile");
 static_assert(FAST_WARP_BYTES % 16 == 0, "TMA destinations are 16-byte aligned");
-constexpr int FAST_JOBS_OFF = FAST_WARPS * FAST_WARP_BYTES;                 // staged job records: 8 x 128 B per warp
-constexpr int FAST_BARS_OFF = FAST_JOBS_OFF + FAST_WARPS * FAST_BATCH * 128;
+constexpr int FAST_REC_BYTES = 128;                                         // staged job record stride
+constexpr int FAST_JOBS_OFF = FAST_WARPS * FAST_WARP_BYTES;                 // staged job records: 8 per warp
+constexpr int FAST_BARS_OFF = FAST_JOBS_OFF + FAST_WARPS * FAST_BATCH * FAST_REC_BYTES;
 constexpr int FAST_SMEM_BYTES = FAST_BARS_OFF + FAST_WARPS * 16;
 static_assert(FAST_SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
 
@@ -197,23 +198,33 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
     }
 }
 
+// Words of a staged job record after the warp's prologue: lane q rewrites source q's record (a private copy per
+// warp) with what this warp's half needs, so that the per-source set-up is four broadcast 16-byte loads.
+#define FJ_SRC 0     // words 0-1: global address of the first float of this half's PCM window
+#define FJ_BYTES 2   // bytes of the window
+#define FJ_CODE 10   // bit 2: full tile, bit 1: left ear on the ds ~= 1 path, bit 0: right ear
+#define FJ_K 12      // words 12-15: per chunk of this half (KL, KR): byte offset of PCM index `base` inside the window,
+                     // minus the magic bits for a doppler ear
+
+__device__ __forceinline__ uint2 lds_u64x(uint32_t addr) { return *reinterpret_cast<const uint2*>(__cvta_shared_to_generic(addr)); }
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) { return *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(addr)); }
+
 template <bool STRICT, bool FULL, bool UL, bool UR>
 __device__ __forceinline__ void consume_source(u64* __restrict__ acc, const int lane, const float lanef, const int half,
-                                               const uint32_t job_sa, const uint32_t pcm_b, const uint32_t rows_sa,
-                                               const int w_start, const int nfr, const u64 d1, const u64 d2, const u64 d3,
+                                               const uint32_t rec_sa, const uint32_t rec_x, const uint32_t pcm_b,
+                                               const uint32_t rows_sa, const uint4 K, const int nfr, const u64 d1, const u64 d2, const u64 d3,
                                                const u64 pgp, const u64 dgp, const u64 nz) {
+    const uint32_t lane4 = (uint32_t)(lane * 4);
 #pragma unroll
     for (int cc = 0; cc < FAST_HCHUNKS; cc++) {
         const int c = half * FAST_HCHUNKS + cc;  // chunk of the tile
         if (!FULL && c * ODB_SPATIAL_CHUNK >= nfr) break;
-        const int baseL = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_BASE + c) * 4));
-        const int baseR = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_BASE + ODB_TILE_CHUNKS + c) * 4));
-        const uint32_t KL = pcm_b + (uint32_t)((baseL - w_start) * 4) + (UL ? (uint32_t)(lane * 4) : 0u - (ODB_MAGIC_BITS << 2));
-        const uint32_t KR = pcm_b + (uint32_t)((baseR - w_start) * 4) + (UR ? (uint32_t)(lane * 4) : 0u - (ODB_MAGIC_BITS << 2));
+        const uint32_t KL = pcm_b + (cc ? K.z : K.x) + (UL ? lane4 : 0u);
+        const uint32_t KR = pcm_b + (cc ? K.w : K.y) + (UR ? lane4 : 0u);
         u64 fr_unit = 0ull;
         if (UL || UR)
-            fr_unit = pk2(__uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + c) * 4))),
-                          __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4))));
+            fr_unit = pk2(__uint_as_float(lds_u32(rec_sa + ((uint32_t)((ODB_JW_OFF0 + c) * 4) ^ rec_x))),
+                          __uint_as_float(lds_u32(rec_sa + ((uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4) ^ rec_x))));
         consume_chunk<STRICT, FULL, UL, UR>(acc, cc, c, lane, lanef + (float)(c * ODB_SPATIAL_CHUNK),
                                             rows_sa + (uint32_t)(cc * FAST_ROW_BYTES), KL, KR, d1, d2, d3, fr_unit, pgp, dgp,
                                             nfr, nz);
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
     const uint32_t smem_sa = smem_u32(smem_raw);
     const uint32_t pcm_sa = smem_sa + (uint32_t)(warp * FAST_WARP_BYTES);
     const uint32_t offs_sa = pcm_sa + 2 * FAST_PCM_BYTES;
-    const uint32_t jobs_sa = smem_sa + (uint32_t)(FAST_JOBS_OFF + warp * FAST_BATCH * 128);
+    const uint32_t jobs_sa = smem_sa + (uint32_t)(FAST_JOBS_OFF + warp * FAST_BATCH * FAST_REC_BYTES);
     const uint32_t bar_sa = smem_sa + (uint32_t)(FAST_BARS_OFF + warp * 16);
     if (lane == 0) {
         mbar_init(bar_sa, 1);
@@ -253,16 +264,20 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
     const OdbJob* tile_jobs = jobs + (size_t)tl * n_sources;
     const int n_batches = (n_sources + FAST_BATCH - 1) / FAST_BATCH;
     const int first_frame = half * (ODB_TILE_FRAMES / FAST_SPLIT);
+    const int c0 = half * FAST_HCHUNKS;
+
+    // Staged job records: record q's word w lives at position w ^ 4q of its 128-byte line, so that the eight lanes
+    // of the prologue (one per source, same field) and the chain lanes hit different banks; aligned 8- and 16-byte
+    // groups stay aligned groups. rec(q, w) = shared address of word w of record q.
+    auto rec = [&](int q, int w) { return jobs_sa + (uint32_t)(q * FAST_REC_BYTES) + (uint32_t)((w * 4) ^ (q * 16)); };
 
     // lane 0: start the bulk copy of source q's PCM window of this half into PCM buffer `b`
     auto start_copy = [&](int q, uint32_t b) {
         if (lane == 0) {
-            const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
-            const u64 p = ((u64)lds_u32(job_sa + ODB_JW_PCM_HI * 4) << 32) | (u64)lds_u32(job_sa + ODB_JW_PCM_LO * 4);
-            const int w_start = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_WINDOW + 2 * half) * 4));
-            const uint32_t bytes = lds_u32(job_sa + (uint32_t)((ODB_JW_WINDOW + 2 * half + 1) * 4)) * 4u;
-            mbar_expect_tx(bar_sa + b * 8, bytes);
-            bulk_g2s(pcm_sa + b * FAST_PCM_BYTES, reinterpret_cast<const float*>(p) + w_start, bytes, bar_sa + b * 8);
+            const uint4 d = lds_u128(rec(q, FJ_SRC));
+            const u64 p = ((u64)d.y << 32) | (u64)d.x;
+            mbar_expect_tx(bar_sa + b * 8, d.z);
+            bulk_g2s(pcm_sa + b * FAST_PCM_BYTES, reinterpret_cast<const void*>(p), d.z, bar_sa + b * 8);
         }
     };
 
@@ -273,27 +288,44 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
         for (int q = 0; q < FAST_BATCH; q++) {
             uint32_t w = lane == ODB_JW_FLAGS ? ODB_JF_SKIP : 0u;
             if (s0 + q < n_sources) w = __ldg(reinterpret_cast<const uint32_t*>(tile_jobs + s0 + q) + lane);
-            sts_u32(jobs_sa + (uint32_t)(q * 128 + lane * 4), w);
+            sts_u32(rec(q, lane), w);
         }
         __syncwarp();
-        uint32_t act = 0;  // sources of the batch this warp mixes: staged, and with frames in this half
-#pragma unroll
-        for (int q = 0; q < FAST_BATCH; q++) {
-            const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
-            if (!(lds_u32(job_sa + ODB_JW_FLAGS * 4) & (ODB_JF_SKIP | ODB_JF_GENERAL)) &&
-                (int)lds_u32(job_sa + ODB_JW_N_FRAMES * 4) > first_frame)
-                act |= 1u << q;
+        // lane q < 8 derives what this half needs of source q and rewrites its private record (FJ_* words)
+        bool mine = false;
+        if (lane < FAST_BATCH) {
+            const uint4 h = lds_u128(rec(lane, 0));                                     // pcm lo/hi, len, flags
+            const int nfr = (int)lds_u32(rec(lane, ODB_JW_N_FRAMES));
+            mine = !(h.w & (ODB_JF_SKIP | ODB_JF_GENERAL)) && nfr > first_frame;       // staged, and with frames in this half
+            if (mine) {
+                const uint2 win = lds_u64x(rec(lane, ODB_JW_WINDOW + 2 * half));        // first PCM index, floats
+                const int w_start = (int)win.x;
+                const u64 p = (((u64)h.y << 32) | (u64)h.x) + (u64)((long long)w_start * 4);
+                const uint32_t mL = (h.w & ODB_JF_FAST_L) ? 0u : (ODB_MAGIC_BITS << 2);
+                const uint32_t mR = (h.w & ODB_JF_FAST_R) ? 0u : (ODB_MAGIC_BITS << 2);
+                const uint2 bL = lds_u64x(rec(lane, ODB_JW_BASE + c0));                   // `base` of this half's two chunks
+                const uint2 bR = lds_u64x(rec(lane, ODB_JW_BASE + ODB_TILE_CHUNKS + c0));
+                const uint32_t code = (nfr == ODB_TILE_FRAMES ? 4u : 0u) | ((h.w & ODB_JF_FAST_L) ? 2u : 0u) | ((h.w & ODB_JF_FAST_R) ? 1u : 0u);
+                sts_u32(rec(lane, FJ_SRC), (uint32_t)p);
+                sts_u32(rec(lane, FJ_SRC + 1), (uint32_t)(p >> 32));
+                sts_u32(rec(lane, FJ_BYTES), win.y * 4u);
+                sts_u32(rec(lane, FJ_CODE), code);
+                sts_u32(rec(lane, FJ_K + 0), (uint32_t)(((int)bL.x - w_start) * 4) - mL);
+                sts_u32(rec(lane, FJ_K + 1), (uint32_t)(((int)bR.x - w_start) * 4) - mR);
+                sts_u32(rec(lane, FJ_K + 2), (uint32_t)(((int)bL.y - w_start) * 4) - mL);
+                sts_u32(rec(lane, FJ_K + 3), (uint32_t)(((int)bR.y - w_start) * 4) - mR);
+            }
         }
+        __syncwarp();
+        uint32_t act = __ballot_sync(0xffffffffu, mine);  // sources of the batch this warp mixes
         if (act) {
             start_copy(__ffs(act) - 1, buf);
             {   // 2. literal cursor chains: lane = (source q, ear e, chunk cc of this half)
                 const int q = lane >> 2, e = (lane >> 1) & 1, cc = lane & 1;
-                const int c = half * FAST_HCHUNKS + cc;
-                const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
-                const uint32_t jf = lds_u32(job_sa + ODB_JW_FLAGS * 4);
+                const uint32_t jf = lds_u32(rec(q, ODB_JW_FLAGS));
                 if (((act >> q) & 1u) && !(jf & (e ? ODB_JF_FAST_R : ODB_JF_FAST_L))) {
-                    float o = __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c) * 4)));
-                    const float ds = __uint_as_float(lds_u32(job_sa + (uint32_t)((ODB_JW_DS + e) * 4)));
+                    float o = __uint_as_float(lds_u32(rec(q, ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c0 + cc)));
+                    const float ds = __uint_as_float(lds_u32(rec(q, ODB_JW_DS + e)));
                     const uint32_t dst = offs_sa + (uint32_t)((q * FAST_HCHUNKS + cc) * FAST_ROW_BYTES + e * 4);
 #pragma unroll 8
                     for (int m = 0; m < FAST_POINTS; m++) {
@@ -304,24 +336,24 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
             }
             __syncwarp();
             // 3. consume the batch source by source
-            for (int q = 0; q < FAST_BATCH; q++) {
-                if (!((act >> q) & 1u)) continue;
-                const uint32_t rest = act >> (q + 1);
-                if (rest) start_copy(q + __ffs(rest), buf ^ 1u);  // next window -> the other buffer
-                const uint32_t job_sa = jobs_sa + (uint32_t)(q * 128);
-                const uint32_t jf = lds_u32(job_sa + ODB_JW_FLAGS * 4);
-                const int nfr = (int)lds_u32(job_sa + ODB_JW_N_FRAMES * 4);
-                const int w_start = (int)lds_u32(job_sa + (uint32_t)((ODB_JW_WINDOW + 2 * half) * 4));
-                const u64 dsp = lds_u64(job_sa + ODB_JW_DS * 4), pgp = lds_u64(job_sa + ODB_JW_PG * 4),
-                          dgp = lds_u64(job_sa + ODB_JW_DG * 4);
+            while (act) {
+                const int q = __ffs(act) - 1;
+                act &= act - 1u;
+                if (act) start_copy(__ffs(act) - 1, buf ^ 1u);  // next window -> the other buffer
+                const uint4 A = lds_u128(rec(q, ODB_JW_DS));   // ds (L, R), prev gain (L, R)
+                const uint4 B = lds_u128(rec(q, ODB_JW_DG));   // d_gain (L, R), code, n_frames
+                const uint4 K = lds_u128(rec(q, FJ_K));
+                const u64 dsp = ((u64)A.y << 32) | A.x, pgp = ((u64)A.w << 32) | A.z, dgp = ((u64)B.y << 32) | B.x;
+                const int nfr = (int)B.w;
+                // lane's frames are k = lane + 32 j: k & 3 = r literal steps after the checkpoint, the rest add +0.0 (exact)
                 const u64 d1 = r >= 1 ? dsp : 0ull, d2 = r >= 2 ? dsp : 0ull, d3 = r >= 3 ? dsp : 0ull;
                 const uint32_t pcm_b = pcm_sa + buf * FAST_PCM_BYTES;
                 const uint32_t rows_sa = offs_sa + (uint32_t)(q * FAST_HCHUNKS * FAST_ROW_BYTES + (lane >> 2) * 8);
+                const uint32_t off0_sa = jobs_sa + (uint32_t)(q * FAST_REC_BYTES), off0_x = (uint32_t)(q * 16);
                 mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
                 parity ^= 1u << buf;
-                const uint32_t code = (nfr == ODB_TILE_FRAMES ? 4u : 0u) | ((jf & ODB_JF_FAST_L) ? 2u : 0u) | ((jf & ODB_JF_FAST_R) ? 1u : 0u);
-#define ODB_CONSUME(F, L, R) consume_source<STRICT, F, L, R>(acc, lane, lanef, half, job_sa, pcm_b, rows_sa, w_start, nfr, d1, d2, d3, pgp, dgp, nz)
-                switch (code) {
+#define ODB_CONSUME(F, L, R) consume_source<STRICT, F, L, R>(acc, lane, lanef, half, off0_sa, off0_x, pcm_b, rows_sa, K, nfr, d1, d2, d3, pgp, dgp, nz)
+                switch (B.z) {
                     case 4: ODB_CONSUME(true, false, false); break;
                     case 7: ODB_CONSUME(true, true, true); break;
                     case 0: ODB_CONSUME(false, false, false); break;
