@@ -199,8 +199,15 @@ void SourceSet::queue_motion(uint32_t slot, const float* pos, const float* vel, 
     for (int k = 0; k < 3; k++) { m.pos[k] = pos[k]; m.vel[k] = vel[k]; }
     m.discontinuity = disc ? 1u : 0u;
     SlotHost& sh = slots[slot];
-    if (sh.motion_idx >= 0) motions[sh.motion_idx] = m;  // latest value wins (swap.rs:36-47)
-    else { sh.motion_idx = (int)motions.size(); motions.push_back(m); }
+    PinBuf<OdbMotionMsg>& hb = h_mot[mot_buf];
+    if (sh.motion_gen == mot_gen) {  // latest value wins (swap.rs:36-47)
+        if (sh.motion_idx >= 0) hb.p[sh.motion_idx] = m;
+        else motions[(size_t)(-sh.motion_idx - 2)] = m;  // spilled message: index encoded as -(i + 2)
+        return;
+    }
+    sh.motion_gen = mot_gen;
+    if (mot_n < hb.cap) { sh.motion_idx = (int)mot_n; hb.p[mot_n++] = m; }
+    else { sh.motion_idx = -(int)motions.size() - 2; motions.push_back(m); }
 }
 void SourceSet::queue_param(uint32_t slot, uint32_t what, float value) {
     OdbParamMsg m = {slot, what, value, 0u};
@@ -235,16 +242,32 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
         ins_src.clear();
         ins_slot.clear();
     }
-    size_t nm = motions.size();
+    size_t nm = mot_n + motions.size();
     if (nm) {
-        ODB_TRY(h_motions.ensure(nm));
         ODB_TRY(d_motions.ensure(nm, st, false));
-        memcpy(h_motions.p, motions.data(), nm * sizeof(OdbMotionMsg));
-        ODB_CUDA(cudaMemcpyAsync(d_motions.p, h_motions.p, nm * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+        const int b = mot_buf;
+        if (mot_n) {  // the pinned buffer the control side filled goes to the device as it lies
+            if (!ev_mot[b]) ODB_CUDA(cudaEventCreateWithFlags(&ev_mot[b], cudaEventDisableTiming));
+            ODB_CUDA(cudaMemcpyAsync(d_motions.p, h_mot[b].p, mot_n * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+            ODB_CUDA(cudaEventRecord(ev_mot[b], st));
+            ev_mot_pending[b] = true;
+        }
+        if (!motions.empty()) {  // what did not fit (rare: sources played since the buffers were sized)
+            ODB_TRY(h_motions.ensure(motions.size()));
+            memcpy(h_motions.p, motions.data(), motions.size() * sizeof(OdbMotionMsg));
+            ODB_CUDA(cudaMemcpyAsync(d_motions.p + mot_n, h_motions.p, motions.size() * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+            motions.clear();
+        }
         odb_launch_scatter_motion(d_src.p, d_motions.p, (int)nm, st);
         (*launches)++;
-        for (auto& m : motions) slots[m.slot].motion_idx = -1;
-        motions.clear();
+        mot_n = 0;
+        mot_gen++;  // forgets every slot's queued-message index at once
+        if (b == mot_buf && ev_mot_pending[b]) mot_buf = b ^ 1;
+    }
+    {   // the buffer the control side fills next: its last copy must have left, and it holds one message per slot
+        const int b = mot_buf;
+        if (ev_mot_pending[b]) { ODB_CUDA(cudaEventSynchronize(ev_mot[b])); ev_mot_pending[b] = false; }
+        if (mot_n == 0 && h_mot[b].cap < slots.size()) ODB_TRY(h_mot[b].ensure(slots.size() + slots.size() / 2 + 256));
     }
     size_t np = params.size();
     if (np) {
@@ -271,7 +294,7 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
     }
     // removal report ring: every live source reports at most once, so a ring of >= order.size() never overflows
     if (removed_cap < order.size() || !d_removed.p) {
-        if (d_removed.p) ODB_TRY(fold_removed(ctx, st, true));
+        if (d_removed.p) ODB_TRY(fold_removed(ctx, st, true, nullptr));
         uint32_t ncap = 1024;
         while (ncap < 2 * order.size()) ncap *= 2;
         d_removed.release();
@@ -296,7 +319,7 @@ int SourceSet::post_callback(odb_ctx* ctx, cudaStream_t st) {
     return ODB_OK;
 }
 
-int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait) {
+int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait, std::mutex* mu) {
     if (!d_removed.p) return ODB_OK;
     if (!count_in_flight) {
         if (!wait) return ODB_OK;
@@ -313,6 +336,9 @@ int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait) {
     uint32_t n_new = count - removed_consumed;
     if (n_new == 0) return ODB_OK;
     if (n_new > removed_cap) return odb_fail(ODB_E_INVALID, "internal: removal ring overflow (%u reports)", n_new);
+    // from here on the membership (order, slots) changes: that is shared with the control side
+    std::unique_lock<std::mutex> lk;
+    if (mu) lk = std::unique_lock<std::mutex>(*mu);
     // fetch the report entries (only happens on callbacks where sources actually finished)
     const uint32_t mask = removed_cap - 1, first = removed_consumed & mask;
     const uint32_t span1 = n_new < removed_cap - first ? n_new : removed_cap - first;
@@ -341,6 +367,11 @@ int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait) {
         sh.stopped = true;
         sh.in_use = false;
         sh.gen++;  // older handles now read as "finished" (see lookup)
+        if (sh.motion_gen == mot_gen) {  // a queued set_motion for a source that is gone must not reach the slot's next tenant
+            if (sh.motion_idx >= 0) h_mot[mot_buf].p[sh.motion_idx].slot = 0xFFFFFFFFu;
+            else if (sh.motion_idx <= -2) motions[(size_t)(-sh.motion_idx - 2)].slot = 0xFFFFFFFFu;
+            sh.motion_gen = 0;
+        }
         sh.motion_idx = sh.speed_idx = sh.gain_idx = -1;
         if (sh.frames) ctx->frames_unref(sh.frames);
         sh.frames = 0;
@@ -368,6 +399,13 @@ void SourceSet::release_all(odb_ctx* ctx) {
     d_motions.release(); d_params.release(); d_removed.release();
     h_stage_src.release(); h_stage_slot.release(); h_motions.release(); h_params.release();
     h_order.release(); h_removed.release(); h_removed_count.release();
+    for (int b = 0; b < 2; b++) {
+        h_mot[b].release();
+        if (ev_mot[b]) cudaEventDestroy(ev_mot[b]);
+        ev_mot[b] = nullptr;
+        ev_mot_pending[b] = false;
+    }
+    mot_n = 0;
     if (ev_removed) cudaEventDestroy(ev_removed);
     ev_removed = nullptr;
     removed_cap = 0;

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -89,6 +90,27 @@ struct ArenaBlock {
     int live = 0;
 };
 
+// The audio thread announces itself before it takes a control-plane mutex; batched control calls check the flag
+// between chunks and stand back, so the callback never queues behind a long batch (std::mutex is not fair).
+struct AudioLock {
+    std::mutex& mu;
+    AudioLock(std::mutex& m, std::atomic<int>& wants) : mu(m) {
+        wants.fetch_add(1, std::memory_order_acq_rel);
+        mu.lock();
+        wants.fetch_sub(1, std::memory_order_acq_rel);
+    }
+    ~AudioLock() { mu.unlock(); }
+    AudioLock(const AudioLock&) = delete;
+    AudioLock& operator=(const AudioLock&) = delete;
+};
+static inline void odb_yield_to_audio(const std::atomic<int>& wants) {
+    while (wants.load(std::memory_order_acquire) > 0) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 struct odb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -123,6 +145,7 @@ struct SlotHost {
     // latest-wins de-duplication of queued control messages (swap.rs semantics): index into the
     // pending vectors, -1 if nothing is queued for this slot since the last apply()
     int motion_idx = -1, speed_idx = -1, gain_idx = -1;
+    uint32_t motion_gen = 0;  // motion_idx is valid only while this equals SourceSet::mot_gen
 };
 
 // A set of playing sources living in HBM plus the control-plane queues feeding it; the common
@@ -135,6 +158,15 @@ struct SourceSet {
     // queued by the control side, applied at the next sample()
     std::vector<OdbSource> ins_src;
     std::vector<uint32_t> ins_slot;
+    // set_motion messages are written by the control side straight into one of two pinned buffers (at most one
+    // message per slot: latest value wins); apply() sends the filled one to the device as it lies and hands the
+    // control side the other. `motions` only takes what does not fit (sources played since the last apply()).
+    PinBuf<OdbMotionMsg> h_mot[2];
+    cudaEvent_t ev_mot[2] = {nullptr, nullptr};  // behind the H2D copy out of h_mot[b]
+    bool ev_mot_pending[2] = {false, false};
+    int mot_buf = 0;
+    size_t mot_n = 0;
+    uint32_t mot_gen = 1;
     std::vector<OdbMotionMsg> motions;
     std::vector<OdbParamMsg> params;
     // device
@@ -172,6 +204,8 @@ struct SourceSet {
     int post_callback(odb_ctx* ctx, cudaStream_t st);
     // audio side: fold the removals the kernels reported into `order` (set.rs:183-188 swap_remove). With
     // wait = false only reports whose read-back has already completed are folded (no host-device sync).
-    int fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait);
+    // `mu` (may be NULL when the caller already holds it) is the owner's control-plane mutex: it is taken only
+    // when there is something to fold, so a callback without removals never contends with the control thread.
+    int fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait, std::mutex* mu);
     void release_all(odb_ctx* ctx);
 };

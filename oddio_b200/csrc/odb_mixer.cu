@@ -10,6 +10,7 @@ struct odb_mixer {
     odb_ctx* ctx = nullptr;
     int channels = 2;
     std::mutex mu;
+    std::atomic<int> audio_wants{0};  // the audio thread is waiting for `mu` (see AudioLock)
     SourceSet set;
     int epilogue = ODB_EPILOGUE_NONE;
     int variant = 0;
@@ -105,8 +106,8 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
     ODB_CUDA(cudaSetDevice(ctx->device));
     uint32_t launches = 0;
     {
-        std::lock_guard<std::mutex> lk(mixer->mu);
-        ODB_TRY(mixer->set.fold_removed(ctx, st, false));
+        AudioLock lk(mixer->mu, mixer->audio_wants);
+        ODB_TRY(mixer->set.fold_removed(ctx, st, false, nullptr));
         ODB_TRY(mixer->set.apply(ctx, st, &launches));  // set.update(), mixer.rs:94
     }
     OdbCallback cb;
@@ -158,10 +159,7 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
                           mixer->d_counters.p, n_unit > 0 ? 1 : 0, n_res > 0 ? ODB_CNT_RESAMPLE : -1, nullptr, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
         launches++;
     }
-    {
-        std::lock_guard<std::mutex> lk(mixer->mu);
-        ODB_TRY(mixer->set.post_callback(ctx, st));
-    }
+    ODB_TRY(mixer->set.post_callback(ctx, st));  // audio-side state only: no control-plane lock
     mixer->last_launches = launches;
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
@@ -173,14 +171,12 @@ extern "C" int odb_mixer_sample(odb_mixer* mixer, float interval, float* out, ui
     odb_ctx* ctx = mixer->ctx;
     ODB_CUDA(cudaSetDevice(ctx->device));
     size_t n = (size_t)n_frames * mixer->channels;
-    ODB_TRY(mixer->d_out.ensure(n ? n : 2, ctx->stream, false));
     ODB_TRY(mixer->h_out.ensure(n ? n : 2));
-    ODB_TRY(mixer_sample_impl(mixer, interval, mixer->d_out.p, n_frames));
-    if (n) ODB_CUDA(cudaMemcpyAsync(mixer->h_out.p, mixer->d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    // the reduce kernel stores the tile straight into the pinned host buffer (unified addressing)
+    ODB_TRY(mixer_sample_impl(mixer, interval, mixer->h_out.p, n_frames));
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n) memcpy(out, mixer->h_out.p, n * sizeof(float));
-    std::lock_guard<std::mutex> lk(mixer->mu);
-    return mixer->set.fold_removed(ctx, ctx->stream, true);
+    return mixer->set.fold_removed(ctx, ctx->stream, true, &mixer->mu);
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_mixer_run(odb_mixer* mixer, uint32_t sample_rate, float* out, uint32_t n_frames) {

@@ -1,6 +1,9 @@
 // odb_scene_*: SpatialSceneControl + SpatialScene over the device-resident source sets.
 // Reference: src/spatial.rs (cited per function), src/lib.rs:90-93.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "odb_host.h"
 
@@ -12,6 +15,7 @@ struct odb_scene {
     uint32_t kind = ODB_KIND_SCENE;
     odb_ctx* ctx = nullptr;
     std::mutex mu;  // guards the control-plane queues of both sets and the rotation
+    std::atomic<int> audio_wants{0};  // the audio thread is waiting for `mu` (see AudioLock)
     SourceSet seek, buffered;
     // swap::Receiver<Quaternion> (spatial.rs:161): received + pending, stored already inverted (:346)
     OdbQuat rot_received = {0.0f, 0.0f, 0.0f, 1.0f};
@@ -42,7 +46,15 @@ struct odb_scene {
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     PinBuf<float> h_out;
+    // ODB_TRACE=1: host-side time of the phases of odb_scene_sample, printed when the scene is destroyed
+    double tr_enqueue = 0.0, tr_wait = 0.0, tr_tail = 0.0, tr_lock = 0.0, tr_apply = 0.0, tr_enqueue_max = 0.0;
+    uint64_t tr_calls = 0;
+    double tr_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+static inline double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool g_trace = getenv("ODB_TRACE") != nullptr;
 
 static int scene_check(odb_scene* s) {
     if (!s || s->kind != ODB_KIND_SCENE) return odb_fail(ODB_E_INVALID, "not a scene handle");
@@ -68,6 +80,15 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     cudaSetDevice(scene->ctx->device);
     cudaStreamSynchronize(scene->wst);
     cudaStreamSynchronize(scene->ctx->stream);
+    if (g_trace && scene->tr_calls)
+        fprintf(stderr, "[odb trace] odb_scene_sample x%llu: enqueue %.1f us (max %.1f; of which lock wait %.1f, control-plane apply %.1f), wait for the tile %.1f us, tail %.1f us\n",
+                (unsigned long long)scene->tr_calls, scene->tr_enqueue / scene->tr_calls, scene->tr_enqueue_max,
+                scene->tr_lock / scene->tr_calls, scene->tr_apply / scene->tr_calls, scene->tr_wait / scene->tr_calls,
+                scene->tr_tail / scene->tr_calls);
+    if (g_trace && scene->tr_calls)
+        fprintf(stderr, "[odb trace]   enqueue segments: walk %.1f, staged mix %.1f, rest of the kernels %.1f, removal read-back %.1f us\n",
+                scene->tr_seg[0] / scene->tr_calls, scene->tr_seg[1] / scene->tr_calls, scene->tr_seg[2] / scene->tr_calls,
+                scene->tr_seg[3] / scene->tr_calls);
     scene->seek.release_all(scene->ctx);
     scene->buffered.release_all(scene->ctx);
     for (int p = 0; p < 2; p++) {
@@ -241,14 +262,23 @@ extern "C" int odb_spatial_set_motion_many(odb_scene* scene, uint32_t n, const o
                                            const float* velocities, const uint8_t* discontinuity) {
     ODB_TRY(scene_check(scene));
     if (n && (!srcs || !positions || !velocities)) return odb_fail(ODB_E_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(scene->mu);
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t tag, slot; bool stale;
-        SourceSet* set = set_of(scene, srcs[i], &tag);
-        if (!set) return odb_fail(ODB_E_INVALID, "srcs[%u] is not a spatial source handle", i);
-        ODB_TRY(set->lookup(srcs[i], tag, &slot, &stale));
-        if (stale) continue;
-        set->queue_motion(slot, positions + 3 * (size_t)i, velocities + 3 * (size_t)i, discontinuity ? discontinuity[i] : 0);
+    // Every update is an independent latest-value-wins write (swap.rs:36-47), so the batch need not be atomic: the
+    // lock is taken per chunk, and a callback that starts meanwhile picks up what has been queued so far instead of
+    // waiting for the whole batch (the rest takes effect one callback later, as it would with the reference's
+    // per-source swap cells).
+    const uint32_t CHUNK = 256;
+    for (uint32_t i0 = 0; i0 < n; i0 += CHUNK) {
+        odb_yield_to_audio(scene->audio_wants);
+        std::lock_guard<std::mutex> lk(scene->mu);
+        const uint32_t i1 = i0 + CHUNK < n ? i0 + CHUNK : n;
+        for (uint32_t i = i0; i < i1; i++) {
+            uint32_t tag, slot; bool stale;
+            SourceSet* set = set_of(scene, srcs[i], &tag);
+            if (!set) return odb_fail(ODB_E_INVALID, "srcs[%u] is not a spatial source handle", i);
+            ODB_TRY(set->lookup(srcs[i], tag, &slot, &stale));
+            if (stale) continue;
+            set->queue_motion(slot, positions + 3 * (size_t)i, velocities + 3 * (size_t)i, discontinuity ? discontinuity[i] : 0);
+        }
     }
     return ODB_OK;
 }
@@ -272,7 +302,7 @@ extern "C" int odb_scene_len(odb_scene* scene, int buffered, uint64_t* out) {
     return ODB_OK;
 }
 
-// <SpatialScene as Signal>::sample, spatial.rs:376-471. Leaves the mixed tile in scene->d_out (or
+// <SpatialScene as Signal>::sample, spatial.rs:376-471. Leaves the mixed tile in `dev_out` (device memory, or
 // `dev_out` when given) on the context's stream.
 // Grows a device buffer that kernels on either stream may still be using: both streams are drained first.
 template <class T>
@@ -297,16 +327,21 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     if (scene->pipelined) ODB_CUDA(cudaStreamWaitEvent(wst, scene->ev_mix[p], 0));
     OdbCallback cb;
     {
-        std::lock_guard<std::mutex> lk(scene->mu);
+        const double tl0 = g_trace ? now_us() : 0.0;
+        AudioLock lk(scene->mu, scene->audio_wants);
+        const double tl1 = g_trace ? now_us() : 0.0;
         // removals reported by earlier callbacks whose read-back has landed (never waits for the device)
-        ODB_TRY(scene->seek.fold_removed(ctx, wst, false));
-        ODB_TRY(scene->buffered.fold_removed(ctx, wst, false));
+        ODB_TRY(scene->seek.fold_removed(ctx, wst, false, nullptr));
+        ODB_TRY(scene->buffered.fold_removed(ctx, wst, false, nullptr));
         ODB_TRY(scene->buffered.apply(ctx, wst, &launches));                // set.update(), spatial.rs:379
         ODB_TRY(scene->seek.apply(ctx, wst, &launches));                    // set.update(), spatial.rs:437
+        if (g_trace && scene->callback_no > 4) { scene->tr_lock += tl1 - tl0; scene->tr_apply += now_us() - tl1; }
         cb.prev_rot = scene->rot_received;                                 // spatial.rs:382-386
         if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
         cb.rot = scene->rot_received;
     }
+    double ts = g_trace ? now_us() : 0.0;
+    auto seg = [&](int i) { if (g_trace && scene->callback_no > 4) { const double t = now_us(); scene->tr_seg[i] += t - ts; ts = t; } };
     cb.interval = interval;
     cb.n_frames = (int)n_frames;
     cb.elapsed = interval * (float)n_frames;                               // spatial.rs:394
@@ -352,6 +387,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
                              (int)scene->seek.removed_cap, counters, cb, wst);
         launches++;
     }
+    seg(0);
     if (scene->pipelined) {
         ODB_CUDA(cudaEventRecord(scene->ev_walk[p], wst));
         // ---- stage 2 on the context's stream: O(sources x frames) -----------------------------------------------------
@@ -375,6 +411,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
                 if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "mix_fast launch failed: %s", cudaGetErrorString(e));
                 if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev1, st));
                 launches++;
+                seg(1);
             }
             if (ns > 0) {
                 // literal kernel for the flagged rest of the seek set (exits at once when the walk kernel flagged nothing)
@@ -402,12 +439,13 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
                           (int)n_frames, nt, 2, scene->epilogue, st);
         launches++;
     }
+    seg(2);
     if (scene->pipelined) ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
-    {   // start the read-back of what walk_set removed; folded in by a later call without waiting
-        std::lock_guard<std::mutex> lk(scene->mu);
-        ODB_TRY(scene->seek.post_callback(ctx, wst));
-        ODB_TRY(scene->buffered.post_callback(ctx, wst));
-    }
+    // start the read-back of what walk_set removed; folded in by a later call without waiting (touches only
+    // audio-side state: no control-plane lock)
+    ODB_TRY(scene->seek.post_callback(ctx, wst));
+    ODB_TRY(scene->buffered.post_callback(ctx, wst));
+    seg(3);
     scene->last_launches = launches;
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
@@ -419,16 +457,24 @@ extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, ui
     odb_ctx* ctx = scene->ctx;
     ODB_CUDA(cudaSetDevice(ctx->device));
     size_t n = (size_t)n_frames * 2;
-    ODB_TRY(scene->d_out.ensure(n ? n : 2, ctx->stream, false));
     ODB_TRY(scene->h_out.ensure(n ? n : 2));
-    ODB_TRY(scene_sample_impl(scene, interval, scene->d_out.p, n_frames));
-    if (n) ODB_CUDA(cudaMemcpyAsync(scene->h_out.p, scene->d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    const double t0 = g_trace ? now_us() : 0.0;
+    // The reduce kernel stores the 8 KiB tile straight into the pinned host buffer (unified addressing: no
+    // device-side staging tile and no copy-engine operation between the last kernel and the host).
+    ODB_TRY(scene_sample_impl(scene, interval, scene->h_out.p, n_frames));
+    const double t1 = g_trace ? now_us() : 0.0;
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double t2 = g_trace ? now_us() : 0.0;
     if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
-    std::lock_guard<std::mutex> lk(scene->mu);
     cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
-    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true));
-    return scene->seek.fold_removed(ctx, ws, true);  // like the reference, removals are visible when sample returns
+    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
+    int rc = scene->seek.fold_removed(ctx, ws, true, &scene->mu);  // like the reference, removals are visible when sample returns
+    if (g_trace && scene->callback_no > 4) {
+        scene->tr_enqueue += t1 - t0; if (t1 - t0 > scene->tr_enqueue_max) scene->tr_enqueue_max = t1 - t0;
+        scene->tr_wait += t2 - t1; scene->tr_tail += now_us() - t2;
+        scene->tr_calls++;
+    }
+    return rc;
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {

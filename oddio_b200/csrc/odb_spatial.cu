@@ -26,6 +26,7 @@ __global__ void k_scatter_motion(OdbSource* __restrict__ src, const OdbMotionMsg
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     OdbMotionMsg m = msgs[i];
+    if (m.slot == 0xFFFFFFFFu) return;  // withdrawn: its source was removed after the message was queued
     OdbSource* s = src + m.slot;
     s->ppos[0] = m.pos[0]; s->ppos[1] = m.pos[1]; s->ppos[2] = m.pos[2];
     s->pvel[0] = m.vel[0]; s->pvel[1] = m.vel[1]; s->pvel[2] = m.vel[2];
