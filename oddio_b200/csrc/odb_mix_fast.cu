@@ -272,13 +272,16 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
     auto rec = [&](int q, int w) { return jobs_sa + (uint32_t)(q * FAST_REC_BYTES) + (uint32_t)((w * 4) ^ (q * 16)); };
 
     // lane 0: start the bulk copy of source q's PCM window of this half into PCM buffer `b`
+    // (every lane loads the same descriptor; one elected lane arms the barrier and issues the copy)
     auto start_copy = [&](int q, uint32_t b) {
-        if (lane == 0) {
-            const uint4 d = lds_u128(rec(q, FJ_SRC));
-            const u64 p = ((u64)d.y << 32) | (u64)d.x;
-            mbar_expect_tx(bar_sa + b * 8, d.z);
-            bulk_g2s(pcm_sa + b * FAST_PCM_BYTES, reinterpret_cast<const void*>(p), d.z, bar_sa + b * 8);
-        }
+        const uint4 d = lds_u128(rec(q, FJ_SRC));
+        const u64 p = ((u64)d.y << 32) | (u64)d.x;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t"
+            "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+            "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}" ::"r"(bar_sa + b * 8),
+            "r"(d.z), "r"(pcm_sa + b * FAST_PCM_BYTES), "l"(p)
+            : "memory");
     };
 
     for (int bi = gp; bi < n_batches; bi += GP) {
@@ -353,8 +356,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_mix_fast(const OdbJob* _
                 mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
                 parity ^= 1u << buf;
 #define ODB_CONSUME(F, L, R) consume_source<STRICT, F, L, R>(acc, lane, lanef, half, off0_sa, off0_x, pcm_b, rows_sa, K, nfr, d1, d2, d3, pgp, dgp, nz)
-                switch (B.z) {
-                    case 4: ODB_CONSUME(true, false, false); break;
+                if (B.z == 4u) ODB_CONSUME(true, false, false);  // the common case: full tile, both ears on the doppler path
+                else switch (B.z) {
                     case 7: ODB_CONSUME(true, true, true); break;
                     case 0: ODB_CONSUME(false, false, false); break;
                     case 3: ODB_CONSUME(false, true, true); break;
