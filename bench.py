@@ -202,9 +202,25 @@ def run_ours(args):
     interval = float(np.float32(1.0) / np.float32(RATE))  # oddio::run, lib.rs:91
     # Offline rendering batches R consecutive callbacks per exchange: the sum over ranks is linear, so one
     # all-reduce of R tiles equals R all-reduces of one tile. R = 1 is the live-playback shape.
-    R = max(1, args.reduce_every) if world > 1 else 1
+    # --exchange peer (default): the library's own one-kernel push/sum over NVLink peer memory, every callback
+    # (R = 1, the live-playback shape); --exchange nccl: torch.distributed all-reduce of R batched tiles.
+    peer = world > 1 and args.exchange == "peer"
+    R = 1 if (world == 1 or peer) else max(1, args.reduce_every)
     groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(2)]
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    exch = None
+    if peer:
+        from oddio_b200.sharding import PeerExchange
+
+        exch = PeerExchange.from_torch(ctx, R * M * 2)
+
+    def exchange(g):
+        """Sum of group g over the ranks, on the `comm` stream."""
+        if peer:
+            exch.allreduce(groups[g].data_ptr(), R * M * 2, 0, comm.cuda_stream)
+        else:
+            with torch.cuda.stream(comm):
+                dist.all_reduce(groups[g])
     mixed = [torch.cuda.Event() for _ in range(2)]
     reduced = [torch.cuda.Event() for _ in range(2)]
     step_no = [0]
@@ -221,9 +237,8 @@ def run_ours(args):
         if world > 1 and slot == R - 1:
             mixed[g].record(stream)
             comm.wait_event(mixed[g])
-            with torch.cuda.stream(comm):
-                dist.all_reduce(groups[g])
-                reduced[g].record(comm)
+            exchange(g)
+            reduced[g].record(comm)
 
     def drain():
         if world > 1:
@@ -232,9 +247,8 @@ def run_ours(args):
                 g = (k // R) % 2
                 mixed[g].record(stream)
                 comm.wait_event(mixed[g])
-                with torch.cuda.stream(comm):
-                    dist.all_reduce(groups[g])
-                    reduced[g].record(comm)
+                exchange(g)
+                reduced[g].record(comm)
                 step_no[0] += R - k % R
             stream.wait_stream(comm)
 
@@ -310,13 +324,19 @@ def run_ours(args):
                 ids, p, v = upd[s]
                 ctl.set_motion_ids(ids, n_upd, p, v)
 
+        e2e_tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+
         def step_e2e(s):
             go.release()
-            odb.run(scene, RATE, host_out)  # host tile: H2D of the queued updates and D2H of the result inside
-            if world > 1:
-                t = torch.from_numpy(host_out).to(dev, non_blocking=False)
-                dist.all_reduce(t)
-                host_out[:] = t.cpu().numpy()
+            if world == 1:
+                odb.run(scene, RATE, host_out)  # host tile: H2D of the queued updates and D2H of the result inside
+            else:  # this rank's shard into a device tile, summed over the ranks, then read back
+                scene.sample_device(interval, e2e_tile.data_ptr(), M)
+                if peer:
+                    exch.allreduce(e2e_tile.data_ptr(), M * 2, 0, stream.cuda_stream)
+                else:
+                    dist.all_reduce(e2e_tile)
+                host_out[:] = e2e_tile.cpu().numpy()
 
         th = threading.Thread(target=control_thread, daemon=True)
         th.start()
@@ -354,7 +374,9 @@ def run_ours(args):
             "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
                                    f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
                        "sources": N, "sources_per_gpu": n_local, "frames": M, "rate": RATE,
-                       "parallelism": f"source-shard x{world}" + (f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes" if world > 1 else ""),
+                       "parallelism": f"source-shard x{world}" + ("" if world == 1 else (
+                           f", tiles summed every callback by the library's peer-memory kernel over NVLink ({M * 8} B per rank pair), overlapped with the next mix"
+                           if peer else f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes")),
                        "l2": "inputs larger than L2: every callback reads fresh PCM "
                              f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
                        "kernel_variant": ("staged, strict (bit-exact per-source contributions)" if args.variant == 0 else
@@ -454,7 +476,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --sources per GPU (default), strong = --sources in total")
-    ap.add_argument("--reduce-every", type=int, default=8, help="N > 1: callbacks per all-reduce (1 = live playback)")
+    ap.add_argument("--reduce-every", type=int, default=8, help="--exchange nccl: callbacks per all-reduce (1 = live playback)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-GPU tiles are summed (peer = the library's NVLink peer-memory kernel, every callback)")
     ap.add_argument("--variant", type=int, default=2, choices=[0, 2],
                     help="2 (default) = staged kernel with FMA-contracted value ops, 0 = strict (bit-exact per-source contributions)")
     args = ap.parse_args()

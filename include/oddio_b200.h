@@ -38,6 +38,7 @@ extern "C" {
 typedef struct odb_ctx odb_ctx;     /* one CUDA device + stream + PCM arena; one per process/GPU */
 typedef struct odb_scene odb_scene; /* SpatialSceneControl + SpatialScene pair (spatial.rs:160-189) */
 typedef struct odb_mixer odb_mixer; /* MixerControl<T> + Mixer<T> pair (mixer.rs:61-87) */
+typedef struct odb_exchange odb_exchange; /* multi-GPU sum of the mixed tile over NVLink peer memory (no reference counterpart) */
 typedef uint64_t odb_frames;        /* Arc<Frames<T>> (frames.rs:16-22); 0 is never valid */
 typedef uint64_t odb_source;        /* a playing signal: Spatial / Mixed + its inner controls */
 
@@ -179,6 +180,27 @@ int odb_last_mix_kernel_ms(void* owner, float* out_ms);
  * value multiply-adds contracted to FMA (cursors and indices still bit-exact). Adding 0x100 runs a scene's
  * per-source set-up kernels on a second stream so that they overlap the previous callback's mix. */
 int odb_set_kernel_variant(void* owner, int variant);
+
+/* ---- multi-GPU: sum of the per-GPU tiles over NVLink peer memory ---------------------------------------
+ * The reference is single-process (one `Signal` graph, signal.rs:19); when its sources are sharded over the
+ * GPUs of one box (one process per GPU, each with its own scene/mixer over its shard), the only exchange is
+ * the additive output tile that `SpatialScene::sample` (spatial.rs:376-471) / `Mixer::sample` (mixer.rs:92-119)
+ * accumulate into. These entry points do that exchange without a collective library: every rank pushes its
+ * tile into every rank's inbox with stores over NVLink and sums the inbox in rank order (bit-identical result
+ * on all ranks), in one kernel per callback. Set-up: create on every rank, export the 64-byte handle, gather
+ * the handles of all ranks by any host-side means (rank order), connect. */
+int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t max_floats, odb_exchange** out);
+int odb_exchange_destroy(odb_exchange* ex);
+/* Bytes of one exported handle (a cudaIpcMemHandle_t). */
+int odb_exchange_handle_size(void);
+int odb_exchange_export(odb_exchange* ex, void* handle_out);
+/* `handles`: world x odb_exchange_handle_size() bytes in rank order (the own entry is ignored). */
+int odb_exchange_connect(odb_exchange* ex, const void* handles);
+/* In-place sum over the ranks of `dev_tile` (n_floats f32 in device memory, 16-byte aligned), then the
+ * epilogue (ODB_EPILOGUE_*: Tanh / Reinhard act on the sum, tanh.rs:22-29, reinhard.rs:28-35), queued on
+ * `cuda_stream` (NULL = the context's stream). Every rank must call it once per callback, in the same order.
+ * The shards' own scenes/mixers run with ODB_EPILOGUE_NONE. */
+int odb_exchange_allreduce(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream);
 
 #ifdef __cplusplus
 }

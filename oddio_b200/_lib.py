@@ -96,8 +96,14 @@ SIGNATURES = {
     "odb_set_profiling": [vp, i32],
     "odb_last_mix_kernel_ms": [vp, fp],
     "odb_set_kernel_variant": [vp, i32],
+    "odb_exchange_create": [vp, i32, i32, u32, pvp],
+    "odb_exchange_destroy": [vp],
+    "odb_exchange_export": [vp, vp],
+    "odb_exchange_connect": [vp, vp],
+    "odb_exchange_allreduce": [vp, vp, u32, i32, vp],
 }
-NON_STATUS = {"odb_last_error": (C.c_char_p, []), "odb_abi_version": (C.c_uint32, [])}
+NON_STATUS = {"odb_last_error": (C.c_char_p, []), "odb_abi_version": (C.c_uint32, []),
+              "odb_exchange_handle_size": (C.c_int, [])}
 
 _lib = None
 

@@ -2,12 +2,15 @@
 // over FramesSignal::sample (frames.rs:176-201) for every source whose PCM window of one 1024-frame
 // tile fits in shared memory.
 //
-// A persistent grid of one 12-warp CTA per SM; every warp works on its own batches of 4 consecutive
-// sources and never synchronises with the other warps until the final fold:
-//   1. the warp stages the batch's four 128-byte job records in shared memory and lane 0 starts a bulk
-//      async copy (TMA, cp.async.bulk -> UBLKCP) of the first source's PCM window HBM -> one of the warp's
-//      two PCM buffers, completion on a per-buffer mbarrier;
-//   2. while the copy is in flight all 32 lanes - one per (source, ear, 256-frame chunk) - walk the
+// A persistent grid of one 16-warp CTA per SM; the two warps of a pair mix the two 512-frame halves of the same
+// sources. Every warp works on its own batches of 8 consecutive sources and never synchronises with the other
+// warps until the final fold:
+//   1. the warp stages the batch's eight 128-byte job records in shared memory (bank-swizzled), lanes 0-7 each
+//      derive what this half needs of one source (window address and size, per-chunk tap offsets, dispatch code)
+//      and rewrite their record, so that the per-source set-up later is three broadcast 16-byte loads; one elected
+//      lane starts a bulk async copy (TMA, cp.async.bulk -> UBLKCP) of the first source's PCM window HBM -> one
+//      of the warp's two PCM buffers, completion on a per-buffer mbarrier;
+//   2. while the copy is in flight all 32 lanes - one per (source, ear, 256-frame chunk of the half) - walk the
 //      reference's serial cursor `offset += ds` (frames.rs:195) literally and store every 4th cursor value
 //      to shared memory. The chain is the one part of the path that is not associative: it is evaluated
 //      with exactly the reference's sequence of f32 additions, so frame indices are bit-exact
@@ -16,8 +19,8 @@
 //      buffer): lane l owns frames l, l+32, ... of the tile, re-derives its cursor from the stored
 //      checkpoint with <= 3 more literal additions, splits it into index and fraction with a round-down
 //      magic add (no F2I/I2F), gathers the sample pair from shared memory, lerps (frame.rs:39-41),
-//      applies the per-frame gain ramp (spatial.rs:459) and accumulates into 64 register accumulators
-//      (32 frames x 2 ears, ears packed as FP32x2: FADD2/FFMA2). An ear on FramesSignal's ds ~= 1 path
+//      applies the per-frame gain ramp (spatial.rs:459) and accumulates into 32 packed register accumulators
+//      (16 frames x 2 ears, ears packed as FP32x2: FADD2/FFMA2). An ear on FramesSignal's ds ~= 1 path
 //      (frames.rs:180-187) skips the cursor and uses index base + i with a constant fraction;
 //   4. after its last batch a warp parks the accumulators in shared memory, the CTA folds its warps in a
 //      fixed order and writes one partial tile; k_reduce_tiles sums the partial tiles.

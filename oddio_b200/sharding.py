@@ -1,8 +1,11 @@
 """Multi-GPU plumbing of the spatial/mixer path: one process per GPU, sources sharded over the ranks,
-one sum all-reduce of the small output tile per callback. The reference has no
-counterpart (it is single-process); the collective goes through torch.distributed (NCCL on GPUs,
-gloo in the CPU tests)."""
+one sum of the small output tile per callback. The reference has no counterpart (it is
+single-process). On GPUs the exchange is `PeerExchange`: the library's own one-kernel push/sum over NVLink
+peer memory (csrc/odb_exchange.cu); torch.distributed only carries the 64-byte set-up handles (and the
+NCCL / gloo all-reduce of `allreduce_tile`, kept for comparison and for the CPU tests)."""
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -21,3 +24,58 @@ def allreduce_tile(tile, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(tile, op=dist.ReduceOp.SUM, group=group)
     return tile
+
+
+class PeerExchange:
+    """Sum of the per-rank tiles over NVLink peer memory (include/oddio_b200.h, odb_exchange_*).
+
+    `gather(handle: bytes) -> list[bytes]` returns every rank's handle in rank order; `from_torch` builds
+    it from torch.distributed (any backend: the handles are host bytes)."""
+
+    def __init__(self, ctx, rank: int, world: int, max_floats: int, gather=None):
+        from . import _lib
+
+        self._lib = _lib
+        L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(L.odb_exchange_create(ctx._h, int(rank), int(world), int(max_floats), C.byref(h)))
+        self._h = h
+        self.rank, self.world = rank, world
+        if world > 1:
+            if gather is None:
+                raise ValueError("world > 1 needs a gather function for the set-up handles")
+            n = L.odb_exchange_handle_size()
+            mine = C.create_string_buffer(n)
+            _lib.check(L.odb_exchange_export(self._h, mine))
+            handles = gather(mine.raw)
+            if len(handles) != world or any(len(x) != n for x in handles):
+                raise ValueError("gather must return one handle per rank, in rank order")
+            blob = C.create_string_buffer(b"".join(handles), n * world)
+            _lib.check(L.odb_exchange_connect(self._h, blob))
+
+    @classmethod
+    def from_torch(cls, ctx, max_floats: int, group=None):
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return cls(ctx, 0, 1, max_floats)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def gather(handle: bytes):
+            out = [None] * world
+            dist.all_gather_object(out, handle, group=group)
+            return out
+
+        ex = cls(ctx, rank, world, max_floats, gather)
+        dist.barrier(group)  # every rank has mapped every inbox before the first push
+        return ex
+
+    def allreduce(self, dev_ptr: int, n_floats: int, epilogue: int = 0, stream: int = 0) -> None:
+        """In place on the device tile at `dev_ptr`; queued on `stream` (0 = the context's stream)."""
+        self._lib.check(self._lib.load().odb_exchange_allreduce(self._h, C.c_void_p(dev_ptr), int(n_floats), int(epilogue),
+                                                                C.c_void_p(stream) if stream else None))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.load().odb_exchange_destroy(self._h)
+            self._h = None

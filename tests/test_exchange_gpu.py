@@ -1,0 +1,129 @@
+"""The multi-GPU tile exchange over NVLink peer memory (csrc/odb_exchange.cu) through the C ABI.
+
+* one rank: the exchange is the identity plus the epilogue (every code path of the kernel but the remote stores);
+* two ranks (needs a box with >= 2 GPUs, skipped otherwise): two processes, one GPU each, shard a SpatialScene
+  round-robin, mix their shards with the CUDA path and sum the tiles with the exchange; rank 0 checks the result
+  against the CPU oracle's unsharded mix on the same inputs, callback after callback (both inbox parities),
+  and that both ranks hold bit-identical tiles.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_single_rank_exchange_is_identity_plus_epilogue():
+    import torch
+
+    import oddio_b200 as odb
+    from oddio_b200.sharding import PeerExchange
+
+    ctx = odb.init(0)
+    ex = PeerExchange(ctx, 0, 1, 4096)
+    rng = np.random.default_rng(3)
+    for n in (2048, 514, 2):  # 16-byte multiples and tails
+        x = rng.uniform(-2, 2, n).astype(np.float32)
+        for epi in (0, 1, 2):
+            t = torch.from_numpy(x).cuda()
+            ex.allreduce(t.data_ptr(), n, epi, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = t.cpu().numpy()
+            if epi == 0:
+                assert np.array_equal(got, x)
+            elif epi == 1:
+                np.testing.assert_allclose(got, np.tanh(x.astype(np.float64)), rtol=0, atol=4e-7)  # tanh.rs:26
+            else:
+                assert np.array_equal(got, x / (np.float32(1.0) + np.abs(x)))                       # reinhard.rs:31
+    with pytest.raises(odb.OddioError):
+        ex.allreduce(0, 8, 0)          # NULL tile
+    t = torch.zeros(8192, device="cuda")
+    with pytest.raises(odb.OddioError):
+        ex.allreduce(t.data_ptr(), 8192, 0)  # beyond the capacity given at creation
+    ex.close()
+
+
+def _worker(rank, world, port, n_src, n_frames, n_callbacks, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import oddio_b200 as odb
+    from helpers import rand_in_shell, synth_pcm
+    from oddio_b200.sharding import PeerExchange, shard_sources
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)  # set-up handles only
+    ctx = odb.Context(rank)
+    ex = PeerExchange.from_torch(ctx, 2 * n_frames)
+    rng = np.random.default_rng(11)  # the same scene description on every rank
+    pcms = [synth_pcm(rng, 60000, 48000) for _ in range(4)]
+    pos = [rand_in_shell(rng, 2, 100) for _ in range(n_src)]
+    vel = [rng.uniform(-30, 30, 3).astype(np.float32) for _ in range(n_src)]
+    mine = shard_sources(n_src, rank, world)
+    frames = [odb.Frames.from_slice(48000, p, ctx) for p in pcms]
+    ctl, scene = odb.SpatialScene.new(ctx)
+    for s in mine:
+        ctl.play(odb.FramesSignal(frames[s % 4], 1.0), odb.SpatialOptions(pos[s], vel[s], 0.1))
+    interval = float(np.float32(1.0) / np.float32(48000))
+    tile = torch.zeros((n_frames, 2), device=f"cuda:{rank}", dtype=torch.float32)
+    outs = []
+    for _ in range(n_callbacks):
+        scene.sample_device(interval, tile.data_ptr(), n_frames)
+        ex.allreduce(tile.data_ptr(), 2 * n_frames, 0)
+        ctx.synchronize()
+        outs.append(tile.cpu().numpy().copy())
+    q.put((rank, outs))
+    dist.barrier()
+    scene.close()
+    ex.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_scene_matches_the_oracle(oracle):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box")
+    import torch.multiprocessing as mp
+
+    from helpers import assert_mix_close, rand_in_shell, synth_pcm
+
+    n_src, n_frames, n_cb, world = 37, 1024, 4, 2
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, n_src, n_frames, n_cb, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the unsharded mix on the CPU oracle, same inputs (same seed as the workers)
+    o = oracle
+    rng = np.random.default_rng(11)
+    pcms = [synth_pcm(rng, 60000, 48000) for _ in range(4)]
+    pos = [rand_in_shell(rng, 2, 100) for _ in range(n_src)]
+    vel = [rng.uniform(-30, 30, 3).astype(np.float32) for _ in range(n_src)]
+    full = o.SpatialScene()
+    fr = [o.Frames.from_slice(48000, p) for p in pcms]
+    for s in range(n_src):
+        full.play(o.FramesSignal(fr[s % 4], 1.0), pos[s], vel[s], 0.1)
+    for k in range(n_cb):
+        ref = o.run(full, 48000, n_frames)
+        assert np.array_equal(got[0][k], got[1][k]), "ranks must hold bit-identical sums"
+        assert_mix_close(got[0][k], ref, ref.astype(np.float64))
