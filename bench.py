@@ -202,10 +202,10 @@ def run_ours(args):
     interval = float(np.float32(1.0) / np.float32(RATE))  # oddio::run, lib.rs:91
     # Offline rendering batches R consecutive callbacks per exchange: the sum over ranks is linear, so one
     # all-reduce of R tiles equals R all-reduces of one tile. R = 1 is the live-playback shape.
-    # --exchange peer (default): the library's own one-kernel push/sum over NVLink peer memory, every callback
-    # (R = 1, the live-playback shape); --exchange nccl: torch.distributed all-reduce of R batched tiles.
+    # --exchange peer (default): the library's own one-kernel push/sum over NVLink peer memory; --exchange nccl:
+    # torch.distributed all-reduce. Either way R tiles per exchange (--reduce-every; 1 = the live-playback shape).
     peer = world > 1 and args.exchange == "peer"
-    R = 1 if (world == 1 or peer) else max(1, args.reduce_every)
+    R = 1 if world == 1 else max(1, args.reduce_every)
     groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(2)]
     comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     exch = None
@@ -375,7 +375,7 @@ def run_ours(args):
                                    f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
                        "sources": N, "sources_per_gpu": n_local, "frames": M, "rate": RATE,
                        "parallelism": f"source-shard x{world}" + ("" if world == 1 else (
-                           f", tiles summed every callback by the library's peer-memory kernel over NVLink ({M * 8} B per rank pair), overlapped with the next mix"
+                           f", tiles summed by the library's peer-memory kernel over NVLink, one exchange per {R} callbacks ({R * M * 8} B per rank pair), overlapped with the next mixes"
                            if peer else f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes")),
                        "l2": "inputs larger than L2: every callback reads fresh PCM "
                              f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
@@ -476,7 +476,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --sources per GPU (default), strong = --sources in total")
-    ap.add_argument("--reduce-every", type=int, default=8, help="--exchange nccl: callbacks per all-reduce (1 = live playback)")
+    ap.add_argument("--reduce-every", type=int, default=8, help="N > 1: callbacks per exchange of the tiles (1 = live playback)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-GPU tiles are summed (peer = the library's NVLink peer-memory kernel, every callback)")
     ap.add_argument("--variant", type=int, default=2, choices=[0, 2],

@@ -3,8 +3,9 @@
 // counterpart; `Tanh`/`Reinhard` (tanh.rs:22-29, reinhard.rs:28-35) are applied here because they act on the SUM.
 //
 // One process per GPU. Every rank owns an inbox in its own HBM: [2 parities][world][cap] floats plus
-// [2][world] sequence flags, exported to the other ranks of the box as a CUDA IPC handle and mapped by them.
-// One kernel per callback and rank, no NCCL on the data path:
+// [2][world][slices] sequence flags, exported to the other ranks of the box as a CUDA IPC handle and mapped by them.
+// One kernel per exchange and rank, one CTA per 2048-float slice of the tile (a 1024-frame stereo callback is one
+// slice; offline rendering exchanges several callbacks at once), no NCCL on the data path. Per slice:
 //   1. push: the rank stores its partial tile into slot `rank` of every rank's inbox (plain stores over NVLink;
 //      its own inbox included), fences to system scope and then publishes the callback's sequence number in the
 //      same slot's flag with a release store;
@@ -36,13 +37,18 @@ struct ExchangePeers {
     char* inbox[ODB_MAX_RANKS];  // inbox of every rank as mapped into this process ([rank] = the local one)
 };
 
-__global__ void __launch_bounds__(1024) k_exchange_tiles(float* __restrict__ tile, int n_floats, ExchangePeers peers, int rank,
-                                                          int world, uint32_t cap, size_t flags_off, uint32_t seq,
-                                                          int epilogue) {
+#define ODB_EXCHANGE_SLICE 2048  // floats per CTA
+
+__global__ void __launch_bounds__(512) k_exchange_tiles(float* __restrict__ tile_all, int n_floats_all, ExchangePeers peers,
+                                                         int rank, int world, uint32_t cap, size_t flags_off, int max_slices,
+                                                         uint32_t seq, int epilogue) {
     const uint32_t par = seq & 1u;
     const int tid = threadIdx.x, nth = blockDim.x;
-    // 1. push (16-byte stores; the tile and the slots are 16-byte aligned, n_floats is even: stereo or padded mono)
-    const size_t slot = ((size_t)par * world + rank) * cap;
+    const int first = blockIdx.x * ODB_EXCHANGE_SLICE;
+    const int n_floats = min(ODB_EXCHANGE_SLICE, n_floats_all - first);
+    float* tile = tile_all + first;
+    // 1. push (16-byte stores; the tile and the slots are 16-byte aligned)
+    const size_t slot = ((size_t)par * world + rank) * cap + first;
     const int n4 = n_floats >> 2;
     for (int g = 0; g < world; g++) {
         float* dst = reinterpret_cast<float*>(peers.inbox[g]) + slot;
@@ -51,15 +57,17 @@ __global__ void __launch_bounds__(1024) k_exchange_tiles(float* __restrict__ til
     }
     __threadfence_system();
     __syncthreads();
-    if (tid < world) st_release_sys(reinterpret_cast<uint32_t*>(peers.inbox[tid] + flags_off) + par * world + rank, seq);
+    const size_t flag_idx = ((size_t)par * world) * max_slices + blockIdx.x;  // + rank * max_slices
+    if (tid < world)
+        st_release_sys(reinterpret_cast<uint32_t*>(peers.inbox[tid] + flags_off) + flag_idx + (size_t)rank * max_slices, seq);
     // 2. pull
     const char* mine = peers.inbox[rank];
     if (tid < world) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + par * world + tid;
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + flag_idx + (size_t)tid * max_slices;
         while ((int)(ld_acquire_sys(flag) - seq) < 0) __nanosleep(20);
     }
     __syncthreads();
-    const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * world * cap;
+    const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * world * cap + first;
     for (int i = tid; i < n_floats; i += nth) {
         float sum = 0.0f;
         for (int g = 0; g < world; g++) sum = sum + __ldcv(in + (size_t)g * cap + i);  // rank order: same sum on every rank
@@ -76,6 +84,7 @@ struct odb_exchange {
     odb_ctx* ctx = nullptr;
     int rank = 0, world = 1;
     uint32_t cap = 0;          // floats per slot
+    int max_slices = 1;
     size_t flags_off = 0, bytes = 0;
     char* local = nullptr;
     odbk::ExchangePeers peers;
@@ -99,8 +108,9 @@ extern "C" int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t m
     ex->rank = rank;
     ex->world = world;
     ex->cap = (max_floats + 31u) & ~31u;  // slots stay 128-byte aligned
+    ex->max_slices = (int)((ex->cap + ODB_EXCHANGE_SLICE - 1) / ODB_EXCHANGE_SLICE);
     ex->flags_off = (size_t)2 * world * ex->cap * sizeof(float);
-    ex->bytes = ex->flags_off + (size_t)2 * world * sizeof(uint32_t);
+    ex->bytes = ex->flags_off + (size_t)2 * world * ex->max_slices * sizeof(uint32_t);
     for (int g = 0; g < ODB_MAX_RANKS; g++) ex->peers.inbox[g] = nullptr;
     cudaError_t e = cudaMalloc((void**)&ex->local, ex->bytes);
     if (e != cudaSuccess) {
@@ -155,8 +165,10 @@ extern "C" int odb_exchange_allreduce(odb_exchange* ex, void* dev_tile, uint32_t
     ODB_CUDA(cudaSetDevice(ex->ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->ctx->stream;
     ex->seq++;  // flags are compared as signed differences, so wrap-around is harmless
-    odbk::k_exchange_tiles<<<1, 1024, 0, st>>>((float*)dev_tile, (int)n_floats, ex->peers, ex->rank, ex->world, ex->cap,
-                                               ex->flags_off, ex->seq, epilogue);
+    if (n_floats == 0) return ODB_OK;
+    const int n_slices = (int)((n_floats + ODB_EXCHANGE_SLICE - 1) / ODB_EXCHANGE_SLICE);
+    odbk::k_exchange_tiles<<<n_slices, 512, 0, st>>>((float*)dev_tile, (int)n_floats, ex->peers, ex->rank, ex->world, ex->cap,
+                                                     ex->flags_off, ex->max_slices, ex->seq, epilogue);
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
 }

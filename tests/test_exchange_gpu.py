@@ -34,7 +34,7 @@ def test_single_rank_exchange_is_identity_plus_epilogue():
     ctx = odb.init(0)
     ex = PeerExchange(ctx, 0, 1, 4096)
     rng = np.random.default_rng(3)
-    for n in (2048, 514, 2):  # 16-byte multiples and tails
+    for n in (2048, 514, 2, 4096, 3000):  # 16-byte multiples, tails, several slices
         x = rng.uniform(-2, 2, n).astype(np.float32)
         for epi in (0, 1, 2):
             t = torch.from_numpy(x).cuda()
