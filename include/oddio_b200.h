@@ -67,6 +67,11 @@ int odb_frames_from_slice(odb_ctx* ctx, uint32_t rate, int channels, const float
  * the arena, so the caller may free it afterwards). For PCM decoded or synthesised on the GPU. */
 int odb_frames_from_device(odb_ctx* ctx, uint32_t rate, int channels, const void* dev_samples, uint64_t n_frames,
                            odb_frames* out);
+/* PCM ingest of integer WAV data (examples/wav.rs:30-46): `n_frames` interleaved frames of 16-bit containers holding
+ * `bits_per_sample`-bit signed samples (2..16) are uploaded as they are and scaled on the device exactly as the
+ * example does on the CPU, `sample as f32 / (2^(bits-1) - 1) as f32`, into an f32 Frames block. */
+int odb_frames_from_i16(odb_ctx* ctx, uint32_t rate, int channels, const int16_t* samples, uint64_t n_frames,
+                        int bits_per_sample, odb_frames* out);
 /* Drops one reference (Arc drop). Storage is freed once no playing source uses it. */
 int odb_frames_release(odb_ctx* ctx, odb_frames frames);
 
@@ -123,6 +128,9 @@ int odb_spatial_set_motion_many(odb_scene* scene, uint32_t n, const odb_source* 
 int odb_spatial_is_finished(odb_scene* scene, odb_source src, int* out);
 /* <SpatialScene as Signal>::sample (spatial.rs:376-471): n_frames stereo frames, interleaved L,R */
 int odb_scene_sample(odb_scene* scene, float interval, float* out, uint32_t n_frames);
+/* Offline render (examples/offline.rs:33-43): as odb_scene_sample, with the tile quantised on the device as the
+ * example does before it writes the WAV file, `(sample * i16::MAX as f32) as i16` (toward zero, saturating). */
+int odb_scene_sample_i16(odb_scene* scene, float interval, int16_t* out, uint32_t n_frames);
 /* oddio::run(&mut scene, sample_rate, out) (lib.rs:90-93): interval = 1.0 / sample_rate as f32 */
 int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames);
 /* As odb_scene_sample, but the mixed tile is left in DEVICE memory `dev_out` (2*n_frames f32),
@@ -145,6 +153,8 @@ int odb_mixed_is_stopped(odb_mixer* mixer, odb_source src, int* out);
 /* <Mixer<T> as Signal>::sample (mixer.rs:92-119) and oddio::run over it */
 int odb_mixer_sample(odb_mixer* mixer, float interval, float* out, uint32_t n_frames);
 int odb_mixer_run(odb_mixer* mixer, uint32_t sample_rate, float* out, uint32_t n_frames);
+/* Offline render: as odb_scene_sample_i16 (examples/offline.rs:39) */
+int odb_mixer_sample_i16(odb_mixer* mixer, float interval, int16_t* out, uint32_t n_frames);
 int odb_mixer_sample_device(odb_mixer* mixer, float interval, void* dev_out, uint32_t n_frames);
 int odb_mixer_len(odb_mixer* mixer, uint64_t* out);
 

@@ -96,6 +96,9 @@ SIGNATURES = {
     "odb_set_profiling": [vp, i32],
     "odb_last_mix_kernel_ms": [vp, fp],
     "odb_set_kernel_variant": [vp, i32],
+    "odb_frames_from_i16": [vp, u32, i32, C.POINTER(C.c_int16), u64, i32, pu64],
+    "odb_scene_sample_i16": [vp, f32, C.POINTER(C.c_int16), u32],
+    "odb_mixer_sample_i16": [vp, f32, C.POINTER(C.c_int16), u32],
     "odb_exchange_create": [vp, i32, i32, u32, pvp],
     "odb_exchange_destroy": [vp],
     "odb_exchange_export": [vp, vp],

@@ -101,6 +101,18 @@ class Frames:
         return Frames(ctx, h.value, rate, ch, a.shape[0])
 
     @staticmethod
+    def from_i16(rate: int, samples, bits_per_sample: int = 16, ctx: Optional[Context] = None) -> "Frames":
+        """Integer PCM (examples/wav.rs:30-46): uploaded as int16 and scaled to f32 on the device,
+        `sample as f32 / (2^(bits-1) - 1) as f32`. `samples`: int16, shape (n,) or (n, 2)."""
+        ctx = ctx or default_context()
+        a = np.ascontiguousarray(samples, dtype=np.int16)
+        ch = 1 if a.ndim == 1 else int(a.shape[1])
+        h = C.c_uint64()
+        check(_lib.load().odb_frames_from_i16(ctx._h, int(rate), ch, a.ctypes.data_as(C.POINTER(C.c_int16)), a.shape[0],
+                                              int(bits_per_sample), C.byref(h)))
+        return Frames(ctx, h.value, rate, ch, a.shape[0])
+
+    @staticmethod
     def from_iter(rate: int, it, ctx: Optional[Context] = None) -> "Frames":
         """Frames::from_iter (frames.rs:50-77)."""
         return Frames.from_slice(rate, np.asarray(list(it), dtype=np.float32), ctx)
@@ -351,7 +363,7 @@ class Spatial:
 class _Aggregator(Signal):
     """Common part of the two hot-loop owners: sample / run / epilogue wrapper."""
 
-    _sample = _sample_device = _destroy = _set_epilogue = None
+    _sample = _sample_device = _sample_i16 = _destroy = _set_epilogue = None
 
     def _out(self, n: int, out: Optional[np.ndarray]) -> np.ndarray:
         shape = (n, self.channels) if self.channels > 1 else (n,)
@@ -372,6 +384,14 @@ class _Aggregator(Signal):
 
     def sample_device(self, interval: float, dev_ptr: int, n_frames: int) -> None:
         check(self._sample_device(self._h, _f32(interval), C.c_void_p(dev_ptr), int(n_frames)))
+
+    def sample_i16(self, interval: float, n_frames: int) -> np.ndarray:
+        """One callback quantised to 16-bit PCM on the device, `(sample * i16::MAX as f32) as i16`
+        (examples/offline.rs:39); returns int16 of shape (n, channels) or (n,)."""
+        n = int(n_frames)
+        out = np.zeros((n, self.channels) if self.channels > 1 else (n,), dtype=np.int16)
+        check(self._sample_i16(self._h, _f32(interval), out.ctypes.data_as(C.POINTER(C.c_int16)), n))
+        return out
 
     def is_finished(self) -> bool:  # spatial.rs:473-476 / Signal default
         return False
@@ -421,7 +441,7 @@ class SpatialScene(_Aggregator):
         h = C.c_void_p()
         check(L.odb_scene_create(ctx._h, C.byref(h)))
         self._h, self._ctx = h, ctx
-        self._sample, self._sample_device = L.odb_scene_sample, L.odb_scene_sample_device
+        self._sample, self._sample_device, self._sample_i16 = L.odb_scene_sample, L.odb_scene_sample_device, L.odb_scene_sample_i16
         self._destroy, self._set_epilogue = L.odb_scene_destroy, L.odb_scene_set_epilogue
 
     @staticmethod
@@ -513,7 +533,7 @@ class Mixer(_Aggregator):
         h = C.c_void_p()
         check(L.odb_mixer_create(ctx._h, int(channels), C.byref(h)))
         self._h, self._ctx, self.channels = h, ctx, int(channels)
-        self._sample, self._sample_device = L.odb_mixer_sample, L.odb_mixer_sample_device
+        self._sample, self._sample_device, self._sample_i16 = L.odb_mixer_sample, L.odb_mixer_sample_device, L.odb_mixer_sample_i16
         self._destroy, self._set_epilogue = L.odb_mixer_destroy, L.odb_mixer_set_epilogue
 
     @staticmethod
@@ -561,6 +581,9 @@ class _Epilogue(Signal):
 
     def sample_device(self, interval: float, dev_ptr: int, n_frames: int) -> None:
         self.inner.sample_device(interval, dev_ptr, n_frames)
+
+    def sample_i16(self, interval: float, n_frames: int) -> np.ndarray:
+        return self.inner.sample_i16(interval, n_frames)
 
     def is_finished(self) -> bool:
         return self.inner.is_finished()

@@ -147,6 +147,37 @@ static int frames_new(odb_ctx* ctx, uint32_t rate, int channels, const void* sam
     *out = id;
     return ODB_OK;
 }
+// examples/wav.rs:30-46: integer PCM is uploaded as it is (half the bytes of f32) and scaled to f32 on the device
+extern "C" int odb_frames_from_i16(odb_ctx* ctx, uint32_t rate, int channels, const int16_t* samples, uint64_t n_frames,
+                                   int bits_per_sample, odb_frames* out) {
+    if (!samples) return odb_fail(ODB_E_INVALID, "samples is NULL");
+    if (bits_per_sample < 2 || bits_per_sample > 16)
+        return odb_fail(ODB_E_UNSUPPORTED, "bits_per_sample %d: 2..16 fit the 16-bit container", bits_per_sample);
+    ODB_TRY(frames_new(ctx, rate, channels, nullptr, n_frames, false, out));
+    FramesRec rec;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        rec = ctx->frames[*out];
+    }
+    const size_t elems = (size_t)n_frames * channels;
+    short* tmp = nullptr;
+    cudaError_t e = cudaMalloc((void**)&tmp, elems * sizeof(short));
+    if (e != cudaSuccess) {
+        ctx->frames_unref(*out);
+        return odb_fail(ODB_E_NOMEM, "cudaMalloc of the %zu-byte upload buffer failed: %s", elems * sizeof(short), cudaGetErrorString(e));
+    }
+    e = cudaMemcpyAsync(tmp, samples, elems * sizeof(short), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        odb_launch_convert_i16(tmp, rec.dev, elems, (float)((1u << (bits_per_sample - 1)) - 1u), ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        ctx->frames_unref(*out);
+        return odb_fail(ODB_E_CUDA, "integer PCM upload failed: %s", cudaGetErrorString(e));
+    }
+    return ODB_OK;
+}
 extern "C" int odb_frames_from_slice(odb_ctx* ctx, uint32_t rate, int channels, const float* samples, uint64_t n_frames,
                                      odb_frames* out) {
     if (!samples) return odb_fail(ODB_E_INVALID, "samples is NULL");

@@ -56,6 +56,9 @@ struct OdbParamMsg {  // SpeedControl::set_speed / GainControl::set_amplitude_ra
     uint32_t pad;
 };
 
+// Internal bit of the reduce kernel's epilogue argument: store the tile as 16-bit PCM (offline render) instead of f32.
+#define ODB_EPILOGUE_I16_BIT 0x100
+void odb_launch_convert_i16(const short* in, float* out, size_t n, float max_value, cudaStream_t st);
 void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const uint32_t* slots, int n, cudaStream_t st);
 void odb_launch_scatter_motion(OdbSource* src, const OdbMotionMsg* msgs, int n, cudaStream_t st);
 void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, cudaStream_t st);

@@ -97,7 +97,7 @@ extern "C" int odb_mixed_is_stopped(odb_mixer* mixer, odb_source src, int* out) 
 }
 
 // <Mixer<T> as Signal>::sample, mixer.rs:92-119
-static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, uint32_t n_frames) {
+static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, uint32_t n_frames, bool as_i16 = false) {
     odb_ctx* ctx = mixer->ctx;
     cudaStream_t st = ctx->stream;
     if (n_frames > ODB_MIXER_MAX_TILES * ODB_MIXER_CHUNK)
@@ -156,7 +156,7 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
             launches++;
         }
         odb_launch_reduce(mixer->d_partials_unit.p, n_unit, mixer->d_partials_gen.p, n_gen, mixer->d_partials_res.p, n_res,
-                          mixer->d_counters.p, n_unit > 0 ? 1 : 0, n_res > 0 ? ODB_CNT_RESAMPLE : -1, nullptr, dev_out, (int)n_frames, nt, ch, mixer->epilogue, st);
+                          mixer->d_counters.p, n_unit > 0 ? 1 : 0, n_res > 0 ? ODB_CNT_RESAMPLE : -1, nullptr, dev_out, (int)n_frames, nt, ch, mixer->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0), st);
         launches++;
     }
     ODB_TRY(mixer->set.post_callback(ctx, st));  // audio-side state only: no control-plane lock
@@ -176,6 +176,19 @@ extern "C" int odb_mixer_sample(odb_mixer* mixer, float interval, float* out, ui
     ODB_TRY(mixer_sample_impl(mixer, interval, mixer->h_out.p, n_frames));
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n) memcpy(out, mixer->h_out.p, n * sizeof(float));
+    return mixer->set.fold_removed(ctx, ctx->stream, true, &mixer->mu);
+}
+// Offline render (examples/offline.rs:33-43): one callback quantised to 16-bit PCM on the device
+extern "C" int odb_mixer_sample_i16(odb_mixer* mixer, float interval, int16_t* out, uint32_t n_frames) {
+    ODB_TRY(mixer_check(mixer));
+    if (!out && n_frames) return odb_fail(ODB_E_INVALID, "out is NULL");
+    odb_ctx* ctx = mixer->ctx;
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)n_frames * mixer->channels;
+    ODB_TRY(mixer->h_out.ensure(n ? n : 2));
+    ODB_TRY(mixer_sample_impl(mixer, interval, mixer->h_out.p, n_frames, /*as_i16=*/true));
+    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n) memcpy(out, mixer->h_out.p, n * sizeof(int16_t));
     return mixer->set.fold_removed(ctx, ctx->stream, true, &mixer->mu);
 }
 // oddio::run, lib.rs:90-93

@@ -313,7 +313,7 @@ static int ensure_idle(odb_scene* scene, DevBuf<T>& buf, size_t n) {
     return buf.ensure(n, scene->ctx->stream, false);
 }
 
-static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames) {
+static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames, bool as_i16 = false) {
     odb_ctx* ctx = scene->ctx;
     cudaStream_t st = ctx->stream, wst = scene->pipelined ? scene->wst : ctx->stream;
     if (n_frames > ODB_MAX_FRAMES)
@@ -436,7 +436,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
                           counters, /*b_is_general=*/n_fast > 0 ? 1 : 0,
                           /*c_counter=*/(n_fast > 0 && n_ring > 0) ? ODB_CNT_RING_GENERAL : -1,
                           /*zero_counters=*/scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p, dev_out,
-                          (int)n_frames, nt, 2, scene->epilogue, st);
+                          (int)n_frames, nt, 2, scene->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0), st);
         launches++;
     }
     seg(2);
@@ -475,6 +475,22 @@ extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, ui
         scene->tr_calls++;
     }
     return rc;
+}
+// Offline render (examples/offline.rs:33-43): one callback quantised to 16-bit PCM on the device,
+// `(sample * i16::MAX as f32) as i16`; half the bytes of the f32 tile cross to the host.
+extern "C" int odb_scene_sample_i16(odb_scene* scene, float interval, int16_t* out, uint32_t n_frames) {
+    ODB_TRY(scene_check(scene));
+    if (!out && n_frames) return odb_fail(ODB_E_INVALID, "out is NULL");
+    odb_ctx* ctx = scene->ctx;
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)n_frames * 2;
+    ODB_TRY(scene->h_out.ensure(n ? n : 2));
+    ODB_TRY(scene_sample_impl(scene, interval, scene->h_out.p, n_frames, /*as_i16=*/true));
+    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n) memcpy(out, scene->h_out.p, n * sizeof(int16_t));
+    cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
+    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
+    return scene->seek.fold_removed(ctx, ws, true, &scene->mu);
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {

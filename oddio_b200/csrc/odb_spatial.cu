@@ -354,9 +354,23 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
     for (int g = 0; g < RED_GROUPS; g++) sum = sum + fold[g][lane];
     const int frame = tl * ODB_TILE_FRAMES + f / channels;
     if (frame >= n_frames) return;
-    if (epilogue == 1) sum = tanhf(sum);
-    else if (epilogue == 2) sum = sum / (1.0f + fabsf(sum));
-    out[(size_t)tl * tile_floats + f] = sum;
+    if ((epilogue & 0xFF) == 1) sum = tanhf(sum);
+    else if ((epilogue & 0xFF) == 2) sum = sum / (1.0f + fabsf(sum));
+    if (epilogue & ODB_EPILOGUE_I16_BIT) {
+        // offline render, examples/offline.rs:39 `(sample * i16::MAX as f32) as i16`: one f32 multiply, then Rust's
+        // float -> int `as`: toward zero, saturating, NaN -> 0 (cvt.rzi.s32.f32 does the same for the i32 range)
+        int v = __float2int_rz(sum * 32767.0f);
+        v = max(-32768, min(32767, v));
+        reinterpret_cast<short*>(out)[(size_t)tl * tile_floats + f] = (short)v;
+    } else {
+        out[(size_t)tl * tile_floats + f] = sum;
+    }
+}
+
+// PCM ingest, examples/wav.rs:30-37: integer samples -> `sample as f32 / max_value as f32`, max_value = 2^(bits-1) - 1
+__global__ void k_convert_i16(const short* __restrict__ in, float* __restrict__ out, size_t n, float max_value) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i] / max_value;
 }
 
 }  // namespace odbk
@@ -365,6 +379,10 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_tiles(const float* _
 // Launchers (host side, called from odb_api.cu)
 using namespace odbk;
 
+void odb_launch_convert_i16(const short* in, float* out, size_t n, float max_value, cudaStream_t st) {
+    if (n == 0) return;
+    k_convert_i16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, max_value);
+}
 void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const uint32_t* slots, int n, cudaStream_t st) {
     if (n <= 0) return;
     long long total = (long long)n * (long long)(sizeof(OdbSource) / 16);

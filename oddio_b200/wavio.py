@@ -1,6 +1,9 @@
-"""The steps either side of the hot path, host side only:
-WAV ingest -> Frames (examples/wav.rs:15-46) and offline render -> 16-bit WAV (examples/offline.rs:25-45).
-Pure Python/numpy over the standard `wave` module; no arithmetic of the mix itself lives here."""
+"""The steps either side of the hot path: WAV ingest -> Frames (examples/wav.rs:15-46)
+and offline render -> 16-bit WAV (examples/offline.rs:25-45). File handling is Python's `wave` module; the
+arithmetic of both steps runs on the device when the data allows it (8/16-bit integer files are uploaded as
+int16 and scaled by `odb_frames_from_i16`; `render_offline_device` quantises every block with `*_sample_i16`).
+The numpy versions below are the reference statements the tests compare the device against; no arithmetic of
+the mix itself lives here."""
 from __future__ import annotations
 
 import wave
@@ -41,11 +44,21 @@ def read_wav(path: str) -> Tuple[int, np.ndarray]:
 
 
 def frames_from_wav(path: str, ctx=None):
-    """examples/wav.rs:44-46: decode, `frame_stereo`, `Frames::from_slice` - PCM goes to HBM once."""
+    """examples/wav.rs:44-46: decode, `frame_stereo`, `Frames::from_slice` - PCM goes to HBM once. 8- and 16-bit
+    files cross the bus as int16 and are scaled on the device (bit-identical to `read_wav`)."""
     from .api import Frames
 
-    rate, x = read_wav(path)
-    return Frames.from_slice(rate, x, ctx)
+    with wave.open(path, "rb") as w:
+        ch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        raw = w.readframes(n) if width in (1, 2) and ch in (1, 2) else None
+    if raw is None:
+        rate, x = read_wav(path)
+        return Frames.from_slice(rate, x, ctx)
+    if width == 1:
+        ints = (np.frombuffer(raw, dtype=np.uint8).astype(np.int16) - 128)
+    else:
+        ints = np.frombuffer(raw, dtype="<i2").astype(np.int16)
+    return Frames.from_i16(rate, ints if ch == 1 else ints.reshape(-1, ch), 8 * width, ctx)
 
 
 def render_offline(run: Callable[[int], np.ndarray], path: str, rate: int, block_size: int, n_blocks: int, channels: int = 2) -> int:
@@ -57,4 +70,17 @@ def render_offline(run: Callable[[int], np.ndarray], path: str, rate: int, block
         w.setframerate(rate)
         for _ in range(n_blocks):
             w.writeframes(quantize_i16(run(block_size)).astype("<i2").tobytes())
+    return n_blocks * block_size
+
+
+def render_offline_device(signal, path: str, rate: int, block_size: int, n_blocks: int) -> int:
+    """examples/offline.rs:25-45 with the quantisation on the device: `n_blocks` callbacks of `block_size` frames of
+    `signal` (a SpatialScene / Mixer, possibly under Tanh / Reinhard), each leaving the GPU as 16-bit PCM."""
+    interval = float(np.float32(1.0) / np.float32(rate))  # oddio::run, lib.rs:91
+    with wave.open(path, "wb") as w:
+        w.setnchannels(signal.channels)
+        w.setsampwidth(2)
+        w.setframerate(rate)
+        for _ in range(n_blocks):
+            w.writeframes(signal.sample_i16(interval, block_size).astype("<i2").tobytes())
     return n_blocks * block_size
