@@ -87,6 +87,9 @@ int odb_frames_release(odb_ctx* ctx, odb_frames frames);
 #define ODB_CHAIN_SPEED 0x1u
 #define ODB_CHAIN_FIXED_GAIN 0x2u
 #define ODB_CHAIN_GAIN 0x4u
+#define ODB_CHAIN_CYCLE 0x8u /* the innermost signal is Cycle<T> (cycle.rs:6-61) instead of FramesSignal<T>: `start_seconds`
+                              * then holds the initial cursor in SAMPLES (0 after Cycle::new; whatever Seek::seek calls made
+                              * before play left, cycle.rs:57-60). Mixer only: odb_scene_play* answer ODB_E_UNSUPPORTED. */
 typedef struct odb_chain {
     odb_frames frames;     /* the Arc<Frames<T>> played */
     double start_seconds;  /* FramesSignal::new start_seconds, may be negative */

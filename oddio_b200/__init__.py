@@ -7,7 +7,7 @@ and is test infrastructure only.
 """
 from ._lib import OddioError, SO_PATH, load  # noqa: F401
 from .api import (  # noqa: F401
-    Context, FixedGain, Frames, FramesSignal, FramesSignalControl, Gain, GainControl, Mixed, Mixer, MixerControl,
+    Context, Cycle, FixedGain, Frames, FramesSignal, FramesSignalControl, Gain, GainControl, Mixed, Mixer, MixerControl,
     Reinhard, Signal, Spatial, SpatialOptions, SpatialScene, SpatialSceneControl, Speed, SpeedControl, Tanh,
     default_context, flatten_stereo, frame_stereo, init, run,
 )

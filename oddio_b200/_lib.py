@@ -20,6 +20,7 @@ ODB_E_NOMEM = -4
 CHAIN_SPEED = 0x1
 CHAIN_FIXED_GAIN = 0x2
 CHAIN_GAIN = 0x4
+CHAIN_CYCLE = 0x8
 
 EPILOGUE_NONE = 0
 EPILOGUE_TANH = 1

@@ -224,6 +224,31 @@ class FramesSignal(Signal):
         controls.append(self.control)
 
 
+class Cycle(Signal):
+    """cycle.rs:6-61: loops a Frames block end to end. On the device it plays under a Mixer (optionally inside
+    Speed / FixedGain / Gain); the literal kernel walks its cursor exactly as Cycle::sample does."""
+
+    _is_seek = True
+
+    def __init__(self, frames: Frames):
+        self.frames, self.channels = frames, frames.channels
+        self._cursor = 0.0  # in samples (cycle.rs:8); moved by seek() until the signal is played
+        self.control = FramesSignalControl(frames, 0.0)  # parity aid only: cursor() reads the device's f64 cursor
+
+    def seek(self, seconds: float) -> None:
+        """Seek::seek (cycle.rs:57-60), before playing."""
+        n = float(len(self.frames))
+        c = self._cursor + float(np.float32(seconds)) * float(self.frames.rate())
+        r = float(np.fmod(c, n))
+        self._cursor = r + n if r < 0.0 else r  # f64::rem_euclid
+
+    def _chain(self, chain: Chain, controls: list) -> None:
+        chain.frames = self.frames._h
+        chain.start_seconds = self._cursor
+        chain.flags |= _lib.CHAIN_CYCLE
+        controls.append(self.control)
+
+
 class SpeedControl(_Bound):
     """speed.rs:43-55"""
 
@@ -244,8 +269,8 @@ class Speed(Signal):
     """speed.rs:9-41. Not Seek."""
 
     def __init__(self, inner: Signal):
-        if not isinstance(inner, FramesSignal):
-            raise OddioError(_lib.ODB_E_UNSUPPORTED, "device path: Speed must wrap a FramesSignal directly")
+        if not isinstance(inner, (FramesSignal, Cycle)):
+            raise OddioError(_lib.ODB_E_UNSUPPORTED, "device path: Speed must wrap a FramesSignal or Cycle directly")
         self.inner, self.channels = inner, inner.channels
         self.control = SpeedControl()
 
@@ -265,7 +290,7 @@ class FixedGain(Signal):
     """gain.rs:9-51. Seek iff inner is."""
 
     def __init__(self, inner: Signal, db: float):
-        if not isinstance(inner, (FramesSignal, Speed)):
+        if not isinstance(inner, (FramesSignal, Cycle, Speed)):
             raise OddioError(_lib.ODB_E_UNSUPPORTED, "device path: FixedGain must wrap FramesSignal or Speed")
         self.inner, self.channels, self.db = inner, inner.channels, _f32(db)
         self._is_seek = inner._is_seek
@@ -302,7 +327,7 @@ class Gain(Signal):
     """gain.rs:58-127. Not Seek."""
 
     def __init__(self, inner: Signal):
-        if not isinstance(inner, (FramesSignal, Speed, FixedGain)):
+        if not isinstance(inner, (FramesSignal, Cycle, Speed, FixedGain)):
             raise OddioError(_lib.ODB_E_UNSUPPORTED, "device path: Gain must wrap FramesSignal, Speed or FixedGain")
         self.inner, self.channels = inner, inner.channels
         self.control = GainControl()

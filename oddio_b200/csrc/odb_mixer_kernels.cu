@@ -47,17 +47,39 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
     const float gstep = cb.interval / ODB_GAIN_SMOOTHING;                           // gain.rs:120
     long long sample_t = s.sample_t;
     uint32_t n_general = 0, n_fast = 0, n_resample = 0;
+    const bool cycle = (flags & ODB_SF_CYCLE) != 0;
     for (int tl = 0; tl < nt; tl++) {
         const int n = min(ODB_MIXER_CHUNK, cb.n_frames - tl * ODB_MIXER_CHUNK);
         OdbMixJob j;
         j.pcm = s.pcm; j.len = s.len; j.n_frames = n; j.ds = ds;
         uint32_t jf = unit ? ODB_JF_FAST_L : 0u;
-        const double s0 = t * rate;                                                 // frames.rs:177
-        const long long base = (long long)s0;                                       // frames.rs:179
-        const float off0 = (float)(s0 - (double)base);                              // frames.rs:183 / :189
+        long long base;
+        float off0;
+        if (cycle) {
+            // Cycle::sample (cycle.rs:26-53): `t` is the cursor in samples. Where the next chunk starts depends on the f32
+            // chain of this one (and on where it wrapped), so the chain is walked here once without the taps; the literal
+            // kernel walks it again from (base, off0) with them.
+            jf = ODB_JF_CYCLE;
+            const unsigned long long len = (unsigned long long)s.len;
+            unsigned long long cbase = (unsigned long long)t;                       // :28 `self.cursor as usize`
+            float offset = (float)(t - (double)cbase);                              // :29
+            base = (long long)cbase; off0 = offset;
+            for (int i = 0; i < n; i++) {
+                const unsigned long long tr = (unsigned long long)offset;           // :31
+                const float fract = offset - (float)tr;                             // :32
+                const unsigned long long x = cbase + tr;                            // :33
+                if (x >= len) { cbase = 0; offset = (float)(x % len) + fract; }     // :38-40
+                offset = offset + ds;                                               // :50
+            }
+            t = (double)cbase + (double)offset;                                     // :52
+        } else {
+            const double s0 = t * rate;                                             // frames.rs:177
+            base = (long long)s0;                                                   // frames.rs:179
+            off0 = (float)(s0 - (double)base);                                      // frames.rs:183 / :189
+            t = t + (double)iv * (double)n;                                         // frames.rs:198
+            sample_t = (long long)(t * rate);                                       // frames.rs:199-200
+        }
         j.base = sat_i32(base); j.off0 = off0;
-        t = t + (double)iv * (double)n;                                             // frames.rs:198
-        sample_t = (long long)(t * rate);                                           // frames.rs:199-200
         j.fixed_gain = s.fixed_gain;                                                // 1.0 when the chain has no FixedGain
         j.g = 1.0f; j.gprev = 0.0f; j.gnext = 0.0f; j.gprog = 0.0f; j.gstep = gstep;
         if (flags & ODB_SF_GAIN) {                                                  // gain.rs:104-121
@@ -82,7 +104,7 @@ __global__ void __launch_bounds__(128) k_walk_mixer(OdbSource* __restrict__ src,
         const long long reach = unit ? n : (long long)((double)off0 + (double)(n - 1) * (double)ds) + 4;
         const bool in_block = base >= -(pad_frames - 4) && base + reach + 1 <= (long long)s.len + pad_frames - 4 &&
                               base < (1ll << 29) && base > -(1ll << 29);
-        if (cb.force_general || off0 < 0.0f || !in_block || (jf & ODB_JF_RAMP)) jf |= ODB_JF_GENERAL;
+        if (cb.force_general || off0 < 0.0f || !in_block || (jf & (ODB_JF_RAMP | ODB_JF_CYCLE))) jf |= ODB_JF_GENERAL;
         else if (!unit) {
             if (ds > 0.0f && (reach + 2) * ch + 4 <= ODB_MIXER_RESAMPLE_CAP) jf |= ODB_JF_RESAMPLE;
             else jf |= ODB_JF_GENERAL;
@@ -382,13 +404,35 @@ __global__ void __launch_bounds__(WARPS * 32) k_mixer_general(const OdbMixJob* _
             const float* __restrict__ pcm = job->pcm;
             const long long len = job->len, base = job->base, pad_frames = ODB_PCM_PAD / CH;
             const float ds = job->ds, fg = job->fixed_gain;
-            const bool unit = (jf & ODB_JF_FAST_L) != 0, ramp = (jf & ODB_JF_RAMP) != 0;
+            const bool unit = (jf & ODB_JF_FAST_L) != 0, ramp = (jf & ODB_JF_RAMP) != 0, cycle = (jf & ODB_JF_CYCLE) != 0;
             const float g = job->g, gprev = job->gprev, gnext = job->gnext, gstep = job->gstep;
             float gprog = job->gprog;
             float offset = job->off0;
+            unsigned long long cbase = (unsigned long long)(base < 0 ? 0 : base);  // Cycle: `base`, reset to 0 by a wrap
             for (int i = 0; i < ODB_MIXER_CHUNK; i++) {
                 float v = 0.0f;
-                if (i < n) {
+                if (i < n && cycle) {                              // cycle.rs:30-51
+                    const unsigned long long ulen = (unsigned long long)len;
+                    const unsigned long long tr = (unsigned long long)offset;
+                    const float fract = offset - (float)tr;
+                    unsigned long long x = cbase + tr;
+                    if (x >= ulen) {                               // :38-47 (fract is the one computed before the wrap)
+                        cbase = 0;
+                        offset = (float)(x % ulen) + fract;
+                        x = (unsigned long long)offset;
+                    }
+                    const float a = pcm[x * CH + lane];
+                    const float b = x < ulen - 1 ? pcm[(x + 1) * CH + lane] : pcm[lane];   // :34-37 / :42-46 wrap to frames[0]
+                    v = a + fract * (b - a);                       // frame.rs:39-41
+                    offset = offset + ds;                          // :50
+                    v = v * fg;                                    // gain.rs:35
+                    if (ramp) {                                    // gain.rs:118-121
+                        v = v * (gprev + gprog * (gnext - gprev));
+                        gprog = fminf(gprog + gstep, 1.0f);
+                    } else {
+                        v = v * g;
+                    }
+                } else if (i < n) {
                     long long k;
                     float fract;
                     if (unit) {                                    // frames.rs:183-187

@@ -136,6 +136,15 @@ int odb_make_source(odb_ctx* ctx, const odb_chain* chain, int want_channels, Odb
     if (chain->flags & ODB_CHAIN_SPEED) s.flags |= ODB_SF_SPEED;
     if (chain->flags & ODB_CHAIN_FIXED_GAIN) s.flags |= ODB_SF_FIXED_GAIN;
     if (chain->flags & ODB_CHAIN_GAIN) s.flags |= ODB_SF_GAIN;
+    if (chain->flags & ODB_CHAIN_CYCLE) {                         // Cycle::new (cycle.rs:15-20) + earlier seeks
+        if (!(chain->start_seconds >= 0.0 && chain->start_seconds < (double)rec->n_frames)) {
+            ctx->frames_unref(chain->frames);
+            return odb_fail(ODB_E_INVALID, "Cycle cursor %g outside [0, %llu)", chain->start_seconds, (unsigned long long)rec->n_frames);
+        }
+        s.flags |= ODB_SF_CYCLE;
+        s.t_end = 1.0 / 0.0;                                      // Signal::is_finished default: never (signal.rs:25-27)
+        s.sample_t = 0;
+    }
     *out = s;
     return ODB_OK;
 }
@@ -147,6 +156,8 @@ extern "C" int odb_scene_play(odb_scene* scene, const odb_chain* chain, const fl
     if (!chain || !position || !velocity || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
     if (chain->flags & (ODB_CHAIN_SPEED | ODB_CHAIN_GAIN))
         return odb_fail(ODB_E_UNSUPPORTED, "SpatialSceneControl::play requires Seek; Speed and Gain do not implement it (use play_buffered)");
+    if (chain->flags & ODB_CHAIN_CYCLE)
+        return odb_fail(ODB_E_UNSUPPORTED, "device path: Cycle plays under a Mixer only");
     OdbSource s;
     FramesRec rec;
     ODB_TRY(odb_make_source(scene->ctx, chain, 1, &s, &rec));
@@ -174,6 +185,7 @@ extern "C" int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain,
     ODB_TRY(scene_check(scene));
     if (!chain || !position || !velocity || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
     if (rate == 0) return odb_fail(ODB_E_INVALID, "rate must be nonzero");
+    if (chain->flags & ODB_CHAIN_CYCLE) return odb_fail(ODB_E_UNSUPPORTED, "device path: Cycle plays under a Mixer only");
     odb_ctx* ctx = scene->ctx;
     OdbSource s;
     FramesRec rec;

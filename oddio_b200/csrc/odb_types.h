@@ -18,6 +18,7 @@
 #define ODB_SF_SPEED 0x40u           // chain has Speed
 #define ODB_SF_GAIN 0x80u            // chain has Gain
 #define ODB_SF_STOP_REQ 0x100u       // Mixed::stop() requested from the control side
+#define ODB_SF_CYCLE 0x200u          // the innermost signal is Cycle (cycle.rs:6-61): `t` is its cursor in SAMPLES
 
 // One playing source: SpatialSignal<FramesSignal chain> (spatial.rs:60-63) or MixedSignal (mixer.rs:46-49).
 // 160 bytes, 16-byte aligned; an array of these lives in HBM, indexed by slot.
@@ -129,6 +130,7 @@ struct __attribute__((aligned(16))) OdbRingWrite {
 #define ODB_JF_RAMP1 0x40u      // ring write: Gain is mid-transition during the second span
 #define ODB_JF_RESAMPLE 0x80u   // mixer: a resampling chain the staged resampling kernel takes (never together with GENERAL)
 #define ODB_JF_RING 0x100u      // the job belongs to a buffered source: pcm is its delay ring, flagged ones go to k_mix_ring
+#define ODB_JF_CYCLE 0x200u      // mixer: the innermost signal is Cycle; base/off0 are its cursor split at the chunk start (always GENERAL)
 #define ODB_JF_GENERAL 0x10u    // must take the general kernel (window too large, ds <= 0, negative offset, ...)
 
 // Device counters written by the walk kernels each callback (uint32 each).
