@@ -89,7 +89,8 @@ int odb_frames_release(odb_ctx* ctx, odb_frames frames);
 #define ODB_CHAIN_GAIN 0x4u
 #define ODB_CHAIN_CYCLE 0x8u /* the innermost signal is Cycle<T> (cycle.rs:6-61) instead of FramesSignal<T>: `start_seconds`
                               * then holds the initial cursor in SAMPLES (0 after Cycle::new; whatever Seek::seek calls made
-                              * before play left, cycle.rs:57-60). Mixer only: odb_scene_play* answer ODB_E_UNSUPPORTED. */
+                              * before play left, cycle.rs:57-60). Plays under odb_mixer_play and odb_scene_play (Cycle is Seek); odb_scene_play_buffered
+                              * answers ODB_E_UNSUPPORTED. Cycle sources take the literal kernels. */
 typedef struct odb_chain {
     odb_frames frames;     /* the Arc<Frames<T>> played */
     double start_seconds;  /* FramesSignal::new start_seconds, may be negative */

@@ -156,8 +156,6 @@ extern "C" int odb_scene_play(odb_scene* scene, const odb_chain* chain, const fl
     if (!chain || !position || !velocity || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
     if (chain->flags & (ODB_CHAIN_SPEED | ODB_CHAIN_GAIN))
         return odb_fail(ODB_E_UNSUPPORTED, "SpatialSceneControl::play requires Seek; Speed and Gain do not implement it (use play_buffered)");
-    if (chain->flags & ODB_CHAIN_CYCLE)
-        return odb_fail(ODB_E_UNSUPPORTED, "device path: Cycle plays under a Mixer only");
     OdbSource s;
     FramesRec rec;
     ODB_TRY(odb_make_source(scene->ctx, chain, 1, &s, &rec));

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     const float dt = eff / nf;                                          // :452
     const float d_gain = (nx.gain - ps.gain) / nf;                      // :453
     const float ds = dt * ratef;                                        // frames.rs:178
-    const bool fast = fabsf(ds - 1.0f) <= ODB_F32_EPSILON;              // frames.rs:180
+    const bool cycle = (s.flags & ODB_SF_CYCLE) != 0;                   // the inner signal is Cycle, not FramesSignal
+    const bool fast = !cycle && fabsf(ds - 1.0f) <= ODB_F32_EPSILON;    // frames.rs:180
     const bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
     // the left ear's scalars, needed by the right ear's threads to replay the cursor up to their own start
     const unsigned full = 0xffffffffu;
@@ -102,6 +103,54 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
     const float ps_off_l = __shfl_sync(full, ps.offset, src_lane0);
     const float eff_l = __shfl_sync(full, eff, src_lane0);
     const float dt_l = __shfl_sync(full, dt, src_lane0);
+    // Cycle (cycle.rs:26-61): `t` is the cursor in samples, and where a chunk starts depends on the f32 chain of the
+    // one before it (and on where it wrapped), so the chains are walked here once without the taps; the literal mix
+    // kernel walks each chunk again from the recorded (base, offset) with them. The right ear's thread replays the
+    // left ear's pass first - the reference runs the ears one after the other on the same cursor (spatial.rs:446-466).
+    double cyc_cursor = s.t;
+    if (cycle && mixing) {
+        const double dlen = (double)s.len;
+        const unsigned long long ulen = (unsigned long long)s.len;
+        auto cyc_seek = [&](double cur, float seconds) {                // cycle.rs:57-60
+            const double r = fmod(cur + (double)seconds * rate, dlen);
+            return r < 0.0 ? r + dlen : r;                              // f64::rem_euclid
+        };
+        auto cyc_pass = [&](double cur, float dt_e, bool record) {
+            const float ds_e = dt_e * ratef;                            // cycle.rs:27
+            for (int cg = 0; cg < n_chunks; cg++) {
+                const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
+                unsigned long long cbase = (unsigned long long)cur;    // :28
+                float offset = (float)(cur - (double)cbase);            // :29
+                if (record && emit && cg / ODB_TILE_CHUNKS < nt) {
+                    OdbJob* j = jobs + (size_t)(cg / ODB_TILE_CHUNKS) * ns + idx;
+                    j->base[e][cg % ODB_TILE_CHUNKS] = (int)cbase;
+                    j->off0[e][cg % ODB_TILE_CHUNKS] = offset;
+                }
+                for (int i = 0; i < m; i++) {
+                    const unsigned long long tr = (unsigned long long)offset;              // :31
+                    const float fract = offset - (float)tr;                                // :32
+                    const unsigned long long x = cbase + tr;                               // :33
+                    if (x >= ulen) { cbase = 0; offset = (float)(x % ulen) + fract; }      // :38-40
+                    offset = offset + ds_e;                                                // :50
+                }
+                cur = (double)cbase + (double)offset;                                      // :52
+            }
+            return cur;
+        };
+        double cur = s.t;
+        if (e == 1) {
+            cur = cyc_seek(cur, ps_off_l);                              // spatial.rs:449 (left ear)
+            cur = cyc_pass(cur, dt_l, false);
+            cur = cyc_seek(cur, -eff_l - ps_off_l);                     // :465
+        }
+        cur = cyc_seek(cur, ps.offset);                                 // :449
+        cur = cyc_pass(cur, dt, true);
+        if (e == 1) {
+            cur = cyc_seek(cur, -eff - ps.offset);                      // :465
+            cur = cyc_seek(cur, elapsed);                               // :468
+        }
+        cyc_cursor = cur;
+    }
     // cursor at the start of this thread's ear
     double t = s.t;
     if (e == 1) {  // left ear first: seek(prev.offset), all chunks, seek(-eff - prev.offset)  (:449-465)
@@ -135,7 +184,8 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
                 const float off0 = (float)(s0 - (double)base);          // frames.rs:183 / :189
                 bool g = general || off0 < 0.0f;                        // negative-fract quirk
                 if (base > (1 << 29) || base < -(1 << 29)) { g = true; base = base > 0 ? (1 << 30) : -(1 << 30); }
-                if (emit) {
+                if (cycle) g = true;                                    // Cycle sources always take the literal kernel
+                if (emit && !cycle) {
                     OdbJob* j = jobs + (size_t)tl * ns + idx;
                     j->base[e][c] = base;
                     j->off0[e][c] = off0;
@@ -177,6 +227,7 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
 #pragma unroll
         for (int x = 1; x < TPS; x <<= 1) f |= __shfl_xor_sync(full, f, x);
         if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
+        if (cycle) f |= ODB_JF_CYCLE | ODB_JF_GENERAL;
         if (cb.force_general) f |= ODB_JF_GENERAL;
         if (emit) {
             OdbJob* j = jobs + (size_t)tl * ns + idx;
@@ -192,7 +243,9 @@ __global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, 
             }
         }
     }
-    if (emit && sub == CS) {  // (right ear, group 0): finish the cursor, :465-468
+    if (emit && sub == CS && cycle) {
+        sp->t = cyc_cursor;
+    } else if (emit && sub == CS) {  // (right ear, group 0): finish the cursor, :465-468
         double te = t;
         for (int cg = 0; cg < n_chunks; cg++) {
             const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
@@ -244,7 +297,33 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
         if (jf & (ODB_JF_SKIP | ODB_JF_RING)) continue;  // flagged buffered-source jobs belong to k_mix_ring
         if (only_flagged && !(jf & ODB_JF_GENERAL)) continue;
         const int nfr = job->n_frames;
-        if (lane < 2 * ODB_TILE_CHUNKS) {
+        const bool cycle = (jf & ODB_JF_CYCLE) != 0;
+        if (cycle && lane < 2 * ODB_TILE_CHUNKS) {  // Cycle::sample, cycle.rs:26-53: the chain lanes also take the (wrapping) taps
+            const int e = lane & 1, c = lane >> 1;
+            const int m = min(ODB_SPATIAL_CHUNK, nfr - c * ODB_SPATIAL_CHUNK);
+            if (m > 0) {
+                const float* __restrict__ x0 = job->pcm;
+                const unsigned long long ulen = (unsigned long long)job->len;
+                const float ds = job->ds[e];
+                unsigned long long cbase = (unsigned long long)job->base[e][c];
+                float offset = job->off0[e][c];
+                float* dst = tile + e * ODB_TILE_FRAMES + c * ODB_SPATIAL_CHUNK;
+                for (int k = 0; k < m; k++) {
+                    const unsigned long long tr = (unsigned long long)offset;              // :31
+                    const float fract = offset - (float)tr;                                // :32 (kept across a wrap)
+                    unsigned long long x = cbase + tr;                                     // :33
+                    if (x >= ulen) {                                                       // :38-41
+                        cbase = 0;
+                        offset = (float)(x % ulen) + fract;
+                        x = (unsigned long long)offset;
+                    }
+                    const float a = x0[x];
+                    const float b = x < ulen - 1 ? x0[x + 1] : x0[0];                      // :34-37 / :42-46
+                    dst[k] = a + fract * (b - a);                                          // frame.rs:39-41
+                    offset = offset + ds;                                                  // :50
+                }
+            }
+        } else if (lane < 2 * ODB_TILE_CHUNKS) {
             const int e = lane & 1, c = lane >> 1;
             const bool unit = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
             if (!unit) {
@@ -272,17 +351,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_mix_general(const OdbJob* __rest
                 const int k = 32 * (j & 7) + lane, i = 32 * j + lane;
                 if (i < nfr) {
                     const long long base = job->base[e][c];
-                    float a, b, fract;
-                    if (unit) {                                            // frames.rs:183-187
-                        get_pair_mono(pcm, len, base + k, a, b);
-                        fract = job->off0[e][c];
-                    } else {                                               // frames.rs:191-193
-                        const float offset = tile[e * ODB_TILE_FRAMES + i];
-                        const long long tr = (long long)offset;
-                        get_pair_mono(pcm, len, base + tr, a, b);
-                        fract = offset - (float)tr;
+                    float smp;
+                    if (cycle) {
+                        smp = tile[e * ODB_TILE_FRAMES + i];               // lerped by the chain lane above
+                    } else {
+                        float a, b, fract;
+                        if (unit) {                                        // frames.rs:183-187
+                            get_pair_mono(pcm, len, base + k, a, b);
+                            fract = job->off0[e][c];
+                        } else {                                           // frames.rs:191-193
+                            const float offset = tile[e * ODB_TILE_FRAMES + i];
+                            const long long tr = (long long)offset;
+                            get_pair_mono(pcm, len, base + tr, a, b);
+                            fract = offset - (float)tr;
+                        }
+                        smp = a + fract * (b - a);                         // frame.rs:39-41
                     }
-                    float smp = a + fract * (b - a);                       // frame.rs:39-41
                     if (has_fg) smp = smp * fg;                            // gain.rs:35
                     const float gain = pg + (float)(tl * ODB_TILE_FRAMES + i) * dg;  // spatial.rs:459
                     const float contrib = smp * gain;                      // spatial.rs:460

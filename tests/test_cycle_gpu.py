@@ -117,8 +117,52 @@ def test_cycles_under_wrappers_match_the_oracle(oracle, odb, ctx, channels):
     assert len(dev) == len(ref) == 28                          # a Cycle never finishes
 
 
-def test_cycle_is_rejected_by_the_spatial_scene(odb, ctx):
+def test_cycles_in_a_spatial_scene_match_the_oracle(oracle, odb, ctx):
+    """SpatialSceneControl::play(Cycle) (Cycle is Seek, cycle.rs:56-61): looping point sources, moving and static,
+    bare and under FixedGain, next to ordinary FramesSignal sources; the seeks of the mix closure (spatial.rs:449,
+    :465, :468) go through Cycle's rem_euclid. One looping source alone is bit-exact; cursors always are."""
+    from helpers import assert_mix_close, rand_in_shell
+
+    o = oracle
+    rng = np.random.default_rng(77)
+    rate = 48000
+    ref, (ctl, dev) = o.SpatialScene(), odb.SpatialScene.new(ctx)
+    ref1, (ctl1, dev1) = o.SpatialScene(), odb.SpatialScene.new(ctx)
+    pcms = [synth_pcm(rng, int(n), rate) for n in (211, 1999, 4801, 24000)]
+    long_pcm = synth_pcm(rng, 60000, rate)
+    cursors = []
+    for i in range(20):
+        p = pcms[i % 4]
+        fo, fd = o.Frames.from_slice(rate, p), odb.Frames.from_slice(rate, p, ctx)
+        so, sd = o.Cycle(fo), odb.Cycle(fd)
+        cursors.append((so, sd))
+        io, idv = (o.FixedGain(so, -3.0), odb.FixedGain(sd, -3.0)) if i % 4 == 3 else (so, sd)
+        pos = rand_in_shell(rng, 2.0, 60.0)
+        vel = rng.uniform(-30, 30, 3).astype(F32) if i % 2 else np.zeros(3, F32)
+        ref.play(io, pos, vel, 0.1); ctl.play(idv, odb.SpatialOptions(pos, vel, 0.1))
+    for _ in range(6):
+        fo, fd = o.Frames.from_slice(rate, long_pcm), odb.Frames.from_slice(rate, long_pcm, ctx)
+        pos, vel = rand_in_shell(rng, 2.0, 60.0), rng.uniform(-30, 30, 3).astype(F32)
+        ref.play(o.FramesSignal(fo, 1.0), pos, vel, 0.1); ctl.play(odb.FramesSignal(fd, 1.0), odb.SpatialOptions(pos, vel, 0.1))
+    fo, fd = o.Frames.from_slice(rate, pcms[1]), odb.Frames.from_slice(rate, pcms[1], ctx)
+    one_o, one_d = o.Cycle(fo), odb.Cycle(fd)
+    ref1.play(one_o, [3.0, 1.0, -2.0], [10.0, -3.0, 4.0], 0.1)
+    ctl1.play(one_d, odb.SpatialOptions([3.0, 1.0, -2.0], [10.0, -3.0, 4.0], 0.1))
+    for n in (256, 1024, 1500, 33, 4096):
+        r = o.run(ref, rate, n)
+        out = odb.run(dev, rate, np.zeros((n, 2), F32))
+        assert_mix_close(out, r, ref.out64(n))
+        np.testing.assert_array_equal(odb.run(dev1, rate, np.zeros((n, 2), F32)), o.run(ref1, rate, n))
+        for so, sd in cursors:
+            assert sd.control.cursor()[0] == so.cursor
+        assert one_d.control.cursor()[0] == one_o.cursor
+    assert dev.len() == ref.len() == 26
+    cnt = dev.last_job_counters()
+    assert cnt["general"] == 20 * 4 and cnt["staged"] == 6 * 4   # 4096 frames = 4 tiles: loops literal, the rest staged
+
+
+def test_cycle_is_rejected_by_play_buffered(odb, ctx):
     fr = odb.Frames.from_slice(48000, np.zeros(100, F32), ctx)
     ctl, scene = odb.SpatialScene.new(ctx)
     with pytest.raises(odb.OddioError):
-        ctl.play(odb.Cycle(fr), odb.SpatialOptions([1.0, 0.0, 0.0], [0.0, 0.0, 0.0], 0.1))
+        ctl.play_buffered(odb.Cycle(fr), odb.SpatialOptions([1.0, 0.0, 0.0], [0.0, 0.0, 0.0], 0.1), 100.0, 48000, 0.1)
