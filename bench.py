@@ -96,17 +96,26 @@ def pcm_len(frames: int, callbacks: int) -> int:
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons of this rank's GPU while the timed region runs: an `nvidia-smi -lms 100` child
+    started before the region (rank 0 only: NVML queries take driver locks, and one poller per rank on an 8-GPU box
+    measurably slows the launches of all of them). The timed region of the default run is a few milliseconds, so
+    the poller may not land a sample inside it on a box where nvidia-smi starts slowly; `after()` then takes
+    readings through NVML right after the region's closing synchronisation (reported as "sampled": "after")."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+    def __init__(self, device: int, enabled: bool = True):
+        self.device, self.rows, self.proc, self.enabled, self.how = device, [], None, enabled, "during"
+        self.all_rows, self.t0, self.t1 = [], None, None
 
-    def __enter__(self):
+    def start(self):
+        """Starts the poller. Called long before the timed region: nvidia-smi needs a noticeable fraction of a second
+        to initialise on a multi-GPU box and holds driver locks while it does, which must not overlap the region."""
+        if not self.enabled:
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self._smi_id()}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -115,18 +124,61 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _smi_id(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",")]
+            if self.device < len(ids):
+                return ids[self.device]
+        return str(self.device)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.all_rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def __exit__(self, *a):
+    def __enter__(self):  # the timed region starts
+        self.t0 = time.time()
+        return self
+
+    def __exit__(self, *a):  # ... and has ended (after its closing synchronisation)
+        self.t1 = time.time()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.12)  # one more polling period: the reading that covers the end of the region
+            self.rows = [r for t, r in self.all_rows if self.t0 - 0.02 <= t <= self.t1 + 0.12]
+        self.after()
+
+    def stop(self):
+        if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
+
+    def after(self):
+        """No sample landed inside the region: read the clocks now (the device has just finished it)."""
+        if not self.enabled or self.rows:
+            return
+        try:
+            import pynvml as p
+
+            p.nvmlInit()
+            sid = self._smi_id()
+            h = p.nvmlDeviceGetHandleByIndex(int(sid)) if sid.isdigit() else p.nvmlDeviceGetHandleByUUID(sid.encode())
+            mx = p.nvmlDeviceGetMaxClockInfo(h, p.NVML_CLOCK_SM)
+            bits = (getattr(p, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(p, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    getattr(p, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(p, "nvmlClocksEventReasonSwPowerCap", 0x4))
+            for _ in range(2):
+                sm = p.nvmlDeviceGetClockInfo(h, p.NVML_CLOCK_SM)
+                try:
+                    r = p.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = p.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b in bits])
+            self.how = "after"
+        except Exception:
+            pass
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
@@ -139,7 +191,7 @@ class ClockSampler:
                         reasons.add(name)
         busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": self.how}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -162,6 +214,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     ctx = odb.Context(local, stream=stream.cuda_stream)  # our kernels and NCCL share one stream: no extra events
+    clk = ClockSampler(local, enabled=(rank == 0)).start()  # initialises during the set-up below, far from the timed region
 
     from oddio_b200.sharding import shard_sources
 
@@ -206,23 +259,36 @@ def run_ours(args):
     # torch.distributed all-reduce. Either way R tiles per exchange (--reduce-every; 1 = the live-playback shape).
     peer = world > 1 and args.exchange == "peer"
     R = 1 if world == 1 else max(1, args.reduce_every)
-    groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(2)]
+    # NG group buffers in flight: a rank may run up to NG - 1 exchanges ahead of the slowest one, which absorbs the
+    # host-side jitter of the other ranks instead of paying max-over-ranks at every exchange
+    NG = max(2, min(8, args.exchange_depth)) if world > 1 else 2
+    groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(NG)]
     comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     exch = None
     if peer:
         from oddio_b200.sharding import PeerExchange
 
-        exch = PeerExchange.from_torch(ctx, R * M * 2)
+        exch = PeerExchange.from_torch(ctx, R * M * 2, depth=NG)
+
+    pending = [False] * NG  # peer exchange: group g has been pushed and not yet pulled
 
     def exchange(g):
-        """Sum of group g over the ranks, on the `comm` stream."""
+        """Sum of group g over the ranks, started on the `comm` stream. Peer exchange: only the push half (it never
+        waits for another rank); the pull half is queued one group later, right before group g's buffer is reused,
+        when every rank has long pushed - a pipelined renderer consumes the summed tiles one group late."""
         if peer:
-            exch.allreduce(groups[g].data_ptr(), R * M * 2, 0, comm.cuda_stream)
+            exch.push(groups[g].data_ptr(), R * M * 2, comm.cuda_stream)
+            pending[g] = True
         else:
             with torch.cuda.stream(comm):
                 dist.all_reduce(groups[g])
-    mixed = [torch.cuda.Event() for _ in range(2)]
-    reduced = [torch.cuda.Event() for _ in range(2)]
+
+    def finish_exchange(g):
+        if peer and pending[g]:
+            exch.pull(groups[g].data_ptr(), R * M * 2, 0, stream.cuda_stream)
+            pending[g] = False
+    mixed = [torch.cuda.Event() for _ in range(NG)]
+    reduced = [torch.cuda.Event() for _ in range(NG)]
     step_no = [0]
 
     def step_device(scene):
@@ -230,9 +296,10 @@ def run_ours(args):
         the NCCL sum of the group runs on `comm` and overlaps the next group's mixes."""
         k = step_no[0]
         step_no[0] += 1
-        g, slot = (k // R) % 2, k % R
+        g, slot = (k // R) % NG, k % R
         if world > 1 and slot == 0:
-            stream.wait_event(reduced[g])  # the group buffer is free again once its previous all-reduce is done
+            stream.wait_event(reduced[g])  # the group buffer is free again once its previous exchange has left
+            finish_exchange(g)             # (peer exchange: the sum of the group's previous contents lands here)
         scene.sample_device(interval, groups[g][slot].data_ptr(), M)
         if world > 1 and slot == R - 1:
             mixed[g].record(stream)
@@ -244,13 +311,15 @@ def run_ours(args):
         if world > 1:
             k = step_no[0]
             if k % R:  # flush a partial group
-                g = (k // R) % 2
+                g = (k // R) % NG
                 mixed[g].record(stream)
                 comm.wait_event(mixed[g])
                 exchange(g)
                 reduced[g].record(comm)
                 step_no[0] += R - k % R
             stream.wait_stream(comm)
+            for i in range(NG):  # oldest first: pulls follow push order
+                finish_exchange((step_no[0] // R + i) % NG)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -265,10 +334,21 @@ def run_ours(args):
         for _ in range(W):
             step_device(scene)
         drain()
+        if world > 1:  # both buffers / inbox parities of the exchange have been through it once before the clock starts
+            first = (step_no[0] // R) % NG  # keep the rotation: the timed loop continues with this group
+            for i in range(NG):
+                g = (first + i) % NG
+                mixed[g].record(stream)
+                comm.wait_event(mixed[g])
+                exchange(g)
+                reduced[g].record(comm)
+            stream.wait_stream(comm)
+            for i in range(NG):
+                finish_exchange((first + i) % NG)
         launches_per_step = scene.last_launch_count() + (1 if world > 1 else 0)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
+        with clk:
             e0.record(stream)
             h0 = time.perf_counter()
             for _ in range(K):
@@ -282,7 +362,8 @@ def run_ours(args):
         # the rare source with exactly one ear on FramesSignal's ds ~= 1 path takes the literal kernel
         assert counters["general"] <= max(1, n_local // 1000), f"{counters['general']} jobs fell back to the general kernel"
         assert scene.len() == n_local, "a source finished during the timed region"
-        checksum = float(groups[((step_no[0] - 1) // R) % 2][(step_no[0] - 1) % R].abs().sum().item())
+        checksum = float(groups[((step_no[0] - 1) // R) % NG][(step_no[0] - 1) % R].abs().sum().item())
+        clk.stop()
         scene.close()
 
         # ---- (2) mix-kernel device time for the roofline (separate pass: events around the kernel) ------------
@@ -477,6 +558,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --sources per GPU (default), strong = --sources in total")
     ap.add_argument("--reduce-every", type=int, default=8, help="N > 1: callbacks per exchange of the tiles (1 = live playback)")
+    ap.add_argument("--exchange-depth", type=int, default=4, help="N > 1: group buffers (exchanges) in flight, 2..8")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-GPU tiles are summed (peer = the library's NVLink peer-memory kernel, every callback)")
     ap.add_argument("--variant", type=int, default=2, choices=[0, 2],

@@ -203,7 +203,8 @@ int odb_set_kernel_variant(void* owner, int variant);
  * tile into every rank's inbox with stores over NVLink and sums the inbox in rank order (bit-identical result
  * on all ranks), in one kernel per callback. Set-up: create on every rank, export the 64-byte handle, gather
  * the handles of all ranks by any host-side means (rank order), connect. */
-int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t max_floats, odb_exchange** out);
+/* `depth` (2..8): how many pushed exchanges may await their pull (inbox slots per rank). */
+int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t max_floats, int depth, odb_exchange** out);
 int odb_exchange_destroy(odb_exchange* ex);
 /* Bytes of one exported handle (a cudaIpcMemHandle_t). */
 int odb_exchange_handle_size(void);
@@ -215,6 +216,12 @@ int odb_exchange_connect(odb_exchange* ex, const void* handles);
  * `cuda_stream` (NULL = the context's stream). Every rank must call it once per callback, in the same order.
  * The shards' own scenes/mixers run with ODB_EPILOGUE_NONE. */
 int odb_exchange_allreduce(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream);
+/* The two halves of odb_exchange_allreduce for a pipelined renderer: push sends this rank's tile to every rank's
+ * inbox and never waits for a peer's data; pull (same n_floats, in push order, at most `depth` pushes outstanding)
+ * leaves the sum over the ranks in `dev_tile` (which need not be the pushed buffer). Queuing the pull one callback
+ * group later keeps every rank's GPU busy with the next mixes instead of waiting for the slowest rank. */
+int odb_exchange_push(odb_exchange* ex, const void* dev_tile, uint32_t n_floats, void* cuda_stream);
+int odb_exchange_pull(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream);
 
 #ifdef __cplusplus
 }

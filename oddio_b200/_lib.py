@@ -100,11 +100,13 @@ SIGNATURES = {
     "odb_frames_from_i16": [vp, u32, i32, C.POINTER(C.c_int16), u64, i32, pu64],
     "odb_scene_sample_i16": [vp, f32, C.POINTER(C.c_int16), u32],
     "odb_mixer_sample_i16": [vp, f32, C.POINTER(C.c_int16), u32],
-    "odb_exchange_create": [vp, i32, i32, u32, pvp],
+    "odb_exchange_create": [vp, i32, i32, u32, i32, pvp],
     "odb_exchange_destroy": [vp],
     "odb_exchange_export": [vp, vp],
     "odb_exchange_connect": [vp, vp],
     "odb_exchange_allreduce": [vp, vp, u32, i32, vp],
+    "odb_exchange_push": [vp, vp, u32, vp],
+    "odb_exchange_pull": [vp, vp, u32, i32, vp],
 }
 NON_STATUS = {"odb_last_error": (C.c_char_p, []), "odb_abi_version": (C.c_uint32, []),
               "odb_exchange_handle_size": (C.c_int, [])}

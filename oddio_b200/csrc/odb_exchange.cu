@@ -2,25 +2,29 @@
 // of one box, the only exchange is the additive 8 KiB output tile). The reference is single-process and has no
 // counterpart; `Tanh`/`Reinhard` (tanh.rs:22-29, reinhard.rs:28-35) are applied here because they act on the SUM.
 //
-// One process per GPU. Every rank owns an inbox in its own HBM: [2 parities][world][cap] floats plus
-// [2][world][slices] sequence flags, exported to the other ranks of the box as a CUDA IPC handle and mapped by them.
-// One kernel per exchange and rank, one CTA per 2048-float slice of the tile (a 1024-frame stereo callback is one
-// slice; offline rendering exchanges several callbacks at once), no NCCL on the data path. Per slice:
-//   1. push: the rank stores its partial tile into slot `rank` of every rank's inbox (plain stores over NVLink;
-//      its own inbox included), fences to system scope and then publishes the callback's sequence number in the
-//      same slot's flag with a release store;
-//   2. pull: it waits until its own inbox holds this callback's flag from every rank (acquire loads of local
-//      memory), sums the `world` tiles in rank order - every rank adds the same numbers in the same order, so all
-//      ranks end up with bit-identical tiles - and applies the epilogue.
-// Inbox slots alternate with the parity of the sequence number: a rank can only reach callback k+2 after every
-// peer has pushed k+1, i.e. after every peer has finished pulling k (kernels of one rank run in stream order), so
-// two parities suffice and nobody overwrites a tile that is still being read.
+// One process per GPU. Every rank owns an inbox in its own HBM: [depth][world][cap] floats,
+// [depth][world][slices] "pushed" flags and [world][slices] "pulled" acknowledgements, exported to the other ranks of the
+// box as a CUDA IPC handle and mapped by them. No NCCL on the data path; two small kernels per exchange and rank, one
+// CTA per 2048-float slice of the tile (a 1024-frame stereo callback is one slice; offline rendering exchanges several
+// callbacks at once):
+//   push: the rank stores its partial tile into slot `rank` of every rank's inbox (plain stores over NVLink; its own
+//      inbox included), fences to system scope and then publishes the exchange's sequence number in the same slot's
+//      flag with a release store. It never waits for a peer's data, so it can be queued right behind the mix and does
+//      not hold an SM while other ranks are still mixing;
+//   pull: waits until its own inbox holds this exchange's flag from every rank (acquire loads of local memory), sums
+//      the `world` tiles in rank order - every rank adds the same numbers in the same order, so all ranks end up with
+//      bit-identical tiles - applies the epilogue, and acknowledges the sequence number in every peer's inbox.
+// Inbox slots rotate with the sequence number modulo `depth` (2..8 exchanges in flight); before a push overwrites a
+// peer's slot of `depth` exchanges ago it checks that peer's acknowledgement of that exchange (practically never a wait). A caller that
+// wants the sum at once queues pull right behind push (odb_exchange_allreduce); a pipelined renderer queues the pull
+// one group of callbacks later, when every peer has long pushed, and nobody spins (bench.py).
 #include <cuda_runtime.h>
 
 #include "odb_host.h"
 
 #define ODB_KIND_EXCHANGE 0x58434847u
 #define ODB_MAX_RANKS 16
+#define ODB_MAX_DEPTH 8
 
 namespace odbk {
 
@@ -39,41 +43,68 @@ struct ExchangePeers {
 
 #define ODB_EXCHANGE_SLICE 2048  // floats per CTA
 
-__global__ void __launch_bounds__(512) k_exchange_tiles(float* __restrict__ tile_all, int n_floats_all, ExchangePeers peers,
-                                                         int rank, int world, uint32_t cap, size_t flags_off, int max_slices,
-                                                         uint32_t seq, int epilogue) {
-    const uint32_t par = seq & 1u;
+struct ExchangeGeom {
+    int rank, world, max_slices, depth;
+    uint32_t cap;        // floats per inbox slot
+    size_t flags_off;    // byte offset of the pushed flags [depth][world][max_slices]
+    size_t acks_off;     // byte offset of the pulled acknowledgements [world][max_slices]
+};
+
+__global__ void __launch_bounds__(512) k_exchange_push(const float* __restrict__ tile_all, int n_floats_all, ExchangePeers peers,
+                                                        ExchangeGeom g, uint32_t seq) {
+    const uint32_t par = seq % (uint32_t)g.depth;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int first = blockIdx.x * ODB_EXCHANGE_SLICE;
     const int n_floats = min(ODB_EXCHANGE_SLICE, n_floats_all - first);
-    float* tile = tile_all + first;
-    // 1. push (16-byte stores; the tile and the slots are 16-byte aligned)
-    const size_t slot = ((size_t)par * world + rank) * cap + first;
+    const float* tile = tile_all + first;
+    // the slot about to be overwritten held exchange seq - depth: every peer must have pulled that one
+    if (tid < g.world && seq > (uint32_t)g.depth) {
+        const uint32_t* ack = reinterpret_cast<const uint32_t*>(peers.inbox[g.rank] + g.acks_off) + (size_t)tid * g.max_slices + blockIdx.x;
+        while ((int)(ld_acquire_sys(ack) - (seq - (uint32_t)g.depth)) < 0) __nanosleep(20);
+    }
+    __syncthreads();
+    // 16-byte stores; the tile and the slots are 16-byte aligned
+    const size_t slot = ((size_t)par * g.world + g.rank) * g.cap + first;
     const int n4 = n_floats >> 2;
-    for (int g = 0; g < world; g++) {
-        float* dst = reinterpret_cast<float*>(peers.inbox[g]) + slot;
+    for (int p = 0; p < g.world; p++) {
+        float* dst = reinterpret_cast<float*>(peers.inbox[p]) + slot;
         for (int i = tid; i < n4; i += nth) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(tile)[i];
         for (int i = 4 * n4 + tid; i < n_floats; i += nth) dst[i] = tile[i];
     }
     __threadfence_system();
     __syncthreads();
-    const size_t flag_idx = ((size_t)par * world) * max_slices + blockIdx.x;  // + rank * max_slices
-    if (tid < world)
-        st_release_sys(reinterpret_cast<uint32_t*>(peers.inbox[tid] + flags_off) + flag_idx + (size_t)rank * max_slices, seq);
-    // 2. pull
-    const char* mine = peers.inbox[rank];
-    if (tid < world) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + flag_idx + (size_t)tid * max_slices;
+    if (tid < g.world)
+        st_release_sys(reinterpret_cast<uint32_t*>(peers.inbox[tid] + g.flags_off) + ((size_t)par * g.world + g.rank) * g.max_slices + blockIdx.x, seq);
+}
+
+__global__ void __launch_bounds__(512) k_exchange_pull(float* __restrict__ tile_all, int n_floats_all, ExchangePeers peers,
+                                                        ExchangeGeom g, uint32_t seq, int epilogue) {
+    const uint32_t par = seq % (uint32_t)g.depth;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int first = blockIdx.x * ODB_EXCHANGE_SLICE;
+    const int n_floats = min(ODB_EXCHANGE_SLICE, n_floats_all - first);
+    float* tile = tile_all + first;
+    const char* mine = peers.inbox[g.rank];
+    if (tid < g.world) {
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + g.flags_off) + ((size_t)par * g.world + tid) * g.max_slices + blockIdx.x;
         while ((int)(ld_acquire_sys(flag) - seq) < 0) __nanosleep(20);
     }
     __syncthreads();
-    const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * world * cap + first;
+    const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * g.world * g.cap + first;
     for (int i = tid; i < n_floats; i += nth) {
         float sum = 0.0f;
-        for (int g = 0; g < world; g++) sum = sum + __ldcv(in + (size_t)g * cap + i);  // rank order: same sum on every rank
+        for (int p = 0; p < g.world; p++) sum = sum + __ldcv(in + (size_t)p * g.cap + i);  // rank order: same sum on every rank
         if (epilogue == 1) sum = tanhf(sum);
         else if (epilogue == 2) sum = sum / (1.0f + fabsf(sum));
         tile[i] = sum;
+    }
+    __syncthreads();  // every thread has read its share of the inbox: the peers may overwrite this slot `depth` exchanges on
+    if (tid < g.world) {
+        uint32_t* ack = reinterpret_cast<uint32_t*>(peers.inbox[tid] + g.acks_off) + (size_t)g.rank * g.max_slices;
+        st_release_sys(ack + blockIdx.x, seq);
+        // slices this exchange did not use are free as well (a later, larger exchange checks them)
+        if (blockIdx.x == 0)
+            for (int sl = (int)gridDim.x; sl < g.max_slices; sl++) st_release_sys(ack + sl, seq);
     }
 }
 
@@ -84,12 +115,15 @@ struct odb_exchange {
     odb_ctx* ctx = nullptr;
     int rank = 0, world = 1;
     uint32_t cap = 0;          // floats per slot
-    int max_slices = 1;
-    size_t flags_off = 0, bytes = 0;
+    int max_slices = 1, depth = 2;
+    size_t flags_off = 0, acks_off = 0, bytes = 0;
     char* local = nullptr;
     odbk::ExchangePeers peers;
     bool connected = false;
-    uint32_t seq = 0;
+    uint32_t seq = 0;          // exchanges pushed
+    uint32_t pulled = 0;       // exchanges pulled
+    uint32_t pushed_floats[ODB_MAX_DEPTH] = {0};
+    odbk::ExchangeGeom geom() const { return odbk::ExchangeGeom{rank, world, max_slices, depth, cap, flags_off, acks_off}; }
 };
 
 static int exchange_check(odb_exchange* ex) {
@@ -97,8 +131,9 @@ static int exchange_check(odb_exchange* ex) {
     return ODB_OK;
 }
 
-extern "C" int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t max_floats, odb_exchange** out) {
+extern "C" int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t max_floats, int depth, odb_exchange** out) {
     if (!ctx || !out) return odb_fail(ODB_E_INVALID, "NULL argument");
+    if (depth < 2 || depth > ODB_MAX_DEPTH) return odb_fail(ODB_E_INVALID, "depth %d: 2..%d exchanges in flight", depth, ODB_MAX_DEPTH);
     if (world < 1 || world > ODB_MAX_RANKS || rank < 0 || rank >= world)
         return odb_fail(ODB_E_INVALID, "rank %d of %d: at most %d ranks (the GPUs of one box)", rank, world, ODB_MAX_RANKS);
     if (max_floats == 0) return odb_fail(ODB_E_INVALID, "max_floats is 0");
@@ -107,10 +142,12 @@ extern "C" int odb_exchange_create(odb_ctx* ctx, int rank, int world, uint32_t m
     ex->ctx = ctx;
     ex->rank = rank;
     ex->world = world;
+    ex->depth = depth;
     ex->cap = (max_floats + 31u) & ~31u;  // slots stay 128-byte aligned
     ex->max_slices = (int)((ex->cap + ODB_EXCHANGE_SLICE - 1) / ODB_EXCHANGE_SLICE);
-    ex->flags_off = (size_t)2 * world * ex->cap * sizeof(float);
-    ex->bytes = ex->flags_off + (size_t)2 * world * ex->max_slices * sizeof(uint32_t);
+    ex->flags_off = (size_t)depth * world * ex->cap * sizeof(float);
+    ex->acks_off = ex->flags_off + (size_t)depth * world * ex->max_slices * sizeof(uint32_t);
+    ex->bytes = ex->acks_off + (size_t)world * ex->max_slices * sizeof(uint32_t);
     for (int g = 0; g < ODB_MAX_RANKS; g++) ex->peers.inbox[g] = nullptr;
     cudaError_t e = cudaMalloc((void**)&ex->local, ex->bytes);
     if (e != cudaSuccess) {
@@ -155,22 +192,50 @@ extern "C" int odb_exchange_connect(odb_exchange* ex, const void* handles) {
     return ODB_OK;
 }
 
-extern "C" int odb_exchange_allreduce(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream) {
+static int exchange_args(odb_exchange* ex, const void* dev_tile, uint32_t n_floats) {
     ODB_TRY(exchange_check(ex));
     if (!dev_tile && n_floats) return odb_fail(ODB_E_INVALID, "dev_tile is NULL");
     if (!ex->connected) return odb_fail(ODB_E_INVALID, "exchange is not connected to its peers yet");
-    if (n_floats > ex->cap) return odb_fail(ODB_E_INVALID, "%u floats exceed the exchange's capacity of %u", n_floats, ex->cap);
-    if (epilogue < 0 || epilogue > 2) return odb_fail(ODB_E_INVALID, "unknown epilogue %d", epilogue);
+    if (n_floats == 0 || n_floats > ex->cap) return odb_fail(ODB_E_INVALID, "%u floats: between 1 and the exchange's capacity of %u", n_floats, ex->cap);
     if (((uintptr_t)dev_tile & 15u) != 0) return odb_fail(ODB_E_INVALID, "dev_tile must be 16-byte aligned");
+    return ODB_OK;
+}
+
+extern "C" int odb_exchange_push(odb_exchange* ex, const void* dev_tile, uint32_t n_floats, void* cuda_stream) {
+    ODB_TRY(exchange_args(ex, dev_tile, n_floats));
+    if (ex->seq - ex->pulled >= (uint32_t)ex->depth)
+        return odb_fail(ODB_E_INVALID, "%d exchanges are already pushed and not pulled (the depth given at creation)", ex->depth);
     ODB_CUDA(cudaSetDevice(ex->ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->ctx->stream;
     ex->seq++;  // flags are compared as signed differences, so wrap-around is harmless
-    if (n_floats == 0) return ODB_OK;
+    ex->pushed_floats[ex->seq % (uint32_t)ex->depth] = n_floats;
     const int n_slices = (int)((n_floats + ODB_EXCHANGE_SLICE - 1) / ODB_EXCHANGE_SLICE);
-    odbk::k_exchange_tiles<<<n_slices, 512, 0, st>>>((float*)dev_tile, (int)n_floats, ex->peers, ex->rank, ex->world, ex->cap,
-                                                     ex->flags_off, ex->max_slices, ex->seq, epilogue);
+    odbk::k_exchange_push<<<n_slices, 512, 0, st>>>((const float*)dev_tile, (int)n_floats, ex->peers, ex->geom(), ex->seq);
     ODB_CUDA(cudaGetLastError());
     return ODB_OK;
+}
+
+extern "C" int odb_exchange_pull(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream) {
+    ODB_TRY(exchange_args(ex, dev_tile, n_floats));
+    if (epilogue < 0 || epilogue > 2) return odb_fail(ODB_E_INVALID, "unknown epilogue %d", epilogue);
+    if (ex->pulled == ex->seq) return odb_fail(ODB_E_INVALID, "nothing pushed that has not been pulled");
+    const uint32_t seq = ex->pulled + 1;
+    if (ex->pushed_floats[seq % (uint32_t)ex->depth] != n_floats)
+        return odb_fail(ODB_E_INVALID, "pull of %u floats does not match the push of %u", n_floats, ex->pushed_floats[seq % (uint32_t)ex->depth]);
+    ODB_CUDA(cudaSetDevice(ex->ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->ctx->stream;
+    ex->pulled = seq;
+    const int n_slices = (int)((n_floats + ODB_EXCHANGE_SLICE - 1) / ODB_EXCHANGE_SLICE);
+    odbk::k_exchange_pull<<<n_slices, 512, 0, st>>>((float*)dev_tile, (int)n_floats, ex->peers, ex->geom(), seq, epilogue);
+    ODB_CUDA(cudaGetLastError());
+    return ODB_OK;
+}
+
+extern "C" int odb_exchange_allreduce(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream) {
+    ODB_TRY(exchange_args(ex, dev_tile, n_floats));
+    if (ex->seq != ex->pulled) return odb_fail(ODB_E_INVALID, "a pushed exchange is still waiting for its pull");
+    ODB_TRY(odb_exchange_push(ex, dev_tile, n_floats, cuda_stream));
+    return odb_exchange_pull(ex, dev_tile, n_floats, epilogue, cuda_stream);
 }
 
 extern "C" int odb_exchange_destroy(odb_exchange* ex) {

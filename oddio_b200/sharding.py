@@ -32,13 +32,13 @@ class PeerExchange:
     `gather(handle: bytes) -> list[bytes]` returns every rank's handle in rank order; `from_torch` builds
     it from torch.distributed (any backend: the handles are host bytes)."""
 
-    def __init__(self, ctx, rank: int, world: int, max_floats: int, gather=None):
+    def __init__(self, ctx, rank: int, world: int, max_floats: int, gather=None, depth: int = 2):
         from . import _lib
 
         self._lib = _lib
         L = _lib.load()
         h = C.c_void_p()
-        _lib.check(L.odb_exchange_create(ctx._h, int(rank), int(world), int(max_floats), C.byref(h)))
+        _lib.check(L.odb_exchange_create(ctx._h, int(rank), int(world), int(max_floats), int(depth), C.byref(h)))
         self._h = h
         self.rank, self.world = rank, world
         if world > 1:
@@ -54,11 +54,11 @@ class PeerExchange:
             _lib.check(L.odb_exchange_connect(self._h, blob))
 
     @classmethod
-    def from_torch(cls, ctx, max_floats: int, group=None):
+    def from_torch(cls, ctx, max_floats: int, group=None, depth: int = 2):
         import torch.distributed as dist
 
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
-            return cls(ctx, 0, 1, max_floats)
+            return cls(ctx, 0, 1, max_floats, depth=depth)
         rank, world = dist.get_rank(group), dist.get_world_size(group)
 
         def gather(handle: bytes):
@@ -66,7 +66,7 @@ class PeerExchange:
             dist.all_gather_object(out, handle, group=group)
             return out
 
-        ex = cls(ctx, rank, world, max_floats, gather)
+        ex = cls(ctx, rank, world, max_floats, gather, depth)
         dist.barrier(group)  # every rank has mapped every inbox before the first push
         return ex
 
@@ -74,6 +74,16 @@ class PeerExchange:
         """In place on the device tile at `dev_ptr`; queued on `stream` (0 = the context's stream)."""
         self._lib.check(self._lib.load().odb_exchange_allreduce(self._h, C.c_void_p(dev_ptr), int(n_floats), int(epilogue),
                                                                 C.c_void_p(stream) if stream else None))
+
+    def push(self, dev_ptr: int, n_floats: int, stream: int = 0) -> None:
+        """First half of allreduce: sends this rank's tile to every rank; never waits for a peer's data."""
+        self._lib.check(self._lib.load().odb_exchange_push(self._h, C.c_void_p(dev_ptr), int(n_floats),
+                                                           C.c_void_p(stream) if stream else None))
+
+    def pull(self, dev_ptr: int, n_floats: int, epilogue: int = 0, stream: int = 0) -> None:
+        """Second half, in push order (at most `depth` pushes outstanding): the sum over the ranks lands in `dev_ptr`."""
+        self._lib.check(self._lib.load().odb_exchange_pull(self._h, C.c_void_p(dev_ptr), int(n_floats), int(epilogue),
+                                                           C.c_void_p(stream) if stream else None))
 
     def close(self) -> None:
         if self._h:

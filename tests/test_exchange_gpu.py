@@ -32,7 +32,7 @@ def test_single_rank_exchange_is_identity_plus_epilogue():
     from oddio_b200.sharding import PeerExchange
 
     ctx = odb.init(0)
-    ex = PeerExchange(ctx, 0, 1, 4096)
+    ex = PeerExchange(ctx, 0, 1, 4096, depth=2)
     rng = np.random.default_rng(3)
     for n in (2048, 514, 2, 4096, 3000):  # 16-byte multiples, tails, several slices
         x = rng.uniform(-2, 2, n).astype(np.float32)
@@ -68,7 +68,7 @@ def _worker(rank, world, port, n_src, n_frames, n_callbacks, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)  # set-up handles only
     ctx = odb.Context(rank)
-    ex = PeerExchange.from_torch(ctx, 2 * n_frames)
+    ex = PeerExchange.from_torch(ctx, 2 * n_frames, depth=3)
     rng = np.random.default_rng(11)  # the same scene description on every rank
     pcms = [synth_pcm(rng, 60000, 48000) for _ in range(4)]
     pos = [rand_in_shell(rng, 2, 100) for _ in range(n_src)]
@@ -86,6 +86,26 @@ def _worker(rank, world, port, n_src, n_frames, n_callbacks, q):
         ex.allreduce(tile.data_ptr(), 2 * n_frames, 0)
         ctx.synchronize()
         outs.append(tile.cpu().numpy().copy())
+    # the pipelined form: `depth` pushes in flight, pulls late and into other buffers, slots reused several times
+    nf = 2 * n_frames
+    for rep in range(4):
+        src = [torch.full((nf,), float((i + 1) * (rank + 1) + rep), device=f"cuda:{rank}") for i in range(3)]
+        dst = [torch.empty_like(x) for x in src]
+        for x in src:
+            ex.push(x.data_ptr(), nf)
+        for y in dst:
+            ex.pull(y.data_ptr(), nf)
+        ctx.synchronize()
+        for i, y in enumerate(dst):
+            assert float(y.min()) == float(y.max()) == sum((i + 1) * (r + 1) + rep for r in range(world))
+    try:
+        for _ in range(4):
+            ex.push(src[0].data_ptr(), nf)
+        raise AssertionError("a fourth outstanding push must be refused at depth 3")
+    except odb.OddioError:
+        for _ in range(3):
+            ex.pull(dst[0].data_ptr(), nf)
+        ctx.synchronize()
     q.put((rank, outs))
     dist.barrier()
     scene.close()
