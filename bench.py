@@ -345,7 +345,9 @@ def run_ours(args):
             stream.wait_stream(comm)
             for i in range(NG):
                 finish_exchange((first + i) % NG)
-        launches_per_step = scene.last_launch_count() + (1 if world > 1 else 0)
+        # our kernels per callback: the scene's own, plus the exchange's push and pull once per R callbacks (an NCCL
+        # all-reduce is not ours and is not counted)
+        launches_per_step = scene.last_launch_count() + ((2.0 / R) if peer else 0.0)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with clk:
@@ -467,8 +469,10 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
                     "h2d_bytes_per_step": n_upd * 32, "d2h_bytes_per_step": M * 8 + 4,
-                    "note": "audio thread: odb_scene_run with a host tile; control thread: set_motion on 1/16 of the sources every callback"},
-            "gpu_launches": launches_per_step * K,
+                    "note": ("audio thread: odb_scene_run with a host tile" if world == 1 else
+                             "audio thread: odb_scene_sample_device on this rank's shard, the tiles summed over the ranks every callback (push + pull), read back to the host")
+                            + "; control thread: set_motion on 1/16 of the sources every callback"},
+            "gpu_launches": int(round(launches_per_step * K)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic("k_mix_fast", n_local), "kernel": "k_mix_fast<strict>" if args.variant == 0 else "k_mix_fast<fma>", "kernel_ms": kernel_ms,
                          "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,

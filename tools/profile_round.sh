@@ -1,7 +1,7 @@
 set -x
 cd /root/repo
 # launch list of the bench command
-ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 60 --csv --log-file gpurun_out/r1b_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r1b_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 60 --csv --log-file gpurun_out/r1b_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r1b_launches.log 2>&1
 # full captures of the dominant kernel, both variants
 ncu --set full --clock-control none --import-source on -k regex:k_mix_fast -s 3 -c 1 -o gpurun_out/r1b_fast_fma python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_mix_fast -s 3 -c 1 -o gpurun_out/r1b_fast_strict python bench.py --steps 4 --warmup 3 --no-cpu-baseline --variant 0 > /dev/null 2>&1
