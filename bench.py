@@ -110,6 +110,12 @@ class ClockSampler:
         self.all_rows, self.t0, self.t1 = [], None, None
 
     def start(self):
+        import atexit
+
+        atexit.register(self.stop)
+        return self._start()
+
+    def _start(self):
         """Starts the poller. Called long before the timed region: nvidia-smi needs a noticeable fraction of a second
         to initialise on a multi-GPU box and holds driver locks while it does, which must not overlap the region."""
         if not self.enabled:
@@ -265,10 +271,15 @@ def run_ours(args):
     groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(NG)]
     comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     exch = None
+    exchange_note = ""
     if peer:
         from oddio_b200.sharding import PeerExchange
 
-        exch = PeerExchange.from_torch(ctx, R * M * 2, depth=NG)
+        try:
+            exch = PeerExchange.from_torch(ctx, R * M * 2, depth=NG)
+        except odb.OddioError as e:  # raised on every rank alike (e.g. CUDA IPC not permitted in this container)
+            peer, exch = False, None
+            exchange_note = f" (peer-memory exchange unavailable, fell back: {str(e)[:120]})"
 
     pending = [False] * NG  # peer exchange: group g has been pushed and not yet pulled
 
@@ -459,7 +470,7 @@ def run_ours(args):
                        "sources": N, "sources_per_gpu": n_local, "frames": M, "rate": RATE,
                        "parallelism": f"source-shard x{world}" + ("" if world == 1 else (
                            f", tiles summed by the library's peer-memory kernel over NVLink, one exchange per {R} callbacks ({R * M * 8} B per rank pair), overlapped with the next mixes"
-                           if peer else f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes")),
+                           if peer else f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes{exchange_note}")),
                        "l2": "inputs larger than L2: every callback reads fresh PCM "
                              f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
                        "kernel_variant": ("staged, strict (bit-exact per-source contributions)" if args.variant == 0 else

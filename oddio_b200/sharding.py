@@ -30,44 +30,71 @@ class PeerExchange:
     """Sum of the per-rank tiles over NVLink peer memory (include/oddio_b200.h, odb_exchange_*).
 
     `gather(handle: bytes) -> list[bytes]` returns every rank's handle in rank order; `from_torch` builds
-    it from torch.distributed (any backend: the handles are host bytes)."""
+    it from torch.distributed (any backend: the handles are host bytes). `depth`: pushed exchanges that may
+    await their pull (2..8)."""
 
     def __init__(self, ctx, rank: int, world: int, max_floats: int, gather=None, depth: int = 2):
         from . import _lib
 
         self._lib = _lib
-        L = _lib.load()
         h = C.c_void_p()
-        _lib.check(L.odb_exchange_create(ctx._h, int(rank), int(world), int(max_floats), int(depth), C.byref(h)))
+        _lib.check(_lib.load().odb_exchange_create(ctx._h, int(rank), int(world), int(max_floats), int(depth), C.byref(h)))
         self._h = h
         self.rank, self.world = rank, world
         if world > 1:
             if gather is None:
                 raise ValueError("world > 1 needs a gather function for the set-up handles")
-            n = L.odb_exchange_handle_size()
-            mine = C.create_string_buffer(n)
-            _lib.check(L.odb_exchange_export(self._h, mine))
-            handles = gather(mine.raw)
-            if len(handles) != world or any(len(x) != n for x in handles):
-                raise ValueError("gather must return one handle per rank, in rank order")
-            blob = C.create_string_buffer(b"".join(handles), n * world)
-            _lib.check(L.odb_exchange_connect(self._h, blob))
+            if gather is not False:  # False: the caller drives _export / _connect itself (from_torch)
+                self._connect(gather(self._export()))
+
+    def _export(self) -> bytes:
+        L = self._lib.load()
+        buf = C.create_string_buffer(L.odb_exchange_handle_size())
+        self._lib.check(L.odb_exchange_export(self._h, buf))
+        return buf.raw
+
+    def _connect(self, handles) -> None:
+        L = self._lib.load()
+        n = L.odb_exchange_handle_size()
+        if len(handles) != self.world or any(len(x) != n for x in handles):
+            raise ValueError("gather must return one handle per rank, in rank order")
+        blob = C.create_string_buffer(b"".join(handles), n * self.world)
+        self._lib.check(L.odb_exchange_connect(self._h, blob))
 
     @classmethod
     def from_torch(cls, ctx, max_floats: int, group=None, depth: int = 2):
+        """Builds the exchange over the ranks of a torch.distributed group. Every rank takes part in both collectives
+        below whether or not its own set-up succeeded, and all ranks agree on the outcome: the connected exchange is
+        returned on every rank, or OddioError is raised on every rank (callers can then fall back together)."""
         import torch.distributed as dist
+
+        from . import _lib
 
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return cls(ctx, 0, 1, max_floats, depth=depth)
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-
-        def gather(handle: bytes):
-            out = [None] * world
-            dist.all_gather_object(out, handle, group=group)
-            return out
-
-        ex = cls(ctx, rank, world, max_floats, gather, depth)
-        dist.barrier(group)  # every rank has mapped every inbox before the first push
+        ex, err, handle = None, None, b""
+        try:
+            ex = cls(ctx, rank, world, max_floats, gather=False, depth=depth)  # local part: inbox + handle
+            handle = ex._export()
+        except Exception as e:  # noqa: BLE001 - reported to every rank below
+            err = f"rank {rank}: {e}"
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        if err is None:
+            try:
+                if not all(handles):
+                    raise RuntimeError("a peer has no inbox")
+                ex._connect(handles)
+            except Exception as e:  # noqa: BLE001
+                err = f"rank {rank}: {e}"
+        errs = [None] * world
+        dist.all_gather_object(errs, err, group=group)  # doubles as the barrier: every rank has mapped every inbox
+        bad = [e for e in errs if e]
+        if bad:
+            if ex is not None:
+                ex.close()
+            raise _lib.OddioError(_lib.ODB_E_CUDA, "peer-memory exchange set-up failed: " + "; ".join(bad))
         return ex
 
     def allreduce(self, dev_ptr: int, n_floats: int, epilogue: int = 0, stream: int = 0) -> None:

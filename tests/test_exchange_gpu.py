@@ -129,7 +129,17 @@ def test_two_rank_sharded_scene_matches_the_oracle(oracle):
     procs = [ctxm.Process(target=_worker, args=(r, world, port, n_src, n_frames, n_cb, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=300) for _ in range(world))
+    import queue
+    import time
+
+    got, deadline = {}, time.time() + 300
+    while len(got) < world:  # fail fast if a worker died instead of waiting for the queue
+        try:
+            r, outs = q.get(timeout=1.0)
+            got[r] = outs
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            assert not dead and time.time() < deadline, f"worker(s) failed: exit codes {[p.exitcode for p in procs]}"
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
