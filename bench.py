@@ -408,59 +408,65 @@ def run_ours(args):
         scene.close()
 
         # ---- (3) end to end through the host-buffer call --------------------------------------------------------
-        ctl, scene, handles = new_scene()
-        host_out = np.zeros((M, 2), dtype=np.float32)
-        n_upd = max(1, n_local // 16)
-        ids_all = [h._src for h in handles]
-        rng = np.random.default_rng(7 + rank)
-        upd = []
-        for s in range(W + K):
-            sel = rng.choice(n_local, n_upd, replace=False)
-            gl = mine[sel]
-            ids = (C.c_uint64 * n_upd)(*[ids_all[i] for i in sel])
-            # the game thread nudges positions along the trajectory it already announced
-            p = (pos[gl] + vel[gl] * np.float32((s + 1) * M / RATE)).astype(np.float32)
-            upd.append((ids, p, vel[gl].copy()))
-
-        # The reference's architecture has two threads: a control ("game") thread that calls set_motion and the
-        # audio thread that calls run (README, examples/realtime.rs). Same here: the control thread queues the
-        # updates of callback s while the audio thread is inside odb_scene_run of callback s (ctypes releases the GIL).
-        # The audio thread paces the control thread with a semaphore (one batch of updates per callback) and never
-        # waits for it.
-        go = threading.Semaphore(0)
-
-        def control_thread():
+        def run_e2e():
+            ctl, scene, handles = new_scene()
+            host_out = np.zeros((M, 2), dtype=np.float32)
+            n_upd = max(1, n_local // 16)
+            ids_all = [h._src for h in handles]
+            rng = np.random.default_rng(7 + rank)
+            upd = []
             for s in range(W + K):
-                go.acquire()
-                ids, p, v = upd[s]
-                ctl.set_motion_ids(ids, n_upd, p, v)
+                sel = rng.choice(n_local, n_upd, replace=False)
+                gl = mine[sel]
+                ids = (C.c_uint64 * n_upd)(*[ids_all[i] for i in sel])
+                # the game thread nudges positions along the trajectory it already announced
+                p = (pos[gl] + vel[gl] * np.float32((s + 1) * M / RATE)).astype(np.float32)
+                upd.append((ids, p, vel[gl].copy()))
 
-        e2e_tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+            # The reference's architecture has two threads: a control ("game") thread that calls set_motion and the
+            # audio thread that calls run (README, examples/realtime.rs). Same here: the control thread queues the
+            # updates of callback s while the audio thread is inside odb_scene_run of callback s (ctypes releases the GIL).
+            # The audio thread paces the control thread with a semaphore (one batch of updates per callback) and never
+            # waits for it.
+            go = threading.Semaphore(0)
 
-        def step_e2e(s):
-            go.release()
-            if world == 1:
-                odb.run(scene, RATE, host_out)  # host tile: H2D of the queued updates and D2H of the result inside
-            else:  # this rank's shard into a device tile, summed over the ranks, then read back
-                scene.sample_device(interval, e2e_tile.data_ptr(), M)
-                if peer:
-                    exch.allreduce(e2e_tile.data_ptr(), M * 2, 0, stream.cuda_stream)
-                else:
-                    dist.all_reduce(e2e_tile)
-                host_out[:] = e2e_tile.cpu().numpy()
+            def control_thread():
+                for s in range(W + K):
+                    go.acquire()
+                    ids, p, v = upd[s]
+                    ctl.set_motion_ids(ids, n_upd, p, v)
 
-        th = threading.Thread(target=control_thread, daemon=True)
-        th.start()
-        for s in range(W):
-            step_e2e(s)
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(W, W + K):
-            step_e2e(s)
-        th.join()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        scene.close()
+            e2e_tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+
+            def step_e2e(s):
+                go.release()
+                if world == 1:
+                    odb.run(scene, RATE, host_out)  # host tile: H2D of the queued updates and D2H of the result inside
+                else:  # this rank's shard into a device tile, summed over the ranks, then read back
+                    scene.sample_device(interval, e2e_tile.data_ptr(), M)
+                    if peer:
+                        exch.allreduce(e2e_tile.data_ptr(), M * 2, 0, stream.cuda_stream)
+                    else:
+                        dist.all_reduce(e2e_tile)
+                    host_out[:] = e2e_tile.cpu().numpy()
+
+            th = threading.Thread(target=control_thread, daemon=True)
+            th.start()
+            for s in range(W):
+                step_e2e(s)
+            barrier()
+            t0 = time.perf_counter()
+            for s in range(W, W + K):
+                step_e2e(s)
+            th.join()
+            barrier()
+            e2e_s = time.perf_counter() - t0
+            scene.close()
+            return e2e_s
+
+
+        e2e_s = float("nan") if args.skip_e2e else run_e2e()
+        n_upd = max(1, n_local // 16)
 
     # max over ranks
     times = torch.tensor([ms, e2e_s * 1e3, float(np.mean(kms))], device=dev, dtype=torch.float64)
@@ -593,8 +599,10 @@ def main():
     ap.add_argument("--exchange-depth", type=int, default=4, help="N > 1: group buffers (exchanges) in flight, 2..8")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-GPU tiles are summed (peer = the library's NVLink peer-memory kernel, every callback)")
-    ap.add_argument("--variant", type=int, default=2, choices=[0, 2],
-                    help="2 (default) = staged kernel with FMA-contracted value ops, 0 = strict (bit-exact per-source contributions)")
+    ap.add_argument("--variant", type=lambda v: int(v, 0), default=2,
+                    help="2 (default, also the library's) = value ops contracted to FMA, 0 = strict (bit-exact per-source "
+                         "contributions); | 0x200 = round 1's multi-kernel callback instead of the one-launch kernel")
+    ap.add_argument("--skip-e2e", action="store_true", help="kernel experiments: device-resident passes only")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

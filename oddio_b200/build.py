@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.environ.get("ODB_SO") or os.path.join(HERE, "liboddio_b200.so")  # ODB_SO / ODB_NVCC_EXTRA: developer experiments
-SOURCES = ["odb_host.cu", "odb_scene.cu", "odb_mixer.cu", "odb_spatial.cu", "odb_mix_fast.cu", "odb_mixer_kernels.cu", "odb_ring.cu", "odb_exchange.cu"]
+SOURCES = ["odb_host.cu", "odb_scene.cu", "odb_mixer.cu", "odb_spatial.cu", "odb_mix_fast.cu", "odb_scene_mix.cu", "odb_mixer_kernels.cu", "odb_ring.cu", "odb_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

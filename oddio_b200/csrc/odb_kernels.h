@@ -67,6 +67,25 @@ void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, u
 int odb_mix_general_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
                                    int only_flagged, const uint32_t* counters, cudaStream_t st);
+// Arguments of the one-launch scene callback kernel (odb_scene_mix.cu).
+struct OdbSceneMixArgs {
+    const OdbJob* jobs;               // [n_tiles][n_sources], written by the walk kernel
+    int n_sources, n_tiles, n_frames;
+    int epilogue;                     // 0 none, 1 Tanh, 2 Reinhard, | ODB_EPILOGUE_I16_BIT
+    float* partials;                  // [n_tiles][grid][2 * ODB_TILE_FRAMES]
+    float* out;                       // interleaved stereo, device or pinned host memory (f32, or int16 with the I16 bit)
+    const uint32_t* counters;         // this callback's job counters (NULL: always scan for flagged jobs)
+    uint32_t* zero_counters;          // the other parity's counters, reset for the next callback (may be NULL)
+    unsigned long long* arrive;       // monotonic count of (CTA, tile) arrivals over the life of the scene
+    unsigned long long arrive_base;   // its value before this launch
+    unsigned long long* done;         // monotonic count of finished CTAs (NULL: no host flag)
+    unsigned long long done_base;
+    unsigned long long* host_flag;    // pinned host word that receives `seq` when the whole grid has stored its output
+    unsigned long long seq;
+    unsigned long long nz;            // (-0.0, -0.0), see odb_f32x2.cuh mulx
+};
+int odb_scene_mix_ctas(int n_sources, int sm_count);
+cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mode, cudaStream_t st);
 int odb_mix_fast_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int mode,
                                 cudaStream_t st);

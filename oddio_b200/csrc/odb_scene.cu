@@ -22,7 +22,7 @@ struct odb_scene {
     OdbQuat rot_pending = {0.0f, 0.0f, 0.0f, 1.0f};
     bool rot_fresh = false;
     int epilogue = ODB_EPILOGUE_NONE;
-    int variant = 0;
+    int variant = 2;  // 0: strict (unfused value arithmetic), 1: literal kernels only, 2: value multiply-adds contracted to FMA
     uint32_t last_launches = 0;
     // Optional two-stage pipeline (odb_set_kernel_variant bit 8): the per-source set-up of callback k+1
     // (control-plane scatter + walk kernels, on the scene's own `wst` stream) overlaps the mix kernels of
@@ -42,6 +42,16 @@ struct odb_scene {
     DevBuf<float> d_partials;
     DevBuf<float> d_partials_fast;
     DevBuf<float> d_partials_ring;
+    // One-launch callback (odb_scene_mix.cu), the default for scenes without buffered sources: partial tiles by
+    // callback parity (the next callback's CTAs may start while this one's reducers still read), the grid's
+    // arrive / done counters and the running totals the kernel compares them with.
+    DevBuf<float> d_partials_fused[2];
+    DevBuf<unsigned long long> d_sync;   // [0] arrivals, [1] finished CTAs
+    unsigned long long arrive_total = 0, done_total = 0;
+    bool legacy = false;                 // odb_set_kernel_variant bit 9: the multi-kernel path of round 1
+    bool flag_armed = false;             // the callback just queued publishes flag_seq to h_flag when its tile is stored
+    PinBuf<unsigned long long> h_flag;   // sequence number of the last callback whose tile has landed in h_out
+    unsigned long long flag_seq = 0;
     DevBuf<float> d_out;
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -98,6 +108,7 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     }
     cudaStreamDestroy(scene->wst);
     scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_partials_ring.release();
+    scene->d_partials_fused[0].release(); scene->d_partials_fused[1].release(); scene->d_sync.release(); scene->h_flag.release();
     scene->d_out.release();
     scene->h_out.release();
     if (scene->ev0) { cudaEventDestroy(scene->ev0); cudaEventDestroy(scene->ev1); }
@@ -323,11 +334,13 @@ static int ensure_idle(odb_scene* scene, DevBuf<T>& buf, size_t n) {
     return buf.ensure(n, scene->ctx->stream, false);
 }
 
-static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames, bool as_i16 = false) {
+static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames, bool as_i16 = false,
+                             bool host_flag = false) {
     odb_ctx* ctx = scene->ctx;
     cudaStream_t st = ctx->stream, wst = scene->pipelined ? scene->wst : ctx->stream;
     if (n_frames > ODB_MAX_FRAMES)
         return odb_fail(ODB_E_UNSUPPORTED, "n_frames %u exceeds the %d frames one callback may render", n_frames, ODB_MAX_FRAMES);
+    scene->flag_armed = false;
     ODB_CUDA(cudaSetDevice(ctx->device));
     uint32_t launches = 0;
     const int p = (int)(scene->callback_no & 1);
@@ -404,6 +417,50 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         ODB_CUDA(cudaStreamWaitEvent(st, scene->ev_walk[p], 0));
     }
     const bool use_fast = scene->variant != 1;
+    // ---- the one-launch callback: staged mix + literal tail + grid reduce + epilogue (seek set only) ----------------
+    if (nb == 0 && ns > 0 && nt > 0 && !scene->legacy) {
+        const int n_ctas = odb_scene_mix_ctas(ns, ctx->sm_count);
+        ODB_TRY(ensure_idle(scene, scene->d_partials_fused[p], (size_t)nt * n_ctas * 2 * ODB_TILE_FRAMES));
+        if (!scene->d_sync.p) {
+            ODB_TRY(ensure_idle(scene, scene->d_sync, 2));
+            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 2 * sizeof(unsigned long long), st));
+        }
+        OdbSceneMixArgs a;
+        memset(&a, 0, sizeof a);
+        a.jobs = scene->d_jobs[p].p;
+        a.n_sources = ns; a.n_tiles = nt; a.n_frames = (int)n_frames;
+        a.epilogue = scene->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0);
+        a.partials = scene->d_partials_fused[p].p;
+        a.out = dev_out;
+        a.counters = counters;
+        a.zero_counters = scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p;
+        a.arrive = scene->d_sync.p;
+        a.arrive_base = scene->arrive_total;
+        scene->arrive_total += (unsigned long long)nt * (unsigned long long)n_ctas;
+        if (host_flag) {
+            ODB_TRY(scene->h_flag.ensure(1));
+            a.done = scene->d_sync.p + 1;
+            a.done_base = scene->done_total;
+            scene->done_total += (unsigned long long)n_ctas;
+            a.host_flag = scene->h_flag.p;
+            a.seq = ++scene->flag_seq;
+            scene->flag_armed = true;
+        }
+        if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev0, st));
+        cudaError_t e = odb_launch_scene_mix(a, n_ctas, /*mode=*/scene->variant == 2 ? 1 : 0, st);
+        if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "scene_mix launch failed: %s", cudaGetErrorString(e));
+        if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev1, st));
+        launches++;
+        seg(1);
+        seg(2);
+        if (scene->pipelined) ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
+        ODB_TRY(scene->seek.post_callback(ctx, wst));
+        ODB_TRY(scene->buffered.post_callback(ctx, wst));
+        seg(3);
+        scene->last_launches = launches;
+        ODB_CUDA(cudaGetLastError());
+        return ODB_OK;
+    }
     int n_ring = 0;
     if (nb > 0) {  // extend the delay rings (Ring::write), before anything reads them
         odb_launch_ring_write(scene->d_ring_writes[p].p, nb, st);
@@ -657,6 +714,7 @@ extern "C" int odb_set_kernel_variant(void* owner, int variant) {
         cudaStreamSynchronize(sc->ctx->stream);
         sc->variant = variant & 0xFF;
         sc->pipelined = (variant & 0x100) != 0;
+        sc->legacy = (variant & 0x200) != 0;
         return ODB_OK;
     }
     if (kind == ODB_KIND_MIXER) return odb_mixer_set_variant(owner, variant);

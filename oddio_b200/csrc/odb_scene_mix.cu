@@ -1,0 +1,622 @@
+// One-launch scene callback for the seek path: SpatialScene's mix closure (spatial.rs:445-469) over
+// FramesSignal::sample (frames.rs:176-201) for every source of the scene, the literal path for the jobs the
+// walk kernel flagged, the sum of the per-CTA partial tiles and the Tanh / Reinhard epilogue - what used to be
+// k_mix_fast + k_mix_general + k_reduce_tiles (three launches, two grid-wide dependencies) in one persistent grid.
+//
+// A persistent grid of one 16-warp CTA per SM; the two warps of a pair mix the two 512-frame halves of the same
+// sources. Per 1024-frame tile of the callback (the tile loop is inside the kernel, so a callback may have any length):
+//   1. batches of 8 sources per warp, as in k_mix_fast (odb_mix_fast.cu): job records staged in bank-swizzled shared
+//      memory, the PCM window of each source fetched by one elected lane with a bulk async copy (TMA, UBLKCP) into
+//      one of two buffers, the reference's serial cursor `offset += ds` (frames.rs:195) walked literally on 32 lanes
+//      (source x ear x chunk) with every 4th value parked in shared memory;
+//   2. consume: lane l owns the frame PAIRS (64 j + 2 l, 64 j + 2 l + 1) of a 256-frame chunk. One checkpoint load
+//      serves both frames: even lanes sit on a checkpoint, odd lanes two literal steps behind one, and the second
+//      frame of the pair is one more literal step - 3 packed additions and one load per two frames where the
+//      lane-strided layout of k_mix_fast needs 6 and 2. Index/fraction split, taps, lerp, gain ramp and the packed
+//      (L, R) accumulators are k_mix_fast's. The price is a 2-way bank conflict on the tap loads (lanes l and l + 16
+//      are 32 ds words apart); the shared-memory pipe has the room;
+//   3. tail: jobs flagged ODB_JF_GENERAL (any ds, windows outside the block, FixedGain, Cycle) are mixed literally by
+//      the warp that owns their batch, straight into its parked accumulators (general_half, the code of
+//      k_mix_general for one half tile);
+//   4. fold warp -> CTA in fixed order, one partial tile per CTA to HBM, then a grid-wide arrive counter: when every
+//      CTA of the grid has arrived, CTA b sums 16-float slices b, b + grid, ... of all partial tiles in index order
+//      (deterministic; no float atomics), applies the epilogue and stores the output - f32 or 16-bit PCM, device
+//      memory or pinned host memory. All CTAs are resident (grid <= SM count, one CTA per SM), so the wait cannot
+//      deadlock. The last CTA to finish publishes the callback's sequence number to an optional host flag.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "odb_kernels.h"
+#include "odb_math.cuh"
+#include "odb_async.cuh"
+#include "odb_f32x2.cuh"
+
+namespace odbk {
+
+// Compile-time shape of the kernel. SPLIT: a 1024-frame tile is mixed as SPLIT parts, one warp each (2: warp pairs,
+// 16 packed accumulators per lane; 1: one warp per tile, 32 accumulators, fewer and longer visits per source).
+// LOOP: 0 = lane l owns frames l + 32 j (conflict-light taps, three literal steps per frame),
+//       1 = lane l owns the frame pairs 64 j + 2 l, + 1 (three literal steps per two frames, 2-way tap conflicts).
+// ILP: frames of a chunk a lane has in flight.
+template <int SPLIT_, int WARPS_, int LOOP_, int ILP_>
+struct SmxCfg {
+    static constexpr int SPLIT = SPLIT_, WARPS = WARPS_, LOOP = LOOP_, ILP = ILP_;
+    static constexpr int HCHUNKS = ODB_TILE_CHUNKS / SPLIT;                   // 256-frame chunks per part
+    static constexpr int NACC = HCHUNKS * 8;                                  // packed (L, R) accumulators per lane
+    static constexpr int BATCH = 16 / HCHUNKS;                                // sources per batch: BATCH x 2 ears x HCHUNKS = 32 chains
+    static constexpr int PCM_FLOATS = ODB_FAST_PCM_CAP * HCHUNKS / 2;         // 640 per 512-frame half
+    static constexpr int PCM_BYTES = PCM_FLOATS * 4;
+    static constexpr int POINTS = ODB_SPATIAL_CHUNK / 4;                      // every 4th cursor value of a chunk
+    static constexpr int ROW_BYTES = POINTS * 8 + 8;                          // (L, R) cursors of one (source, chunk); +8 skews the banks
+    static constexpr int OFFS_BYTES = BATCH * HCHUNKS * ROW_BYTES;            // 8320
+    static constexpr int WARP_BYTES = 2 * PCM_BYTES + OFFS_BYTES;
+    static constexpr int PART_FRAMES = ODB_TILE_FRAMES / SPLIT;
+    static constexpr int REC_BYTES = 128;
+    static constexpr int JOBS_OFF = WARPS * WARP_BYTES;
+    static constexpr int BARS_OFF = JOBS_OFF + WARPS * BATCH * REC_BYTES;
+    static constexpr int SMEM_BYTES = BARS_OFF + WARPS * 16;
+    static_assert(WARP_BYTES >= PART_FRAMES * 8 + 2 * PART_FRAMES * 4, "parked part of the tile + literal-path scratch");
+    static_assert(WARP_BYTES % 16 == 0, "TMA destinations are 16-byte aligned");
+    static_assert(SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
+    static_assert(WARPS % SPLIT == 0 && (WARPS * 32) % 16 == 0, "warps come in groups of SPLIT");
+};
+constexpr int SMX_SLICE = 16;                                              // output floats one reducing CTA sums at a time
+constexpr int SMX_SLICES = 2 * ODB_TILE_FRAMES / SMX_SLICE;                // 128
+
+// Words of a staged job record after the warp's prologue (see k_mix_fast).
+#define SJ_SRC 0
+#define SJ_BYTES 2
+#define SJ_CODE 10
+#define SJ_K 12
+
+// One 256-frame chunk of one source. LOOP 0: lane l owns frames l + 32 j (j = 0..7); LOOP 1: the frame pairs
+// (64 j + 2 l, + 1), j = 0..3 - either way 8 frames and 8 packed accumulators per lane and chunk; frame_of(u) is the
+// chunk-relative frame of the lane's u-th accumulator minus the lane's own offset (lane or 2 lane).
+// UL / UR: that ear is on FramesSignal's ds ~= 1 path (frames.rs:180-187). FULL: every frame of the chunk is inside
+// the tile. KL / KR: doppler ear = shared address of PCM index `base` minus the magic bits; unit ear = shared address
+// of PCM index base + the lane's offset. d1..d3: the literal steps between the lane's checkpoint and its frame
+// (LOOP 0: ds or +0.0 by lane & 3; LOOP 1: d1 = d2 = (ds or +0.0 by lane & 1), d3 = ds for the second frame of a pair).
+template <class CFG, bool STRICT, bool FULL, bool UL, bool UR>
+__device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int cc, const int c, const int lane, const float fbase,
+                                              const uint32_t row_sa, const uint32_t KL, const uint32_t KR, const u64 d1,
+                                              const u64 d2, const u64 d3, const u64 fr_unit, const u64 pgp, const u64 dgp,
+                                              const int nfr, const u64 nz) {
+    constexpr int ILP = CFG::ILP;
+    constexpr int LSTEP = CFG::LOOP == 0 ? 1 : 2;                                       // frames per lane step
+    auto frame_of = [](int u) { return CFG::LOOP == 0 ? 32 * u : 64 * (u >> 1) + (u & 1); };
+    const u64 magic = pk2(ODB_MAGIC, ODB_MAGIC);
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += ILP) {
+        if (!FULL && c * ODB_SPATIAL_CHUNK + frame_of(j0) >= nfr) break;  // warp-uniform
+        uint32_t aL[ILP], aR[ILP];
+        u64 fr[ILP], o[ILP];
+        if (!(UL && UR)) {
+            if (CFG::LOOP == 0) {
+                // cursor of frame k = 32 j + l: checkpoint k & ~3, then k & 3 literal `offset += ds` steps (frames.rs:195);
+                // adding +0.0 is exact
+#pragma unroll
+                for (int u = 0; u < ILP; u++) o[u] = lds_u64(row_sa + (uint32_t)(64 * (j0 + u)));
+#pragma unroll
+                for (int u = 0; u < ILP; u++) o[u] = add2(o[u], d1);
+#pragma unroll
+                for (int u = 0; u < ILP; u++) o[u] = add2(o[u], d2);
+#pragma unroll
+                for (int u = 0; u < ILP; u++) o[u] = add2(o[u], d3);
+            } else {
+                // cursor of frame k = 64 j + 2 l: checkpoint k & ~3, then (k & 3) in {0, 2} literal steps; frame k + 1
+                // is one more step
+#pragma unroll
+                for (int u = 0; u < ILP; u += 2) o[u] = lds_u64(row_sa + (uint32_t)(128 * ((j0 + u) >> 1)));
+#pragma unroll
+                for (int u = 0; u < ILP; u += 2) o[u] = add2(o[u], d1);
+#pragma unroll
+                for (int u = 0; u < ILP; u += 2) o[u] = add2(o[u], d2);
+#pragma unroll
+                for (int u = 0; u < ILP; u += 2) o[u + 1] = add2(o[u], d3);
+            }
+            // trunc = offset as isize; fract = offset - trunc as f32 (frames.rs:191-193): a round-down add of 2^23
+            // leaves trunc(offset) in the low mantissa bits (offset >= 0 here). (An F2I.TRUNC / I2FP split was
+            // measured 8 % slower: the conversions are not full rate on sm_100a.)
+            u64 t[ILP];
+#pragma unroll
+            for (int u = 0; u < ILP; u++) t[u] = add2_rm(o[u], magic);
+#pragma unroll
+            for (int u = 0; u < ILP; u++) {
+                uint32_t tL, tR;
+                upk2u(t[u], tL, tR);
+                aL[u] = KL + (tL << 2);
+                aR[u] = KR + (tR << 2);
+            }
+#pragma unroll
+            for (int u = 0; u < ILP; u++) fr[u] = sub2(o[u], sub2(t[u], magic));
+        }
+        if (UL || UR) {  // frames.rs:183-187
+            float u0, u1;
+            upk2(fr_unit, u0, u1);
+#pragma unroll
+            for (int u = 0; u < ILP; u++) {
+                float f0, f1;
+                if (UL && UR) { f0 = u0; f1 = u1; }
+                else { upk2(fr[u], f0, f1); if (UL) f0 = u0; else f1 = u1; }
+                fr[u] = pk2(f0, f1);
+                if (UL) aL[u] = KL + (uint32_t)(4 * frame_of(j0 + u));
+                if (UR) aR[u] = KR + (uint32_t)(4 * frame_of(j0 + u));
+            }
+        }
+        u64 a[ILP], b[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {  // get_pair (frames.rs:105-123); zeros come from the arena padding
+            a[u] = pk2(lds_f32(aL[u]), lds_f32(aR[u]));
+            b[u] = pk2(lds_f32_4(aL[u]), lds_f32_4(aR[u]));
+        }
+        u64 g[ILP], s[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            const float fi = fbase + (float)frame_of(j0 + u);  // `i as f32` (spatial.rs:459); exact small integer
+            const u64 fi2 = pk2(fi, fi);
+            if (STRICT) g[u] = mulx(fi2, dgp, nz);
+            else g[u] = fma2(fi2, dgp, pgp);
+        }
+        if (STRICT) {
+#pragma unroll
+            for (int u = 0; u < ILP; u++) g[u] = add2(pgp, g[u]);  // prev_state.gain + i as f32 * d_gain
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; u++) b[u] = sub2(b[u], a[u]);     // frame::lerp = a + t * (b - a) (frame.rs:39-41)
+        if (STRICT) {
+#pragma unroll
+            for (int u = 0; u < ILP; u++) s[u] = mulx(fr[u], b[u], nz);
+#pragma unroll
+            for (int u = 0; u < ILP; u++) s[u] = add2(a[u], s[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < ILP; u++) s[u] = fma2(fr[u], b[u], a[u]);
+        }
+        if (!FULL) {
+#pragma unroll
+            for (int u = 0; u < ILP; u++)
+                if (c * ODB_SPATIAL_CHUNK + frame_of(j0 + u) + LSTEP * lane >= nfr) s[u] = 0ull;  // beyond the tile: +0
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            if (STRICT) acc[cc * 8 + j0 + u] = add2(acc[cc * 8 + j0 + u], mulx(s[u], g[u], nz));  // o[ear] += s * gain (spatial.rs:460)
+            else acc[cc * 8 + j0 + u] = fma2(s[u], g[u], acc[cc * 8 + j0 + u]);
+        }
+    }
+}
+
+template <class CFG, bool STRICT, bool FULL, bool UL, bool UR>
+__device__ __forceinline__ void consume_source(u64* __restrict__ acc, const int lane, const float lanef, const int part,
+                                               const uint32_t rec_sa, const uint32_t rec_x, const uint32_t pcm_b,
+                                               const uint32_t rows_sa, const uint32_t* __restrict__ K, const int nfr, const u64 d1,
+                                               const u64 d2, const u64 d3, const u64 pgp, const u64 dgp, const u64 nz) {
+    const uint32_t lane_b = (uint32_t)(lane * (CFG::LOOP == 0 ? 4 : 8));
+#pragma unroll
+    for (int cc = 0; cc < CFG::HCHUNKS; cc++) {
+        const int c = part * CFG::HCHUNKS + cc;
+        if (!FULL && c * ODB_SPATIAL_CHUNK >= nfr) break;
+        const uint32_t KL = pcm_b + K[2 * cc] + (UL ? lane_b : 0u);
+        const uint32_t KR = pcm_b + K[2 * cc + 1] + (UR ? lane_b : 0u);
+        u64 fr_unit = 0ull;
+        if (UL || UR)
+            fr_unit = pk2(__uint_as_float(lds_u32(rec_sa + ((uint32_t)((ODB_JW_OFF0 + c) * 4) ^ rec_x))),
+                          __uint_as_float(lds_u32(rec_sa + ((uint32_t)((ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4) ^ rec_x))));
+        consume_chunk<CFG, STRICT, FULL, UL, UR>(acc, cc, c, lane, lanef + (float)(c * ODB_SPATIAL_CHUNK),
+                                                 rows_sa + (uint32_t)(cc * CFG::ROW_BYTES), KL, KR, d1, d2, d3, fr_unit, pgp, dgp,
+                                                 nfr, nz);
+    }
+}
+
+// The literal path for one flagged job and one part of the tile (PART_FRAMES frames from `first`), added into the
+// warp's parked accumulators `tile` (float2 per frame of the part). The arithmetic is k_mix_general's
+// (odb_spatial.cu): every operation a single unfused IEEE operation in the reference's order.
+// `scratch`: 2 x part_frames floats (cursors, or Cycle's lerped samples).
+__device__ __noinline__ void general_part(const OdbJob* __restrict__ job, const int first, const int part_frames, const int tl,
+                                          const int lane, float2* __restrict__ tile, float* __restrict__ scratch) {
+    const uint32_t jf = job->flags;
+    const int nfr = job->n_frames;
+    if (nfr <= first) return;
+    const bool cycle = (jf & ODB_JF_CYCLE) != 0;
+    const int part_chunks = part_frames / ODB_SPATIAL_CHUNK;
+    if (lane < 2 * part_chunks) {
+        const int e = lane & 1, cc = lane >> 1, c = first / ODB_SPATIAL_CHUNK + cc;
+        const int m = min(ODB_SPATIAL_CHUNK, nfr - c * ODB_SPATIAL_CHUNK);
+        float* dst = scratch + e * part_frames + cc * ODB_SPATIAL_CHUNK;
+        if (m > 0 && cycle) {  // Cycle::sample, cycle.rs:26-53: the chain lane also takes the (wrapping) taps
+            const float* __restrict__ x0 = job->pcm;
+            const unsigned long long ulen = (unsigned long long)job->len;
+            const float ds = job->ds[e];
+            unsigned long long cbase = (unsigned long long)job->base[e][c];
+            float offset = job->off0[e][c];
+            for (int k = 0; k < m; k++) {
+                const unsigned long long tr = (unsigned long long)offset;              // :31
+                const float fract = offset - (float)tr;                                // :32 (kept across a wrap)
+                unsigned long long x = cbase + tr;                                     // :33
+                if (x >= ulen) {                                                       // :38-41
+                    cbase = 0;
+                    offset = (float)(x % ulen) + fract;
+                    x = (unsigned long long)offset;
+                }
+                const float a = x0[x];
+                const float b = x < ulen - 1 ? x0[x + 1] : x0[0];                      // :34-37 / :42-46
+                dst[k] = a + fract * (b - a);                                          // frame.rs:39-41
+                offset = offset + ds;                                                  // :50
+            }
+        } else if (m > 0 && !(jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R))) {
+            const float ds = job->ds[e];
+            float offset = job->off0[e][c];
+            for (int k = 0; k < ODB_SPATIAL_CHUNK; k++) {
+                dst[k] = offset;
+                offset = offset + ds;                                                  // frames.rs:195
+            }
+        }
+    }
+    __syncwarp();
+    const float* __restrict__ pcm = job->pcm;
+    const int len = job->len;
+    const float fg = job->fixed_gain;
+    const bool has_fg = (jf & ODB_JF_FIXED_GAIN) != 0;
+    for (int e = 0; e < 2; e++) {
+        const bool unit = (jf & (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R)) != 0;
+        const float pg = job->pg[e], dg = job->dg[e];
+        for (int j = 0; j < part_frames / 32; j++) {
+            const int f = 32 * j + lane, i = first + f;  // frame of the part / of the tile
+            if (i >= nfr) continue;
+            const int c = i >> 8, k = i & (ODB_SPATIAL_CHUNK - 1);
+            float smp;
+            if (cycle) {
+                smp = scratch[e * part_frames + f];
+            } else {
+                const long long base = job->base[e][c];
+                float a, b, fract;
+                if (unit) {                                                            // frames.rs:183-187
+                    get_pair_mono(pcm, len, base + k, a, b);
+                    fract = job->off0[e][c];
+                } else {                                                               // frames.rs:191-193
+                    const float offset = scratch[e * part_frames + f];
+                    const long long tr = (long long)offset;
+                    get_pair_mono(pcm, len, base + tr, a, b);
+                    fract = offset - (float)tr;
+                }
+                smp = a + fract * (b - a);                                             // frame.rs:39-41
+            }
+            if (has_fg) smp = smp * fg;                                                // gain.rs:35
+            const float gain = pg + (float)(tl * ODB_TILE_FRAMES + i) * dg;            // spatial.rs:459
+            const float contrib = smp * gain;                                          // spatial.rs:460
+            float* o = reinterpret_cast<float*>(tile + f) + e;
+            *o = *o + contrib;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <class CFG, bool STRICT>
+__global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbSceneMixArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int WARPS = CFG::WARPS, SPLIT = CFG::SPLIT, HCHUNKS = CFG::HCHUNKS, BATCH = CFG::BATCH, NACC = CFG::NACC;
+    constexpr int THREADS = WARPS * 32, RGROUPS = THREADS / SMX_SLICE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int part = warp % SPLIT, team = warp / SPLIT;  // the SPLIT warps of a team mix the parts of the same sources
+    const uint32_t smem_sa = smem_u32(smem_raw);
+    const uint32_t pcm_sa = smem_sa + (uint32_t)(warp * CFG::WARP_BYTES);
+    const uint32_t offs_sa = pcm_sa + 2 * CFG::PCM_BYTES;
+    const uint32_t jobs_sa = smem_sa + (uint32_t)(CFG::JOBS_OFF + warp * BATCH * CFG::REC_BYTES);
+    const uint32_t bar_sa = smem_sa + (uint32_t)(CFG::BARS_OFF + warp * 16);
+    if (lane == 0) {
+        mbar_init(bar_sa, 1);
+        mbar_init(bar_sa + 8, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();           // job records and counters come from the walk kernel launched just before
+    if (A.zero_counters && blockIdx.x == 0 && threadIdx.x < ODB_CNT_WORDS) A.zero_counters[threadIdx.x] = 0u;
+    uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
+    uint32_t buf = 0;
+
+    const int n_sources = A.n_sources;
+    const u64 nz = A.nz;
+    const int G = (int)gridDim.x;
+    const int gp = blockIdx.x * (WARPS / SPLIT) + team, GP = G * (WARPS / SPLIT);
+    const int n_batches = (n_sources + BATCH - 1) / BATCH;
+    const int first_frame = part * CFG::PART_FRAMES;
+    const int c0 = part * HCHUNKS;
+
+    auto rec = [&](int q, int w) { return jobs_sa + (uint32_t)(q * CFG::REC_BYTES) + (uint32_t)((w * 4) ^ (q * 16)); };
+    auto start_copy = [&](int q, uint32_t b) {
+        const uint4 d = lds_u128(rec(q, SJ_SRC));
+        const u64 p = ((u64)d.y << 32) | (u64)d.x;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t"
+            "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+            "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}" ::"r"(bar_sa + b * 8),
+            "r"(d.z), "r"(pcm_sa + b * CFG::PCM_BYTES), "l"(p)
+            : "memory");
+    };
+
+    for (int tl = 0; tl < A.n_tiles; tl++) {
+        u64 acc[NACC];
+#pragma unroll
+        for (int j = 0; j < NACC; j++) acc[j] = 0ull;
+        const float lanef = (float)(tl * ODB_TILE_FRAMES + (CFG::LOOP == 0 ? lane : 2 * lane));
+        const OdbJob* tile_jobs = A.jobs + (size_t)tl * n_sources;
+
+        for (int bi = gp; bi < n_batches; bi += GP) {
+            const int s0 = bi * BATCH;
+            // 1. stage the batch's job records (one 128-byte line each: lane l moves word l)
+#pragma unroll
+            for (int q = 0; q < BATCH; q++) {
+                uint32_t w = lane == ODB_JW_FLAGS ? ODB_JF_SKIP : 0u;
+                if (s0 + q < n_sources) w = __ldcg(reinterpret_cast<const uint32_t*>(tile_jobs + s0 + q) + lane);
+                sts_u32(rec(q, lane), w);
+            }
+            __syncwarp();
+            // lane q < BATCH derives what this part needs of source q and rewrites its private record (SJ_* words)
+            bool mine = false;
+            if (lane < BATCH) {
+                const uint4 h = lds_u128(rec(lane, 0));                                     // pcm lo/hi, len, flags
+                const int nfr = (int)lds_u32(rec(lane, ODB_JW_N_FRAMES));
+                mine = !(h.w & (ODB_JF_SKIP | ODB_JF_GENERAL)) && nfr > first_frame;
+                if (mine) {
+                    int w_start, w_len;
+                    if (SPLIT == 2) {
+                        const uint2 win = lds_u64x(rec(lane, ODB_JW_WINDOW + 2 * part));
+                        w_start = (int)win.x; w_len = (int)win.y;
+                    } else {  // the whole tile: both halves' windows abut or overlap (the cursor only moves forward)
+                        const uint4 win = lds_u128(rec(lane, ODB_JW_WINDOW));
+                        w_start = (int)win.x;
+                        w_len = win.w ? (int)win.z + (int)win.w - w_start : (int)win.y;
+                    }
+                    const u64 p = (((u64)h.y << 32) | (u64)h.x) + (u64)((long long)w_start * 4);
+                    const uint32_t mL = (h.w & ODB_JF_FAST_L) ? 0u : (ODB_MAGIC_BITS << 2);
+                    const uint32_t mR = (h.w & ODB_JF_FAST_R) ? 0u : (ODB_MAGIC_BITS << 2);
+                    int bL[HCHUNKS], bR[HCHUNKS];
+#pragma unroll
+                    for (int cc = 0; cc < HCHUNKS; cc++) {
+                        bL[cc] = (int)lds_u32(rec(lane, ODB_JW_BASE + c0 + cc));
+                        bR[cc] = (int)lds_u32(rec(lane, ODB_JW_BASE + ODB_TILE_CHUNKS + c0 + cc));
+                    }
+                    const uint32_t code = (nfr == ODB_TILE_FRAMES ? 4u : 0u) | ((h.w & ODB_JF_FAST_L) ? 2u : 0u) | ((h.w & ODB_JF_FAST_R) ? 1u : 0u);
+                    sts_u32(rec(lane, SJ_SRC), (uint32_t)p);
+                    sts_u32(rec(lane, SJ_SRC + 1), (uint32_t)(p >> 32));
+                    sts_u32(rec(lane, SJ_BYTES), (uint32_t)w_len * 4u);
+                    sts_u32(rec(lane, SJ_CODE), code);
+#pragma unroll
+                    for (int cc = 0; cc < HCHUNKS; cc++) {  // SJ_K + 2 cc (+ 1): overwrites the `base` words (12..19), read above
+                        sts_u32(rec(lane, SJ_K + 2 * cc), (uint32_t)((bL[cc] - w_start) * 4) - mL);
+                        sts_u32(rec(lane, SJ_K + 2 * cc + 1), (uint32_t)((bR[cc] - w_start) * 4) - mR);
+                    }
+                }
+            }
+            __syncwarp();
+            uint32_t act = __ballot_sync(0xffffffffu, mine);
+            if (act) {
+                start_copy(__ffs(act) - 1, buf);
+                {   // 2. literal cursor chains: lane = (source q, ear e, chunk cc of this part)
+                    const int q = lane / (2 * HCHUNKS), e = (lane / HCHUNKS) & 1, cc = lane % HCHUNKS;
+                    const uint32_t jf = lds_u32(rec(q, ODB_JW_FLAGS));
+                    if (((act >> q) & 1u) && !(jf & (e ? ODB_JF_FAST_R : ODB_JF_FAST_L))) {
+                        float o = __uint_as_float(lds_u32(rec(q, ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c0 + cc)));
+                        const float ds = __uint_as_float(lds_u32(rec(q, ODB_JW_DS + e)));
+                        const uint32_t dst = offs_sa + (uint32_t)((q * HCHUNKS + cc) * CFG::ROW_BYTES + e * 4);
+#pragma unroll 8
+                        for (int m = 0; m < CFG::POINTS; m++) {
+                            sts_f32(dst + (uint32_t)(m * 8), o);  // checkpoint m = cursor of frame 4 m
+                            o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds);
+                        }
+                    }
+                }
+                __syncwarp();
+                // 3. consume the batch source by source
+                while (act) {
+                    const int q = __ffs(act) - 1;
+                    act &= act - 1u;
+                    if (act) start_copy(__ffs(act) - 1, buf ^ 1u);
+                    const uint4 P = lds_u128(rec(q, ODB_JW_DS));   // ds (L, R), prev gain (L, R)
+                    const uint4 B = lds_u128(rec(q, ODB_JW_DG));   // d_gain (L, R), code, n_frames
+                    uint32_t K[2 * HCHUNKS];
+#pragma unroll
+                    for (int i = 0; i < 2 * HCHUNKS; i += 4) {
+                        const uint4 k4 = lds_u128(rec(q, SJ_K + i));
+                        K[i] = k4.x; K[i + 1] = k4.y; K[i + 2] = k4.z; K[i + 3] = k4.w;
+                    }
+                    const u64 dsp = ((u64)P.y << 32) | P.x, pgp = ((u64)P.w << 32) | P.z, dgp = ((u64)B.y << 32) | B.x;
+                    const int nfr = (int)B.w;
+                    u64 d1, d2, d3;
+                    uint32_t rows_sa = offs_sa + (uint32_t)(q * HCHUNKS * CFG::ROW_BYTES);
+                    if (CFG::LOOP == 0) {
+                        const int r = lane & 3;
+                        d1 = r >= 1 ? dsp : 0ull; d2 = r >= 2 ? dsp : 0ull; d3 = r >= 3 ? dsp : 0ull;
+                        rows_sa += (uint32_t)((lane >> 2) * 8);
+                    } else {
+                        d1 = (lane & 1) ? dsp : 0ull; d2 = d1; d3 = dsp;
+                        rows_sa += (uint32_t)((lane >> 1) * 8);
+                    }
+                    const uint32_t pcm_b = pcm_sa + buf * CFG::PCM_BYTES;
+                    const uint32_t off0_sa = jobs_sa + (uint32_t)(q * CFG::REC_BYTES), off0_x = (uint32_t)(q * 16);
+                    mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
+                    parity ^= 1u << buf;
+#define ODB_CONSUME(F, L, R) consume_source<CFG, STRICT, F, L, R>(acc, lane, lanef, part, off0_sa, off0_x, pcm_b, rows_sa, K, nfr, d1, d2, d3, pgp, dgp, nz)
+                    if (B.z == 4u) ODB_CONSUME(true, false, false);  // the common case: full tile, both ears on the doppler path
+                    else switch (B.z) {
+                        case 7: ODB_CONSUME(true, true, true); break;
+                        case 0: ODB_CONSUME(false, false, false); break;
+                        case 3: ODB_CONSUME(false, true, true); break;
+                        case 6: ODB_CONSUME(true, true, false); break;
+                        case 5: ODB_CONSUME(true, false, true); break;
+                        case 2: ODB_CONSUME(false, true, false); break;
+                        default: ODB_CONSUME(false, false, true); break;
+                    }
+#undef ODB_CONSUME
+                    __syncwarp();  // every lane is done with this PCM buffer before it is refilled
+                    buf ^= 1u;
+                }
+            }
+            __syncwarp();  // ... and with the staged job records and cursor rows
+        }
+
+        // park the accumulators: float2 per frame of this part at the start of the warp's region
+        if (CFG::LOOP == 0) {
+#pragma unroll
+            for (int j = 0; j < NACC; j++)
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(pcm_sa + (uint32_t)((32 * j + lane) * 8)), "l"(acc[j]) : "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < NACC / 2; j++) {
+                const int f = (j >> 2) * ODB_SPATIAL_CHUNK + 64 * (j & 3) + 2 * lane;  // accumulators 2 j, 2 j + 1 = frames f, f + 1
+                asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(pcm_sa + (uint32_t)(f * 8)), "l"(acc[2 * j]), "l"(acc[2 * j + 1]) : "memory");
+            }
+        }
+        __syncwarp();
+        // 3'. the flagged jobs of this warp's batches, literally (rare: none on C3)
+        if (A.counters == nullptr || __ldcg(A.counters + ODB_CNT_GENERAL) != 0u) {
+            float2* tile = reinterpret_cast<float2*>(smem_raw + warp * CFG::WARP_BYTES);
+            float* scratch = reinterpret_cast<float*>(smem_raw + warp * CFG::WARP_BYTES + CFG::PART_FRAMES * 8);
+            for (int bi = gp; bi < n_batches; bi += GP) {
+                const int s0 = bi * BATCH;
+                uint32_t f = ODB_JF_SKIP;
+                if (lane < BATCH && s0 + lane < n_sources) f = __ldcg(&tile_jobs[s0 + lane].flags);
+                uint32_t m = __ballot_sync(0xffffffffu, (f & ODB_JF_GENERAL) && !(f & (ODB_JF_SKIP | ODB_JF_RING)));
+                while (m) {
+                    const int q = __ffs(m) - 1;
+                    m &= m - 1u;
+                    general_part(tile_jobs + s0 + q, first_frame, CFG::PART_FRAMES, tl, lane, tile, scratch);
+                }
+            }
+        }
+        __syncthreads();
+        // 4. fold warp -> CTA in fixed order: one partial tile per CTA
+        float* pdst = A.partials + ((size_t)tl * G + blockIdx.x) * (2 * ODB_TILE_FRAMES);
+        constexpr int PART_FLOATS = 2 * CFG::PART_FRAMES;
+        for (int f = threadIdx.x; f < 2 * ODB_TILE_FRAMES; f += THREADS) {
+            const int h = f / PART_FLOATS, fh = f - h * PART_FLOATS;
+            float sum = 0.0f;
+#pragma unroll
+            for (int w = 0; w < WARPS / SPLIT; w++)
+                sum = sum + *reinterpret_cast<const float*>(smem_raw + (w * SPLIT + h) * CFG::WARP_BYTES + fh * 4);
+            __stcg(pdst + f, sum);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(A.arrive, 1ull);
+        // 5. when every CTA has arrived: sum slices of the partial tiles in index order, epilogue, store
+        const unsigned long long target = A.arrive_base + (unsigned long long)(tl + 1) * (unsigned long long)G;
+        float* red = reinterpret_cast<float*>(smem_raw);  // [RGROUPS][SMX_SLICE]
+        bool waited = false;
+        for (int sl = blockIdx.x; sl < SMX_SLICES; sl += G) {
+            if (!waited) {
+                if (threadIdx.x == 0)
+                    while (ld_acquire_u64(A.arrive) < target) __nanosleep(40);
+                __syncthreads();
+                waited = true;
+            }
+            const int fl = threadIdx.x & (SMX_SLICE - 1), grp = threadIdx.x / SMX_SLICE;
+            const int f = sl * SMX_SLICE + fl;
+            const float* p = A.partials + (size_t)tl * G * (2 * ODB_TILE_FRAMES) + f;
+            float sum = 0.0f;
+            for (int i = grp; i < G; i += RGROUPS) sum = sum + __ldcg(p + (size_t)i * (2 * ODB_TILE_FRAMES));
+            red[grp * SMX_SLICE + fl] = sum;
+            __syncthreads();
+            if (threadIdx.x < SMX_SLICE) {
+                float total = 0.0f;
+#pragma unroll
+                for (int g = 0; g < RGROUPS; g++) total = total + red[g * SMX_SLICE + fl];
+                const int frame = tl * ODB_TILE_FRAMES + f / 2;
+                if (frame < A.n_frames) {
+                    if ((A.epilogue & 0xFF) == 1) total = tanhf(total);                       // tanh.rs:24-28
+                    else if ((A.epilogue & 0xFF) == 2) total = total / (1.0f + fabsf(total));  // reinhard.rs:30-34
+                    const size_t oi = (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
+                    if (A.epilogue & ODB_EPILOGUE_I16_BIT) {  // examples/offline.rs:39 `(sample * i16::MAX as f32) as i16`
+                        int v = __float2int_rz(total * 32767.0f);
+                        v = max(-32768, min(32767, v));
+                        reinterpret_cast<short*>(A.out)[oi] = (short)v;
+                    } else {
+                        A.out[oi] = total;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();  // the warp regions are reused by the next tile
+    }
+    // the last CTA to get here tells the host (optional): everything the grid stored is visible before the flag
+    if (A.done) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long d = atomicAdd(A.done, 1ull) + 1ull;
+            if (d == A.done_base + (unsigned long long)G) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
+            }
+        }
+    }
+}
+
+}  // namespace odbk
+
+using namespace odbk;
+
+// Shapes built into the library; `odb_scene_mix_select` picks one (experiments: ODB_SMX_CFG in the environment).
+typedef SmxCfg<2, 16, 0, 4> SmxDefault;
+typedef SmxCfg<2, 16, 1, 4> SmxPairs;
+typedef SmxCfg<2, 16, 0, 8> SmxIlp8;
+typedef SmxCfg<1, 12, 0, 4> SmxWhole;
+typedef SmxCfg<1, 12, 0, 8> SmxWholeIlp8;
+
+static int g_smx_cfg = -1;
+static int smx_cfg() {
+    if (g_smx_cfg < 0) {
+        const char* e = getenv("ODB_SMX_CFG");
+        g_smx_cfg = e ? atoi(e) : 0;
+        if (g_smx_cfg < 0 || g_smx_cfg > 4) g_smx_cfg = 0;
+    }
+    return g_smx_cfg;
+}
+
+template <class CFG>
+static int smx_ctas(int n_sources, int sm_count) {
+    const int per_cta = (CFG::WARPS / CFG::SPLIT) * CFG::BATCH;
+    int want = (n_sources + per_cta - 1) / per_cta;
+    return want < 1 ? 1 : (want > sm_count ? sm_count : want);
+}
+int odb_scene_mix_ctas(int n_sources, int sm_count) {
+    switch (smx_cfg()) {
+        case 1: return smx_ctas<SmxPairs>(n_sources, sm_count);
+        case 2: return smx_ctas<SmxIlp8>(n_sources, sm_count);
+        case 3: return smx_ctas<SmxWhole>(n_sources, sm_count);
+        case 4: return smx_ctas<SmxWholeIlp8>(n_sources, sm_count);
+        default: return smx_ctas<SmxDefault>(n_sources, sm_count);
+    }
+}
+
+template <class CFG, bool STRICT>
+static cudaError_t launch_scene_mix(const OdbSceneMixArgs& a, int n_ctas, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_scene_mix<CFG, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return odb_launch_pdl(k_scene_mix<CFG, STRICT>, dim3(n_ctas), dim3(CFG::WARPS * 32), (size_t)CFG::SMEM_BYTES, st, a);
+}
+template <class CFG>
+static cudaError_t launch_scene_mix_mode(const OdbSceneMixArgs& a, int n_ctas, int mode, cudaStream_t st) {
+    return (mode & 1) ? launch_scene_mix<CFG, false>(a, n_ctas, st) : launch_scene_mix<CFG, true>(a, n_ctas, st);
+}
+
+// mode bit 0: value multiply-adds contracted to FMA
+cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mode, cudaStream_t st) {
+    OdbSceneMixArgs a = args;
+    a.nz = 0x8000000080000000ull;
+    switch (smx_cfg()) {
+        case 1: return launch_scene_mix_mode<SmxPairs>(a, n_ctas, mode, st);
+        case 2: return launch_scene_mix_mode<SmxIlp8>(a, n_ctas, mode, st);
+        case 3: return launch_scene_mix_mode<SmxWhole>(a, n_ctas, mode, st);
+        case 4: return launch_scene_mix_mode<SmxWholeIlp8>(a, n_ctas, mode, st);
+        default: return launch_scene_mix_mode<SmxDefault>(a, n_ctas, mode, st);
+    }
+}
