@@ -16,13 +16,6 @@
 #define ODB_MIXER_RESAMPLE_CAP 2112
 #define ODB_MAGIC 8388608.0f          // 2^23: ulp 1, so x +rd 2^23 = 2^23 + floor(x)
 #define ODB_MAGIC_BITS 0x4B000000u
-// k_walk_seek runs 2 * ODB_WALK_CHUNK_SPLIT threads per source (ear x chunk group); measured on C3:
-// one thread per source 15.0 us, 2 threads (split 1) 13.6 us, 4 threads 18.0 us, 8 threads 20.4 us - the shared part
-// (motion smoothing, rotation) is evaluated redundantly by every thread of a source.
-#ifndef ODB_WALK_CHUNK_SPLIT
-#define ODB_WALK_CHUNK_SPLIT 1
-#endif
-
 // Launches `kernel` so that it may overlap the tail of the previous kernel in `st` (programmatic dependent
 // launch); the kernel must call odbk::pdl_wait() before it touches anything the previous kernel wrote.
 template <class... KArgs, class... Args>

@@ -4,6 +4,7 @@
 
 #include "odb_kernels.h"
 #include "odb_math.cuh"
+#include "odb_walk.cuh"
 
 namespace odbk {
 
@@ -46,220 +47,16 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 }
 
 // ------------------------------------------------------------------------------------------
-// walk_set for the seek set (spatial.rs:191-265) plus everything of the mix closure
-// (spatial.rs:445-469) that is O(1) per source and chunk: ear states, dt, d_gain and the f64
-// cursor bookkeeping of FramesSignal::seek/sample (frames.rs:176-213).
-// 2*CS threads per source - one per (ear, group of 4/CS chunks of a tile) - because the work of one source
-// is a long chain of dependent high-latency operations (IEEE divides and square roots, f64 conversions):
-// with one thread per source the kernel took 15 us at 15 % issue utilisation. The threads of a source
-// evaluate the shared part (motion smoothing, listener rotation) redundantly and bit-identically; thread
-// (ear 0, group 0) writes the source's state. A thread reproduces the f64 cursor at the start of each of its
-// chunks with the reference's own sequence of additions (seek(prev.offset), then `t += f64(dt) * f64(m)` per
-// earlier chunk, the rewinding seek between the ears), so every (base, offset) pair is the one the serial
-// code computes. Writes one OdbJob per (tile, source) and the source's state for the next callback.
-template <int CS>
-__global__ void __launch_bounds__(128) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
-                                                    OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
-                                                    int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
-    constexpr int TPS = 2 * CS;                  // threads per source
-    constexpr int CPT = ODB_TILE_CHUNKS / CS;    // chunks of a tile per thread
+// walk_set for the seek set (spatial.rs:191-265) and the per-chunk set-up of the mix closure: see odb_walk.cuh.
+constexpr int WALK_THREADS = 128;
+__global__ void __launch_bounds__(WALK_THREADS) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
+                                                             OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
+                                                             int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+    __shared__ __align__(16) unsigned char smem[WalkSmem<WALK_THREADS>::BYTES];
     pdl_launch_dependents();  // the mix kernel may be set up now; it waits for this grid before reading jobs
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int idx = gtid / TPS, sub = threadIdx.x % TPS;
-    const int e = sub / CS, grp = sub % CS;  // this thread's ear and chunk group
-    const bool live = idx < cb.n_sources;    // dead lanes still take part in the shuffles below
-    const uint32_t slot = order[live ? idx : 0];
-    OdbSource* sp = src + slot;
-    OdbSource s;
-    load_source(s, sp);
-    const int n = cb.n_frames;
-    const float elapsed = cb.elapsed;
-    const int nt = cb.n_tiles, ns = cb.job_stride;
-    const bool leader = live && sub == 0;
-    V3 prev_position, next_position;
-    uint32_t flags;
-    const bool mixing = walk_common(sp, s, cb, slot, removed, removed_cap, prev_position, next_position, flags, leader);
-    if (!mixing && leader)
-        for (int tl = 0; tl < nt; tl++) jobs[(size_t)tl * ns + idx].flags = ODB_JF_SKIP;
-    const bool emit = mixing && live;
-    const double rate = s.rate;
-
-    // --- mix closure set-up, spatial.rs:446-468: this thread's ear
-    const float nf = (float)n;
-    const float ratef = (float)rate;  // `self.data.rate as f32` frames.rs:178
-    const int n_chunks = (n + ODB_SPATIAL_CHUNK - 1) / ODB_SPATIAL_CHUNK;
-    const EarSt ps = ear_state(prev_position, e, s.radius);
-    const EarSt nx = ear_state(next_position, e, s.radius);
-    const float eff = (elapsed + nx.offset) - ps.offset;                // :451
-    const float dt = eff / nf;                                          // :452
-    const float d_gain = (nx.gain - ps.gain) / nf;                      // :453
-    const float ds = dt * ratef;                                        // frames.rs:178
-    const bool cycle = (s.flags & ODB_SF_CYCLE) != 0;                   // the inner signal is Cycle, not FramesSignal
-    const bool fast = !cycle && fabsf(ds - 1.0f) <= ODB_F32_EPSILON;    // frames.rs:180
-    const bool general = !fast && !(ds > 0.0f && ds <= ODB_FAST_DS_MAX);
-    // the left ear's scalars, needed by the right ear's threads to replay the cursor up to their own start
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, src_lane0 = lane - sub;
-    const float ps_off_l = __shfl_sync(full, ps.offset, src_lane0);
-    const float eff_l = __shfl_sync(full, eff, src_lane0);
-    const float dt_l = __shfl_sync(full, dt, src_lane0);
-    // Cycle (cycle.rs:26-61): `t` is the cursor in samples, and where a chunk starts depends on the f32 chain of the
-    // one before it (and on where it wrapped), so the chains are walked here once without the taps; the literal mix
-    // kernel walks each chunk again from the recorded (base, offset) with them. The right ear's thread replays the
-    // left ear's pass first - the reference runs the ears one after the other on the same cursor (spatial.rs:446-466).
-    double cyc_cursor = s.t;
-    if (cycle && mixing) {
-        const double dlen = (double)s.len;
-        const unsigned long long ulen = (unsigned long long)s.len;
-        auto cyc_seek = [&](double cur, float seconds) {                // cycle.rs:57-60
-            const double r = fmod(cur + (double)seconds * rate, dlen);
-            return r < 0.0 ? r + dlen : r;                              // f64::rem_euclid
-        };
-        auto cyc_pass = [&](double cur, float dt_e, bool record) {
-            const float ds_e = dt_e * ratef;                            // cycle.rs:27
-            for (int cg = 0; cg < n_chunks; cg++) {
-                const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
-                unsigned long long cbase = (unsigned long long)cur;    // :28
-                float offset = (float)(cur - (double)cbase);            // :29
-                if (record && emit && cg / ODB_TILE_CHUNKS < nt) {
-                    OdbJob* j = jobs + (size_t)(cg / ODB_TILE_CHUNKS) * ns + idx;
-                    j->base[e][cg % ODB_TILE_CHUNKS] = (int)cbase;
-                    j->off0[e][cg % ODB_TILE_CHUNKS] = offset;
-                }
-                for (int i = 0; i < m; i++) {
-                    const unsigned long long tr = (unsigned long long)offset;              // :31
-                    const float fract = offset - (float)tr;                                // :32
-                    const unsigned long long x = cbase + tr;                               // :33
-                    if (x >= ulen) { cbase = 0; offset = (float)(x % ulen) + fract; }      // :38-40
-                    offset = offset + ds_e;                                                // :50
-                }
-                cur = (double)cbase + (double)offset;                                      // :52
-            }
-            return cur;
-        };
-        double cur = s.t;
-        if (e == 1) {
-            cur = cyc_seek(cur, ps_off_l);                              // spatial.rs:449 (left ear)
-            cur = cyc_pass(cur, dt_l, false);
-            cur = cyc_seek(cur, -eff_l - ps_off_l);                     // :465
-        }
-        cur = cyc_seek(cur, ps.offset);                                 // :449
-        cur = cyc_pass(cur, dt, true);
-        if (e == 1) {
-            cur = cyc_seek(cur, -eff - ps.offset);                      // :465
-            cur = cyc_seek(cur, elapsed);                               // :468
-        }
-        cyc_cursor = cur;
-    }
-    // cursor at the start of this thread's ear
-    double t = s.t;
-    if (e == 1) {  // left ear first: seek(prev.offset), all chunks, seek(-eff - prev.offset)  (:449-465)
-        t = t + (double)ps_off_l;
-        for (int cg = 0; cg < n_chunks; cg++) {
-            const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
-            t = t + (double)dt_l * (double)m;                           // frames.rs:198
-        }
-        t = t + (double)(-eff_l - ps_off_l);
-    }
-    t = t + (double)ps.offset;                                          // :449 seek(prev.offset)
-    // this thread's chunks of every tile
-    double tc = t;                                                      // cursor at the start of chunk `cg_done`
-    int cg_done = 0;
-    uint32_t gen_tiles = 0;                                             // bit tl: something of tile tl needs the general kernel
-    int wlo[4][2], whi[4][2];                                           // per tile and 512-frame half
-#pragma unroll
-    for (int tl = 0; tl < 4; tl++) {
-        wlo[tl][0] = wlo[tl][1] = 0x7fffffff;
-        whi[tl][0] = whi[tl][1] = -0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < CPT; k++) {
-            const int c = grp * CPT + k, cg = tl * ODB_TILE_CHUNKS + c;
-            if (tl < nt && cg < n_chunks) {
-                for (; cg_done < cg; cg_done++) tc = tc + (double)dt * (double)ODB_SPATIAL_CHUNK;  // earlier chunks are full ones
-                const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
-                const double s0 = tc * rate;                            // frames.rs:177
-                // frames.rs:179 `s0 as isize`: 32-bit conversion (saturating); any |s0| >= 2^29 is far outside every
-                // Frames block and only ever yields zeros, which the general kernel produces
-                int base = __double2int_rz(s0);
-                const float off0 = (float)(s0 - (double)base);          // frames.rs:183 / :189
-                bool g = general || off0 < 0.0f;                        // negative-fract quirk
-                if (base > (1 << 29) || base < -(1 << 29)) { g = true; base = base > 0 ? (1 << 30) : -(1 << 30); }
-                if (cycle) g = true;                                    // Cycle sources always take the literal kernel
-                if (emit && !cycle) {
-                    OdbJob* j = jobs + (size_t)tl * ns + idx;
-                    j->base[e][c] = base;
-                    j->off0[e][c] = off0;
-                }
-                // PCM indices this chain can read: [base, base + trunc(offset_{m-1}) + 1]; the f32 chain stays within
-                // 1e-2 of off0 + (m-1)*ds for m <= 256, so +4 on the f32 estimate is a safe upper bound.
-                const float span = g ? 0.0f : __fmaf_rn((float)(m - 1), ds, off0);
-                const int last = fast ? base + m : base + __float2int_rz(span) + 4;
-                const int h = c / ODB_FAST_HALF_CHUNKS;
-                wlo[tl][h] = min(wlo[tl][h], base);
-                whi[tl][h] = max(whi[tl][h], last);
-                if (g) gen_tiles |= 1u << tl;
-            }
-        }
-    }
-    // per tile: ear-level job fields, window per half and flags (reduced over the threads of the source)
-    uint32_t n_general = 0, n_fast = 0;
-#pragma unroll
-    for (int tl = 0; tl < 4; tl++) {
-        if (tl >= nt) break;
-        uint32_t f = ((gen_tiles >> tl) & 1u) ? ODB_JF_GENERAL : 0u;
-        int ws[2], wl[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int lo = wlo[tl][h], hi = whi[tl][h];
-#pragma unroll
-            for (int x = 1; x < TPS; x <<= 1) {  // over the ears and chunk groups of this source
-                lo = min(lo, __shfl_xor_sync(full, lo, x));
-                hi = max(hi, __shfl_xor_sync(full, hi, x));
-            }
-            ws[h] = 0; wl[h] = 0;
-            if (hi >= lo) {  // the half has frames
-                ws[h] = lo & ~3;
-                wl[h] = ((hi - ws[h] + 1) + 3) & ~3;
-                if (wl[h] > ODB_FAST_PCM_CAP || ws[h] < -ODB_PCM_PAD || ws[h] + wl[h] > s.len + ODB_PCM_PAD) f |= ODB_JF_GENERAL;
-            }
-        }
-        if (grp == 0) f |= fast ? (e == 0 ? ODB_JF_FAST_L : ODB_JF_FAST_R) : 0u;
-#pragma unroll
-        for (int x = 1; x < TPS; x <<= 1) f |= __shfl_xor_sync(full, f, x);
-        if (flags & ODB_SF_FIXED_GAIN) f |= ODB_JF_FIXED_GAIN | ODB_JF_GENERAL;
-        if (cycle) f |= ODB_JF_CYCLE | ODB_JF_GENERAL;
-        if (cb.force_general) f |= ODB_JF_GENERAL;
-        if (emit) {
-            OdbJob* j = jobs + (size_t)tl * ns + idx;
-            if (grp == 0) { j->ds[e] = ds; j->pg[e] = ps.gain; j->dg[e] = d_gain; }
-            if (sub == 0) {
-                j->window[0][0] = ws[0]; j->window[0][1] = (f & ODB_JF_GENERAL) ? 0 : wl[0];
-                j->window[1][0] = ws[1]; j->window[1][1] = (f & ODB_JF_GENERAL) ? 0 : wl[1];
-                j->pcm = s.pcm; j->len = s.len;
-                j->fixed_gain = s.fixed_gain;
-                j->n_frames = min(ODB_TILE_FRAMES, n - tl * ODB_TILE_FRAMES);
-                j->flags = f;
-                if (f & ODB_JF_GENERAL) n_general++; else n_fast++;
-            }
-        }
-    }
-    if (emit && sub == CS && cycle) {
-        sp->t = cyc_cursor;
-    } else if (emit && sub == CS) {  // (right ear, group 0): finish the cursor, :465-468
-        double te = t;
-        for (int cg = 0; cg < n_chunks; cg++) {
-            const int m = min(ODB_SPATIAL_CHUNK, n - cg * ODB_SPATIAL_CHUNK);
-            te = te + (double)dt * (double)m;
-        }
-        // frames.rs:199-200 stores (t * rate) as isize at the end of every sample() call; only the last store
-        // (right ear, last chunk) is observable, and the seeks that follow do not touch sample_t
-        if (n_chunks > 0) sp->sample_t = (long long)(te * rate);
-        te = te + (double)(-eff - ps.offset);                           // :465
-        te = te + (double)elapsed;                                      // :468
-        sp->t = te;
-    }
-    if (n_general) atomicAdd(counters + ODB_CNT_GENERAL, n_general);
-    if (n_fast) atomicAdd(counters + ODB_CNT_FAST, n_fast);
+    pdl_wait();               // the previous callback's kernels are done with the source table and the counters
+    walk_seek_block<WALK_THREADS>(src, order, jobs, removed, removed_cap, counters, cb, blockIdx.x * (WALK_THREADS / 2), smem,
+                                  threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -483,8 +280,9 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
                           uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
-    constexpr int CS = ODB_WALK_CHUNK_SPLIT;
-    k_walk_seek<CS><<<(cb.n_sources * 2 * CS + 127) / 128, 128, 0, st>>>(src, order, jobs, removed, removed_cap, counters, cb);
+    const int per_block = WALK_THREADS / 2;
+    odb_launch_pdl(k_walk_seek, dim3((cb.n_sources + per_block - 1) / per_block), dim3(WALK_THREADS), 0, st, src, order, jobs, removed,
+                   removed_cap, counters, cb);
 }
 
 static const int GEN_WARPS = 8;
