@@ -222,6 +222,15 @@ int odb_exchange_allreduce(odb_exchange* ex, void* dev_tile, uint32_t n_floats, 
  * group later keeps every rank's GPU busy with the next mixes instead of waiting for the slowest rank. */
 int odb_exchange_push(odb_exchange* ex, const void* dev_tile, uint32_t n_floats, void* cuda_stream);
 int odb_exchange_pull(odb_exchange* ex, void* dev_tile, uint32_t n_floats, int epilogue, void* cuda_stream);
+/* `SpatialScene::sample` (spatial.rs:376-471) of one rank's shard with the exchange folded into the callback kernel:
+ * its reduce phase stores the rank's sum into every rank's inbox over NVLink (no separate push launch, no local
+ * tile) and, once more than `lag` exchanges are outstanding, leaves the oldest one - summed over the ranks in rank
+ * order, `epilogue` applied - in `dev_out` (*out_written = 1). lag = 0: this callback's own sum (live playback);
+ * lag >= 1 (< depth): callback k - lag while callback k is mixed; the last `lag` tiles are collected with
+ * odb_exchange_pull. Scenes with buffered sources take the multi-kernel path and the stand-alone exchange kernels,
+ * with the same result. */
+int odb_scene_sample_exchange(odb_scene* scene, odb_exchange* ex, float interval, void* dev_out, uint32_t n_frames,
+                              int lag, int epilogue, int* out_written);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,7 @@ SIGNATURES = {
     "odb_exchange_allreduce": [vp, vp, u32, i32, vp],
     "odb_exchange_push": [vp, vp, u32, vp],
     "odb_exchange_pull": [vp, vp, u32, i32, vp],
+    "odb_scene_sample_exchange": [vp, vp, f32, vp, u32, i32, i32, pi32],
 }
 NON_STATUS = {"odb_last_error": (C.c_char_p, []), "odb_abi_version": (C.c_uint32, []),
               "odb_exchange_handle_size": (C.c_int, [])}

@@ -461,6 +461,14 @@ class SpatialScene(_Aggregator):
 
     channels = 2
 
+    def sample_exchange(self, exchange, interval: float, dev_ptr: int, n_frames: int, lag: int = 0, epilogue: int = 0) -> bool:
+        """One callback of this rank's shard with the multi-GPU exchange folded into the callback kernel
+        (odb_scene_sample_exchange). Returns True when `dev_ptr` received a summed tile (callback k - lag)."""
+        w = C.c_int(0)
+        check(_lib.load().odb_scene_sample_exchange(self._h, exchange._h, _f32(interval), C.c_void_p(dev_ptr), int(n_frames),
+                                                    int(lag), int(epilogue), C.byref(w)))
+        return bool(w.value)
+
     def __init__(self, ctx: Context):
         L = _lib.load()
         h = C.c_void_p()

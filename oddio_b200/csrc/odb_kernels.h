@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "odb_types.h"
+#include "odb_exchange.h"
 
 // Largest per-frame source advance (samples per output frame) the fast mix kernel stages in
 // shared memory; sources outside (0, ODB_FAST_DS_MAX] take the general kernel.
@@ -76,6 +77,15 @@ struct OdbSceneMixArgs {
     unsigned long long* host_flag;    // pinned host word that receives `seq` when the whole grid has stored its output
     unsigned long long seq;
     unsigned long long nz;            // (-0.0, -0.0), see odb_f32x2.cuh mulx
+    // Multi-GPU (odb_exchange.h; world <= 1: none of this is used). push_seq != 0: the grid's sum goes, without the
+    // epilogue, into slot `rank` of every rank's inbox as exchange push_seq instead of `out`. pull_seq != 0: the
+    // reduce phase also sums exchange pull_seq (this callback's, or an earlier one's) over the ranks in rank order,
+    // applies the epilogue and stores that into `out`.
+    odbk::ExchangePeers peers;
+    odbk::ExchangeGeom xg;
+    uint32_t push_seq, pull_seq;
+    unsigned long long* pushed;       // monotonic count of CTAs whose pushes are out (d_sync[2])
+    unsigned long long pushed_base;
 };
 int odb_scene_mix_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mode, cudaStream_t st);

@@ -3,7 +3,7 @@
 #include "odb_host.h"
 
 #define ODB_TAG_MIXED 3u
-#define ODB_MIXER_MAX_TILES 16
+#define ODB_MIXER_MAX_TILES 1024
 
 struct odb_mixer {
     uint32_t kind = ODB_KIND_MIXER;

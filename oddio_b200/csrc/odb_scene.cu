@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "odb_host.h"
+#include "odb_exchange.h"
 
 #define ODB_TAG_SEEK 1u
 #define ODB_TAG_BUFFERED 2u
@@ -46,8 +47,8 @@ struct odb_scene {
     // callback parity (the next callback's CTAs may start while this one's reducers still read), the grid's
     // arrive / done counters and the running totals the kernel compares them with.
     DevBuf<float> d_partials_fused[2];
-    DevBuf<unsigned long long> d_sync;   // [0] arrivals, [1] finished CTAs
-    unsigned long long arrive_total = 0, done_total = 0;
+    DevBuf<unsigned long long> d_sync;   // [0] arrivals, [1] finished CTAs, [2] CTAs whose exchange pushes are out
+    unsigned long long arrive_total = 0, done_total = 0, pushed_total = 0;
     bool legacy = false;                 // odb_set_kernel_variant bit 9: the multi-kernel path of round 1
     bool flag_armed = false;             // the callback just queued publishes flag_seq to h_flag when its tile is stored
     PinBuf<unsigned long long> h_flag;   // sequence number of the last callback whose tile has landed in h_out
@@ -334,12 +335,18 @@ static int ensure_idle(odb_scene* scene, DevBuf<T>& buf, size_t n) {
     return buf.ensure(n, scene->ctx->stream, false);
 }
 
+// What odb_scene_sample_exchange asks of a callback: push the tile as the exchange's next sequence number and, once
+// more than `lag` pushes are outstanding, pull the oldest one into dev_out with `epilogue`.
+struct SceneExchange {
+    odb_exchange* ex;
+    int lag, epilogue;
+    int written;  // out: dev_out received a summed tile
+};
+
 static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, uint32_t n_frames, bool as_i16 = false,
-                             bool host_flag = false) {
+                             bool host_flag = false, SceneExchange* xr = nullptr) {
     odb_ctx* ctx = scene->ctx;
     cudaStream_t st = ctx->stream, wst = scene->pipelined ? scene->wst : ctx->stream;
-    if (n_frames > ODB_MAX_FRAMES)
-        return odb_fail(ODB_E_UNSUPPORTED, "n_frames %u exceeds the %d frames one callback may render", n_frames, ODB_MAX_FRAMES);
     scene->flag_armed = false;
     ODB_CUDA(cudaSetDevice(ctx->device));
     uint32_t launches = 0;
@@ -373,6 +380,11 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     cb.force_general = scene->variant == 1;
     const int ns = cb.n_sources, nt = cb.n_tiles;
     const int nb = (int)scene->buffered.order.size();
+    // The one-launch kernel and the seek set's walk loop over any number of 1024-frame tiles (spatial.rs:456 takes any
+    // out.len()); the buffered set's walk kernel and round 1's path keep per-tile state for four tiles.
+    if (n_frames > ODB_MAX_FRAMES && (nb > 0 || scene->legacy))
+        return odb_fail(ODB_E_UNSUPPORTED, "n_frames %u exceeds the %d frames one callback may render with buffered sources", n_frames,
+                        ODB_MAX_FRAMES);
 
     for (int q = 0; q < 2; q++) {  // job counters: zeroed at creation, afterwards by k_reduce_tiles of the previous callback
         if (!scene->d_counters[q].p) {
@@ -422,8 +434,8 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         const int n_ctas = odb_scene_mix_ctas(ns, ctx->sm_count);
         ODB_TRY(ensure_idle(scene, scene->d_partials_fused[p], (size_t)nt * n_ctas * 2 * ODB_TILE_FRAMES));
         if (!scene->d_sync.p) {
-            ODB_TRY(ensure_idle(scene, scene->d_sync, 2));
-            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 2 * sizeof(unsigned long long), st));
+            ODB_TRY(ensure_idle(scene, scene->d_sync, 4));
+            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 4 * sizeof(unsigned long long), st));
         }
         OdbSceneMixArgs a;
         memset(&a, 0, sizeof a);
@@ -437,11 +449,28 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         a.arrive = scene->d_sync.p;
         a.arrive_base = scene->arrive_total;
         scene->arrive_total += (unsigned long long)nt * (unsigned long long)n_ctas;
-        if (host_flag) {
-            ODB_TRY(scene->h_flag.ensure(1));
+        if (xr) {  // multi-GPU: the reduce phase pushes (and pulls) over NVLink peer memory
+            odb_exchange* ex = xr->ex;
+            a.peers = ex->peers;
+            a.xg = ex->geom();
+            a.epilogue = xr->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0);
+            a.push_seq = ++ex->seq;
+            ex->pushed_floats[ex->seq % (uint32_t)ex->depth] = n_frames * 2;
+            a.pushed = scene->d_sync.p + 2;
+            a.pushed_base = scene->pushed_total;
+            scene->pushed_total += (unsigned long long)n_ctas;
+            if (ex->seq - ex->pulled > (uint32_t)xr->lag) {
+                a.pull_seq = ++ex->pulled;
+                xr->written = 1;
+            }
+        }
+        if (host_flag || a.pull_seq) {
             a.done = scene->d_sync.p + 1;
             a.done_base = scene->done_total;
             scene->done_total += (unsigned long long)n_ctas;
+        }
+        if (host_flag) {
+            ODB_TRY(scene->h_flag.ensure(1));
             a.host_flag = scene->h_flag.p;
             a.seq = ++scene->flag_seq;
             scene->flag_armed = true;
@@ -507,6 +536,14 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         launches++;
     }
     seg(2);
+    if (xr) {  // the multi-kernel path rendered this rank's tile into dev_out: exchange it with the stand-alone kernels
+        ODB_TRY(odb_exchange_push(xr->ex, dev_out, n_frames * 2, st));
+        if (xr->ex->seq - xr->ex->pulled > (uint32_t)xr->lag) {
+            ODB_TRY(odb_exchange_pull(xr->ex, dev_out, n_frames * 2, xr->epilogue, st));
+            xr->written = 1;
+        }
+        launches += 2;
+    }
     if (scene->pipelined) ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
     // start the read-back of what walk_set removed; folded in by a later call without waiting (touches only
     // audio-side state: no control-plane lock)
@@ -568,6 +605,31 @@ extern "C" int odb_scene_sample_device(odb_scene* scene, float interval, void* d
     ODB_TRY(scene_check(scene));
     if (!dev_out && n_frames) return odb_fail(ODB_E_INVALID, "dev_out is NULL");
     return scene_sample_impl(scene, interval, (float*)dev_out, n_frames);
+}
+// One callback of a source-sharded scene (one rank of several): mixes this rank's shard and exchanges the tile with
+// the other ranks from inside the callback kernel - its reduce phase stores the rank's sum into every rank's inbox
+// over NVLink and, once more than `lag` exchanges are outstanding, sums the oldest one over the ranks (rank order,
+// bit-identical everywhere), applies `epilogue` and leaves it in dev_out. lag = 0: this callback's own sum (live
+// playback; every rank waits for the slowest one inside the kernel); lag >= 1: a pipelined renderer receives callback
+// k - lag while callback k is mixed, and collects the last `lag` tiles with odb_exchange_pull.
+extern "C" int odb_scene_sample_exchange(odb_scene* scene, odb_exchange* ex, float interval, void* dev_out, uint32_t n_frames,
+                                         int lag, int epilogue, int* out_written) {
+    ODB_TRY(scene_check(scene));
+    if (!ex || ex->kind != ODB_KIND_EXCHANGE) return odb_fail(ODB_E_INVALID, "not an exchange handle");
+    if (!dev_out || !n_frames) return odb_fail(ODB_E_INVALID, "dev_out is NULL or n_frames is 0");
+    if (!ex->connected) return odb_fail(ODB_E_INVALID, "exchange is not connected to its peers yet");
+    if (ex->ctx != scene->ctx) return odb_fail(ODB_E_INVALID, "scene and exchange belong to different contexts");
+    if (epilogue < 0 || epilogue > 2) return odb_fail(ODB_E_INVALID, "unknown epilogue %d", epilogue);
+    if (lag < 0 || lag >= ex->depth) return odb_fail(ODB_E_INVALID, "lag %d: 0..depth-1 (%d) exchanges may await their pull", lag, ex->depth - 1);
+    if ((size_t)n_frames * 2 > ex->cap) return odb_fail(ODB_E_INVALID, "%u frames exceed the exchange's capacity of %u floats", n_frames, ex->cap);
+    if (((uintptr_t)dev_out & 15u) != 0) return odb_fail(ODB_E_INVALID, "dev_out must be 16-byte aligned");
+    if (scene->epilogue != ODB_EPILOGUE_NONE) return odb_fail(ODB_E_INVALID, "a sharded scene runs with ODB_EPILOGUE_NONE; the epilogue acts on the sum");
+    if (ex->seq - ex->pulled >= (uint32_t)ex->depth)
+        return odb_fail(ODB_E_INVALID, "%d exchanges are already pushed and not pulled (the depth given at creation)", ex->depth);
+    SceneExchange xr{ex, lag, epilogue, 0};
+    int rc = scene_sample_impl(scene, interval, (float*)dev_out, n_frames, false, false, &xr);
+    if (out_written) *out_written = xr.written;
+    return rc;
 }
 
 // ---- per-source controls / read-backs ---------------------------------------------------------------

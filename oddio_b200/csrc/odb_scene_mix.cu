@@ -297,6 +297,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
+// Epilogue (tanh.rs:24-28 / reinhard.rs:30-34 act on the finished sum) and store of one output float of tile `tl`.
+__device__ __forceinline__ void store_output(const OdbSceneMixArgs& A, const int tl, const int f, float total) {
+    const int frame = tl * ODB_TILE_FRAMES + f / 2;
+    if (frame >= A.n_frames) return;
+    if ((A.epilogue & 0xFF) == 1) total = tanhf(total);
+    else if ((A.epilogue & 0xFF) == 2) total = total / (1.0f + fabsf(total));
+    const size_t oi = (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
+    if (A.epilogue & ODB_EPILOGUE_I16_BIT) {  // examples/offline.rs:39 `(sample * i16::MAX as f32) as i16`
+        int v = __float2int_rz(total * 32767.0f);
+        v = max(-32768, min(32767, v));
+        reinterpret_cast<short*>(A.out)[oi] = (short)v;
+    } else {
+        A.out[oi] = total;
+    }
+}
+
 template <class CFG, bool STRICT>
 __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbSceneMixArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -506,14 +522,22 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(A.arrive, 1ull);
-        // 5. when every CTA has arrived: sum slices of the partial tiles in index order, epilogue, store
+        // 5. when every CTA has arrived: sum slices of the partial tiles in index order; then either epilogue + store
+        //    (one GPU) or the raw sum into slot `rank` of every rank's inbox over NVLink (exchange push_seq)
         const unsigned long long target = A.arrive_base + (unsigned long long)(tl + 1) * (unsigned long long)G;
-        float* red = reinterpret_cast<float*>(smem_raw);  // [RGROUPS][SMX_SLICE]
+        float* red = reinterpret_cast<float*>(smem_raw);  // [RGROUPS][SMX_SLICE], then [SMX_SLICE] totals
+        const bool pushing = A.push_seq != 0u;
         bool waited = false;
         for (int sl = blockIdx.x; sl < SMX_SLICES; sl += G) {
             if (!waited) {
                 if (threadIdx.x == 0)
                     while (ld_acquire_u64(A.arrive) < target) __nanosleep(40);
+                // the inbox slots about to be overwritten held exchange push_seq - depth: every peer must have pulled it
+                if (pushing && threadIdx.x >= 32 && threadIdx.x < 32 + A.xg.world && A.push_seq > (uint32_t)A.xg.depth) {
+                    const uint32_t* ack = reinterpret_cast<const uint32_t*>(A.peers.inbox[A.xg.rank] + A.xg.acks_off) +
+                                          (size_t)(threadIdx.x - 32) * A.xg.max_slices + tl;
+                    while ((int)(ld_acquire_sys(ack) - (A.push_seq - (uint32_t)A.xg.depth)) < 0) __nanosleep(20);
+                }
                 __syncthreads();
                 waited = true;
             }
@@ -524,38 +548,94 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             for (int i = grp; i < G; i += RGROUPS) sum = sum + __ldcg(p + (size_t)i * (2 * ODB_TILE_FRAMES));
             red[grp * SMX_SLICE + fl] = sum;
             __syncthreads();
+            float total = 0.0f;
             if (threadIdx.x < SMX_SLICE) {
-                float total = 0.0f;
 #pragma unroll
                 for (int g = 0; g < RGROUPS; g++) total = total + red[g * SMX_SLICE + fl];
-                const int frame = tl * ODB_TILE_FRAMES + f / 2;
-                if (frame < A.n_frames) {
-                    if ((A.epilogue & 0xFF) == 1) total = tanhf(total);                       // tanh.rs:24-28
-                    else if ((A.epilogue & 0xFF) == 2) total = total / (1.0f + fabsf(total));  // reinhard.rs:30-34
-                    const size_t oi = (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
-                    if (A.epilogue & ODB_EPILOGUE_I16_BIT) {  // examples/offline.rs:39 `(sample * i16::MAX as f32) as i16`
-                        int v = __float2int_rz(total * 32767.0f);
-                        v = max(-32768, min(32767, v));
-                        reinterpret_cast<short*>(A.out)[oi] = (short)v;
-                    } else {
-                        A.out[oi] = total;
-                    }
+            }
+            if (pushing) {
+                __syncthreads();
+                if (threadIdx.x < SMX_SLICE) red[fl] = total;
+                __syncthreads();
+                if (threadIdx.x < SMX_SLICE * A.xg.world) {  // thread (peer, float): one 64-byte run per peer
+                    const int peer = threadIdx.x / SMX_SLICE;
+                    const uint32_t par = A.push_seq % (uint32_t)A.xg.depth;
+                    float* dst = reinterpret_cast<float*>(A.peers.inbox[peer]) + ((size_t)par * A.xg.world + A.xg.rank) * A.xg.cap +
+                                 (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
+                    *dst = red[fl];
                 }
+            } else if (threadIdx.x < SMX_SLICE) {
+                store_output(A, tl, f, total);
             }
             __syncthreads();
         }
         __syncthreads();  // the warp regions are reused by the next tile
     }
-    // the last CTA to get here tells the host (optional): everything the grid stored is visible before the flag
+    if (A.push_seq != 0u) {
+        // every CTA's pushes are out (system-scope fence, then a device-scope count); the last one publishes the
+        // exchange's sequence number in every rank's inbox - one flag per tile, the stand-alone kernels' protocol
+        __threadfence_system();
+        __syncthreads();
+        __shared__ int last_pusher;
+        if (threadIdx.x == 0) {
+            const unsigned long long d = atomicAdd(A.pushed, 1ull) + 1ull;
+            last_pusher = d == A.pushed_base + (unsigned long long)G;
+            if (last_pusher) __threadfence_system();
+        }
+        __syncthreads();
+        if (last_pusher && threadIdx.x < A.xg.world) {
+            const uint32_t par = A.push_seq % (uint32_t)A.xg.depth;
+            uint32_t* flag = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.flags_off) +
+                             ((size_t)par * A.xg.world + A.xg.rank) * A.xg.max_slices;
+            for (int tl = 0; tl < A.n_tiles; tl++) st_release_sys(flag + tl, A.push_seq);
+        }
+    }
+    if (A.pull_seq != 0u) {
+        // sum of exchange pull_seq over the ranks, in rank order (bit-identical on every rank), epilogue, store.
+        // Every CTA has pushed before it waits here, so no rank can wait for a flag that depends on its own progress.
+        const uint32_t par = A.pull_seq % (uint32_t)A.xg.depth;
+        const char* mine = A.peers.inbox[A.xg.rank];
+        for (int tl = 0; tl < A.n_tiles; tl++) {
+            bool waited = false;
+            for (int sl = blockIdx.x; sl < SMX_SLICES; sl += G) {
+                if (!waited) {
+                    if (threadIdx.x < A.xg.world) {
+                        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + A.xg.flags_off) +
+                                               ((size_t)par * A.xg.world + threadIdx.x) * A.xg.max_slices + tl;
+                        while ((int)(ld_acquire_sys(flag) - A.pull_seq) < 0) __nanosleep(20);
+                    }
+                    __syncthreads();
+                    waited = true;
+                }
+                if (threadIdx.x < SMX_SLICE) {
+                    const int f = sl * SMX_SLICE + threadIdx.x;
+                    const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * A.xg.world * A.xg.cap +
+                                      (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
+                    float sum = 0.0f;
+                    for (int p = 0; p < A.xg.world; p++) sum = sum + __ldcv(in + (size_t)p * A.xg.cap);
+                    store_output(A, tl, f, sum);
+                }
+            }
+        }
+    }
+    // the last CTA to get here acknowledges the pulled exchange to the peers and tells the host (both optional):
+    // everything the grid stored or read is ordered before the flags
     if (A.done) {
         __threadfence_system();
         __syncthreads();
+        __shared__ int last_done;
         if (threadIdx.x == 0) {
             const unsigned long long d = atomicAdd(A.done, 1ull) + 1ull;
-            if (d == A.done_base + (unsigned long long)G) {
-                __threadfence_system();
-                *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
+            last_done = d == A.done_base + (unsigned long long)G;
+            if (last_done) __threadfence_system();
+        }
+        __syncthreads();
+        if (last_done) {
+            if (A.pull_seq != 0u && threadIdx.x < A.xg.world) {  // the peers may overwrite this slot `depth` exchanges on
+                uint32_t* ack = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.acks_off) + (size_t)A.xg.rank * A.xg.max_slices;
+                for (int sl = 0; sl < A.xg.max_slices; sl++) st_release_sys(ack + sl, A.pull_seq);
             }
+            if (A.host_flag && threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
         }
     }
 }

@@ -1,7 +1,7 @@
 """The multi-GPU tile exchange over NVLink peer memory (csrc/odb_exchange.cu) through the C ABI.
 
 * one rank: the exchange is the identity plus the epilogue (every code path of the kernel but the remote stores);
-* two ranks (needs a box with >= 2 GPUs, skipped otherwise): two processes, one GPU each, shard a SpatialScene
+* 2 / 4 / 8 ranks (each needs a box with that many GPUs, skipped otherwise): one process per GPU, shard a SpatialScene
   round-robin, mix their shards with the CUDA path and sum the tiles with the exchange; rank 0 checks the result
   against the CPU oracle's unsharded mix on the same inputs, callback after callback (both inbox parities),
   and that both ranks hold bit-identical tiles.
@@ -75,17 +75,46 @@ def _worker(rank, world, port, n_src, n_frames, n_callbacks, q):
     vel = [rng.uniform(-30, 30, 3).astype(np.float32) for _ in range(n_src)]
     mine = shard_sources(n_src, rank, world)
     frames = [odb.Frames.from_slice(48000, p, ctx) for p in pcms]
-    ctl, scene = odb.SpatialScene.new(ctx)
-    for s in mine:
-        ctl.play(odb.FramesSignal(frames[s % 4], 1.0), odb.SpatialOptions(pos[s], vel[s], 0.1))
+
+    def shard_scene():
+        ctl, scene = odb.SpatialScene.new(ctx)
+        for s in mine:
+            ctl.play(odb.FramesSignal(frames[s % 4], 1.0), odb.SpatialOptions(pos[s], vel[s], 0.1))
+        return ctl, scene
+
     interval = float(np.float32(1.0) / np.float32(48000))
     tile = torch.zeros((n_frames, 2), device=f"cuda:{rank}", dtype=torch.float32)
+    # (a) the callback renders this rank's tile, the stand-alone kernels exchange it
+    ctl, scene = shard_scene()
     outs = []
     for _ in range(n_callbacks):
         scene.sample_device(interval, tile.data_ptr(), n_frames)
         ex.allreduce(tile.data_ptr(), 2 * n_frames, 0)
         ctx.synchronize()
         outs.append(tile.cpu().numpy().copy())
+    # (b) the exchange folded into the callback kernel, live (lag 0) and pipelined (lag 1, the last tile pulled by the
+    # stand-alone kernel): the same per-rank sums in the same rank order, so bit-identical to (a)
+    for lag in (0, 1):
+        ex2 = PeerExchange.from_torch(ctx, 2 * n_frames, depth=3)
+        ctl2, scene2 = shard_scene()
+        got = []
+        for k in range(n_callbacks):
+            tile.fill_(-7.0)
+            wrote = scene2.sample_exchange(ex2, interval, tile.data_ptr(), n_frames, lag=lag)
+            ctx.synchronize()
+            assert wrote == (k >= lag)
+            if wrote:
+                got.append(tile.cpu().numpy().copy())
+        for _ in range(lag):
+            ex2.pull(tile.data_ptr(), 2 * n_frames)
+            ctx.synchronize()
+            got.append(tile.cpu().numpy().copy())
+        assert len(got) == n_callbacks
+        for k in range(n_callbacks):
+            assert np.array_equal(got[k], outs[k]), f"rank {rank}: in-kernel exchange (lag {lag}) differs at callback {k}"
+        dist.barrier()
+        scene2.close()
+        ex2.close()
     # the pipelined form: `depth` pushes in flight, pulls late and into other buffers, slots reused several times
     nf = 2 * n_frames
     for rep in range(4):
@@ -113,16 +142,17 @@ def _worker(rank, world, port, n_src, n_frames, n_callbacks, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_scene_matches_the_oracle(oracle):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_scene_matches_the_oracle(oracle, world):
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs on one box")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs on one box")
     import torch.multiprocessing as mp
 
     from helpers import assert_mix_close, rand_in_shell, synth_pcm
 
-    n_src, n_frames, n_cb, world = 37, 1024, 4, 2
+    n_src, n_frames, n_cb = 37 + 16 * world, 1024, 4
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
@@ -155,5 +185,46 @@ def test_two_rank_sharded_scene_matches_the_oracle(oracle):
         full.play(o.FramesSignal(fr[s % 4], 1.0), pos[s], vel[s], 0.1)
     for k in range(n_cb):
         ref = o.run(full, 48000, n_frames)
-        assert np.array_equal(got[0][k], got[1][k]), "ranks must hold bit-identical sums"
+        for r in range(1, world):
+            assert np.array_equal(got[0][k], got[r][k]), "ranks must hold bit-identical sums"
         assert_mix_close(got[0][k], ref, ref.astype(np.float64))
+
+
+def test_single_rank_in_kernel_exchange_equals_plain_sample(oracle):
+    """World size 1: odb_scene_sample_exchange is the plain callback plus the epilogue on the (one-term) sum."""
+    import torch
+
+    import oddio_b200 as odb
+    from helpers import rand_in_shell, synth_pcm
+    from oddio_b200.sharding import PeerExchange
+
+    ctx = odb.init(0)
+    rng = np.random.default_rng(5)
+    pcms = [synth_pcm(rng, 60000, 48000) for _ in range(3)]
+    frames = [odb.Frames.from_slice(48000, p, ctx) for p in pcms]
+    pos = [rand_in_shell(rng, 2, 60) for _ in range(50)]
+    vel = [rng.uniform(-30, 30, 3).astype(np.float32) for _ in range(50)]
+
+    def scene():
+        ctl, sc = odb.SpatialScene.new(ctx)
+        for i in range(50):
+            ctl.play(odb.FramesSignal(frames[i % 3], 1.0), odb.SpatialOptions(pos[i], vel[i], 0.1))
+        return ctl, sc
+
+    interval = float(np.float32(1.0) / np.float32(48000))
+    for n_frames, epi in ((1024, 0), (700, 1), (2048, 2)):
+        ex = PeerExchange(ctx, 0, 1, 2 * n_frames, depth=2)
+        (_, a), (_, b) = scene(), scene()
+        tile = torch.zeros((n_frames, 2), device="cuda", dtype=torch.float32)
+        for _ in range(3):
+            want = a.sample(interval, n_frames).astype(np.float64)
+            assert b.sample_exchange(ex, interval, tile.data_ptr(), n_frames, lag=0, epilogue=epi)
+            ctx.synchronize()
+            got = tile.cpu().numpy()
+            if epi == 0:
+                assert np.array_equal(got, want.astype(np.float32))
+            elif epi == 1:
+                np.testing.assert_allclose(got, np.tanh(want), rtol=0, atol=4e-7)
+            else:
+                assert np.array_equal(got, (want.astype(np.float32) / (np.float32(1.0) + np.abs(want.astype(np.float32)))))
+        a.close(); b.close(); ex.close()

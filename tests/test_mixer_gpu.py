@@ -157,3 +157,19 @@ def test_empty_mixer(oracle, odb, ctx):
     pair = MixerPair(oracle, odb, ctx, 2)
     ref, _, out = pair.step(48000, 128)
     np.testing.assert_array_equal(out, ref)
+
+
+def test_callback_of_48000_frames(oracle, odb, ctx):
+    """mixer.rs:109-117 chunks any out.len() through its 1024-frame staging buffer."""
+    rng = np.random.default_rng(4800)
+    rate, n = 48000, 48000
+    pair = MixerPair(oracle, odb, ctx, 2)
+    pcms = [synth_pcm(rng, 2 * n * 2 + 4096, rate, 2) for _ in range(3)]
+    for i in range(9):
+        pair.play(rate, pcms[i % 3], 0.01 * i, speed=float(rng.uniform(0.7, 1.6)) if i % 3 else None,
+                  gain=float(rng.uniform(0.1, 1.0)))
+    for _ in range(2):
+        ref, ref64, out = pair.step(rate, n)
+        assert_mix_close(out, ref, ref64)
+    for it in pair.items:
+        assert it["dev_frames_control"].cursor()[0] == it["ref_frames_signal"].t

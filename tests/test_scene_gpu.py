@@ -1,8 +1,9 @@
 """Parity of the device SpatialScene (seek path) against the CPU oracle, through the C ABI.
 
-Kernel variants (odb_set_kernel_variant): 0 = staged kernel, strict arithmetic (default); 1 = literal
-general kernel for every source; 2 = staged kernel with FMA-contracted value operations; +0x100 = per-source
-set-up kernels on a second stream (overlapping the previous callback's mix).
+Kernel variants (odb_set_kernel_variant): 0 = staged mix, strict arithmetic; 1 = the literal path for every
+source; 2 = staged mix with FMA-contracted value operations (the library's default); + 0x100 = per-source
+set-up kernels on a second stream (overlapping the previous callback's mix); + 0x200 = round 1's multi-kernel
+callback (walk, k_mix_fast, k_mix_general, k_reduce_tiles) instead of the one-launch kernel.
 
 Bars: f64 time cursors bit-exact; a single source's contribution bit-exact in the
 strict build; mixed output within 1e-5 * max(|ref|, RMS)."""
@@ -35,7 +36,7 @@ def cursors_equal(pair):
         assert t == so.t, f"f64 cursor differs: {t!r} vs {so.t!r}"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 0x200, 0x202])
 def test_single_source_bit_exact(oracle, odb, ctx, variant):
     """One moving source: no summation-order freedom, so the output must equal the oracle bit for bit."""
     rng = np.random.default_rng(1)
@@ -46,7 +47,7 @@ def test_single_source_bit_exact(oracle, odb, ctx, variant):
     pair.play(rate, pcm, 0.5, [3.0, 1.0, -2.0], [10.0, -3.0, 4.0])
     for n in (256, 1024, 100, 1, 777, 2048, 4096, 3000):
         ref, ref64, out = pair.step(rate, n)
-        if variant == 2:  # value multiply-adds contracted to FMA: <= 1e-5 relative, indices still exact
+        if variant & 0xFF == 2:  # value multiply-adds contracted to FMA: <= 1e-5 relative, indices still exact
             assert_mix_close(out, ref, ref64)
         else:
             np.testing.assert_array_equal(out, ref)
@@ -64,14 +65,14 @@ def test_static_source_fast_path_bit_exact(oracle, odb, ctx, variant):
     pair.play(rate, pcm, 0.25, [0.0, 0.0, -5.0], [0.0, 0.0, 0.0])
     for n in (256, 512, 1024, 33):
         ref, ref64, out = pair.step(rate, n)
-        if variant == 2:
+        if variant & 0xFF == 2:
             assert_mix_close(out, ref, ref64)
         else:
             np.testing.assert_array_equal(out, ref)
         cursors_equal(pair)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 0x100, 0x102])
+@pytest.mark.parametrize("variant", [0, 1, 2, 0x100, 0x102, 0x200, 0x201, 0x202, 0x300])
 @pytest.mark.parametrize("n_src,n_frames", [(8, 256), (300, 256), (1024, 256), (515, 1024), (64, 2048), (33, 1500)])
 def test_many_sources(oracle, odb, ctx, variant, n_src, n_frames):
     rng = np.random.default_rng(100 + n_src)
@@ -96,7 +97,7 @@ def test_many_sources(oracle, odb, ctx, variant, n_src, n_frames):
         assert cnt == {"general": 0, "staged": n_src * tiles, "resampled": 0, "ring_literal": 0}
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 0x200, 0x202])
 def test_start_before_zero_and_run_off_the_end(oracle, odb, ctx, variant):
     """Sources that start at negative time (zeros, then the k == -1 pair, frames.rs:118-122) and
     sources that run past their last frame and get dropped once the tail has propagated
@@ -182,3 +183,30 @@ def test_playback_position_readback(oracle, odb, ctx):
         pair.step(48000, 480)
         assert pair.dev_controls[i].playback_position() == pair.ref_signals[i].playback_position()
         assert pair.dev_controls[i].is_finished() == pair.ref_signals[i].control_is_finished()
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("n_frames", [8192, 48000, 5000])
+def test_callbacks_longer_than_four_tiles(oracle, odb, ctx, variant, n_frames):
+    """spatial.rs:456 takes any out.len(): the walk and the one-launch kernel loop over the 1024-frame tiles."""
+    rng = np.random.default_rng(8000 + n_frames)
+    rate = 48000
+    pair = ScenePair(oracle, odb, ctx)
+    pair.dev.set_kernel_variant(variant)
+    pcms = [synth_pcm(rng, 48000 + int(1.3 * n_frames * 2) + 4096, rate) for _ in range(4)]
+    for i in range(19):
+        pair.play(rate, pcms[i % 4], 1.0, rand_in_shell(rng, 2.0, 100.0), rng.uniform(-30, 30, 3).astype(F32))
+    pair.play(rate, pcms[0], 1.0, [0.0, 0.0, -3.0], [0.0, 0.0, 0.0])   # static: the ds ~= 1 path
+    pair.play(rate, pcms[1], 0.5, rand_in_shell(rng, 2.0, 50.0), rng.uniform(-30, 30, 3).astype(F32), fixed_gain_db=-6.0)  # literal path
+    for _ in range(2):
+        ref, ref64, out = pair.step(rate, n_frames)
+        assert_mix_close(out, ref, ref64)
+        cursors_equal(pair)
+    one = ScenePair(oracle, odb, ctx)   # a single moving source: bit for bit in the strict build
+    one.dev.set_kernel_variant(variant)
+    one.play(rate, pcms[2], 1.0, [30.0, 5.0, -20.0], [-20.0, 3.0, 11.0])
+    ref, ref64, out = one.step(rate, n_frames)
+    if variant == 0:
+        np.testing.assert_array_equal(out, ref)
+    else:
+        assert_mix_close(out, ref, ref64)
