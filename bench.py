@@ -201,6 +201,381 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
+class Rig:
+    """One rank's share of a C3 scene of `n_total` sources: device-synthesised PCM (a private Frames block per source),
+    a scene factory, and - for N > 1 - the peer-memory exchange."""
+
+    def __init__(self, args, odb, torch, dist, ctx, stream, dev, rank, world, n_total, steps, warmup, spare=0):
+        from oddio_b200.sharding import shard_sources
+
+        self.args, self.odb, self.torch, self.dist = args, odb, torch, dist
+        self.ctx, self.stream, self.dev, self.rank, self.world = ctx, stream, dev, rank, world
+        self.N, self.M = n_total, args.frames
+        self.pos, self.vel, freq, phase = scene_geometry(n_total)
+        self.mine = shard_sources(n_total, rank, world)  # round-robin shard (SURVEY.md section 8e)
+        n_local = self.n_local = len(self.mine)
+        M, K, W = self.M, steps, warmup
+        # Every source plays its own PCM and every callback reads fresh samples, so the PCM resident in HBM grows with
+        # K + W (19.6 GB for 65 536 sources and the default 16 + 3). If the requested number of steps does not fit this
+        # GPU, the timed steps are cut to what fits and the JSON line says so - a shorter honest run instead of an
+        # allocation failure.
+        self.note = ""
+        free_b, _total_b = torch.cuda.mem_get_info(dev)
+        per_callback = int(np.ceil(DS_MAX * M)) * 4 * max(1, n_local)
+        fit = int((0.8 * free_b - pcm_len(M, 0) * 4 * max(1, n_local)) // per_callback)
+        if world > 1:  # every rank must time the same number of steps
+            t_fit = torch.tensor([fit], device=dev, dtype=torch.int64)
+            dist.all_reduce(t_fit, op=dist.ReduceOp.MIN)
+            fit = int(t_fit.item())
+        fit -= spare  # callbacks a pass may run on top of W + K (the exchange warm-up of the grouped modes)
+        if K + W > fit:
+            if fit - W < 1:
+                raise SystemExit(f"bench: {n_local} sources x {M} frames do not fit this GPU even for one timed step")
+            self.note = f"--steps {K} needs more PCM than fits in HBM; timed {fit - W} steps instead"
+            K = fit - W
+        self.K, self.W = K, W
+        L = self.L = pcm_len(M, K + W + spare)
+        t0 = time.time()
+        self.frames = []
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(0x0DD10 + rank)
+        kk = torch.arange(L, device=dev, dtype=torch.float32)
+        B = 512
+        for b0 in range(0, n_local, B):
+            ids = self.mine[b0:b0 + B]
+            w = torch.tensor(2 * np.pi * freq[ids] / RATE, device=dev, dtype=torch.float32)[:, None]
+            ph = torch.tensor(phase[ids], device=dev, dtype=torch.float32)[:, None]
+            x = 0.5 * torch.sin(w * kk[None, :] + ph) + 0.05 * (2 * torch.rand((len(ids), L), device=dev, generator=gen) - 1)
+            x = x.contiguous()
+            torch.cuda.synchronize(dev)
+            for r in range(len(ids)):
+                self.frames.append(odb.Frames.from_device(RATE, 1, x[r].data_ptr(), L, ctx))
+            del x
+        self.pcm_gb = n_local * L * 4 / 1e9
+        self.setup_s = time.time() - t0
+        self.interval = float(np.float32(1.0) / np.float32(RATE))  # oddio::run, lib.rs:91
+
+    def new_scene(self):
+        odb = self.odb
+        ctl, scene = odb.SpatialScene.new(self.ctx)
+        scene.set_kernel_variant(self.args.variant)
+        handles = []
+        for i, g in enumerate(self.mine):
+            handles.append(ctl.play(odb.FramesSignal(self.frames[i], START_S), odb.SpatialOptions(self.pos[g], self.vel[g], 0.1)))
+        return ctl, scene, handles
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize(self.dev)
+
+    def release(self):
+        for f in self.frames:
+            f.release()
+        self.frames = []
+
+
+def timed_device_pass(rig, clk, exchange_mode, reduce_every=1, depth=4, lag=1):
+    """K callbacks back to back on the device (inputs resident in HBM), CUDA events on the launch stream.
+    exchange_mode (N > 1): "kernel" = the exchange folded into the callback kernel (odb_scene_sample_exchange; every
+    callback pushes its tile and receives the sum of callback k - lag), "peer" = stand-alone push / pull kernels once
+    per `reduce_every` callbacks, "nccl" = torch.distributed all-reduce once per `reduce_every` callbacks."""
+    torch, dist, world, dev, stream = rig.torch, rig.dist, rig.world, rig.dev, rig.stream
+    M, K, W = rig.M, rig.K, rig.W
+    from oddio_b200.sharding import PeerExchange
+
+    note = ""
+    with torch.cuda.stream(stream):
+        ctl, scene, handles = rig.new_scene()
+        if world == 1:
+            tiles = [torch.zeros((M, 2), device=dev, dtype=torch.float32) for _ in range(2)]
+            k_no = [0]
+
+            def step():
+                scene.sample_device(rig.interval, tiles[k_no[0] & 1].data_ptr(), M)
+                k_no[0] += 1
+
+            def drain():
+                pass
+
+            def last_tile():
+                return tiles[(k_no[0] - 1) & 1]
+            launches_per_step = None
+        elif exchange_mode == "kernel":
+            exch = PeerExchange.from_torch(rig.ctx, M * 2, depth=max(2, min(8, depth)))
+            tiles = [torch.zeros((M, 2), device=dev, dtype=torch.float32) for _ in range(lag + 2)]
+            k_no, got = [0], [0]
+
+            def step():
+                if scene.sample_exchange(exch, rig.interval, tiles[got[0] % len(tiles)].data_ptr(), M, lag=lag):
+                    got[0] += 1
+                k_no[0] += 1
+
+            def drain():
+                while got[0] < k_no[0]:
+                    exch.pull(tiles[got[0] % len(tiles)].data_ptr(), M * 2, 0, stream.cuda_stream)
+                    got[0] += 1
+
+            def last_tile():
+                return tiles[(got[0] - 1) % len(tiles)]
+            launches_per_step = None
+        else:
+            R = max(1, reduce_every)
+            NG = max(2, min(8, depth))
+            groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(NG)]
+            comm = torch.cuda.Stream(device=dev, priority=-1)
+            peer = exchange_mode == "peer"
+            exch = None
+            if peer:
+                try:
+                    exch = PeerExchange.from_torch(rig.ctx, R * M * 2, depth=NG)
+                except rig.odb.OddioError as e:  # raised on every rank alike
+                    peer, exch = False, None
+                    note = f" (peer-memory exchange unavailable, fell back to NCCL: {str(e)[:120]})"
+            pending = [False] * NG
+            mixed = [torch.cuda.Event() for _ in range(NG)]
+            reduced = [torch.cuda.Event() for _ in range(NG)]
+            k_no = [0]
+
+            def exchange(g):
+                if peer:
+                    exch.push(groups[g].data_ptr(), R * M * 2, comm.cuda_stream)
+                    pending[g] = True
+                else:
+                    with torch.cuda.stream(comm):
+                        dist.all_reduce(groups[g])
+
+            def finish(g):
+                if peer and pending[g]:
+                    exch.pull(groups[g].data_ptr(), R * M * 2, 0, stream.cuda_stream)
+                    pending[g] = False
+
+            def step():
+                k = k_no[0]
+                k_no[0] += 1
+                g, slot = (k // R) % NG, k % R
+                if slot == 0:
+                    stream.wait_event(reduced[g])
+                    finish(g)
+                scene.sample_device(rig.interval, groups[g][slot].data_ptr(), M)
+                if slot == R - 1:
+                    mixed[g].record(stream)
+                    comm.wait_event(mixed[g])
+                    exchange(g)
+                    reduced[g].record(comm)
+
+            def drain():
+                k = k_no[0]
+                if k % R:
+                    g = (k // R) % NG
+                    mixed[g].record(stream)
+                    comm.wait_event(mixed[g])
+                    exchange(g)
+                    reduced[g].record(comm)
+                    k_no[0] += R - k % R
+                stream.wait_stream(comm)
+                for i in range(NG):
+                    finish((k_no[0] // R + i) % NG)
+
+            def last_tile():
+                return groups[((k_no[0] - 1) // R) % NG][(k_no[0] - 1) % R]
+            launches_per_step = (2.0 / R) if peer else 0.0
+        for _ in range(W):
+            step()
+        drain()
+        if world > 1 and exchange_mode != "kernel":  # every group buffer / inbox slot has been through the exchange once
+            for _ in range(NG * R):
+                step()
+            drain()
+        own = scene.last_launch_count()
+        rig.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with clk:
+            e0.record(stream)
+            h0 = time.perf_counter()
+            for _ in range(K):
+                step()
+            drain()
+            host_us = (time.perf_counter() - h0) / K * 1e6  # CPU time to queue one callback (the GPU runs behind)
+            e1.record(stream)
+            rig.barrier()
+        ms = e0.elapsed_time(e1)
+        counters = scene.last_job_counters()
+        # the rare source with exactly one ear on FramesSignal's ds ~= 1 path takes the literal path
+        assert counters["general"] <= max(1, rig.n_local // 1000), f"{counters['general']} jobs fell back to the literal path"
+        assert scene.len() == rig.n_local, "a source finished during the timed region"
+        checksum = float(last_tile().abs().sum().item())
+        scene.close()
+        if world > 1 and exch is not None:
+            exch.close()
+    return {"ms": ms, "host_us": host_us, "counters": counters, "checksum": checksum, "note": note,
+            "launches_per_step": own + (launches_per_step or 0.0)}
+
+
+def kernel_time_pass(rig):
+    """The dominant kernel's device time: a separate pass with CUDA events around the kernel (odb_set_profiling)."""
+    torch, stream = rig.torch, rig.stream
+    with torch.cuda.stream(stream):
+        ctl, scene, handles = rig.new_scene()
+        scene.set_profiling(True)
+        tile = torch.zeros((rig.M, 2), device=rig.dev, dtype=torch.float32)
+        kms = []
+        for i in range(rig.W + rig.K):
+            scene.sample_device(rig.interval, tile.data_ptr(), rig.M)
+            if i >= rig.W:
+                kms.append(scene.last_mix_kernel_ms())
+        torch.cuda.synchronize(rig.dev)
+        scene.close()
+    return float(np.mean(kms))
+
+
+def e2e_pass(rig, exchange_mode):
+    """The same K callbacks through the calls a host makes, one at a time: the audio thread renders into HOST memory
+    (one GPU: odb_scene_run with a host tile; N > 1: the in-kernel exchange with lag 0 writes the summed tile into
+    pinned host memory) while a control thread calls set_motion on 1/16 of the sources per callback - the reference's
+    two-thread architecture (README, examples/realtime.rs). H2D of the updates and D2H of the tile are inside the
+    timed region; nothing is pipelined: callback k + 1 starts after the tile of callback k is in host memory."""
+    torch, dist, odb, world, dev, stream = rig.torch, rig.dist, rig.odb, rig.world, rig.dev, rig.stream
+    M, K, W = rig.M, rig.K, rig.W
+    from oddio_b200.sharding import PeerExchange
+
+    with torch.cuda.stream(stream):
+        ctl, scene, handles = rig.new_scene()
+        host_out = np.zeros((M, 2), dtype=np.float32)
+        n_upd = max(1, rig.n_local // 16)
+        ids_all = [h._src for h in handles]
+        rng = np.random.default_rng(7 + rig.rank)
+        upd = []
+        for s in range(W + K):
+            sel = rng.choice(rig.n_local, n_upd, replace=False)
+            gl = rig.mine[sel]
+            ids = (C.c_uint64 * n_upd)(*[ids_all[i] for i in sel])
+            # the game thread nudges positions along the trajectory it already announced
+            p = (rig.pos[gl] + rig.vel[gl] * np.float32((s + 1) * M / RATE)).astype(np.float32)
+            upd.append((ids, p, rig.vel[gl].copy()))
+        go = threading.Semaphore(0)
+
+        def control_thread():
+            for s in range(W + K):
+                go.acquire()
+                ids, p, v = upd[s]
+                ctl.set_motion_ids(ids, n_upd, p, v)
+
+        exch, pinned, dtile = None, None, None
+        if world > 1:
+            if exchange_mode == "nccl":
+                dtile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+            else:
+                exch = PeerExchange.from_torch(rig.ctx, M * 2, depth=2)
+                pinned = torch.zeros((M, 2), dtype=torch.float32, pin_memory=True)
+
+        def step_e2e():
+            go.release()
+            if world == 1:
+                odb.run(scene, RATE, host_out)
+            elif exch is not None:  # the summed tile lands in pinned host memory straight from the kernel's reduce phase
+                scene.sample_exchange(exch, rig.interval, pinned.data_ptr(), M, lag=0)
+                rig.ctx.synchronize()
+                host_out[:] = pinned.numpy()
+            else:
+                scene.sample_device(rig.interval, dtile.data_ptr(), M)
+                dist.all_reduce(dtile)
+                host_out[:] = dtile.cpu().numpy()
+
+        th = threading.Thread(target=control_thread, daemon=True)
+        th.start()
+        for _ in range(W):
+            step_e2e()
+        rig.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        th.join()
+        rig.barrier()
+        e2e_s = time.perf_counter() - t0
+        scene.close()
+        if exch is not None:
+            exch.close()
+    return e2e_s, n_upd
+
+
+def parity_pass(rig, n_sample=4096, callbacks=2):
+    """N > 1, after the timed passes: a 4096-source scene sharded over the ranks like the timed one. Per callback,
+    (i) the exchanged tile is bit-identical on every rank and equals the rank-order f32 sum of the per-rank tiles
+    gathered with NCCL, (ii) rank 0 checks it against the CPU oracle's unsharded mix."""
+    torch, dist, odb, world, dev, stream, rank = rig.torch, rig.dist, rig.odb, rig.world, rig.dev, rig.stream, rig.rank
+    from oddio_b200.sharding import PeerExchange, shard_sources
+
+    M = rig.M
+    n = min(n_sample, rig.N)
+    pos, vel, freq, phase = scene_geometry(rig.N)
+    # trimmed private blocks: block i holds just what `callbacks` callbacks can touch (see tests/test_fullsize_gpu.py)
+    dist_m = np.linalg.norm(pos[:n].astype(np.float64), axis=1)
+    off = np.floor(RATE * (START_S - dist_m / 343.0)).astype(np.int64) - 128
+    start = START_S - off.astype(np.float64) / RATE
+    L = 128 + int(DS_MAX * M * callbacks) + 512
+    kk = np.arange(L, dtype=np.float64)
+
+    def block(i):
+        r = np.random.default_rng(1000 + i)
+        return (0.5 * np.sin(2 * np.pi * freq[i] / RATE * (kk + off[i]) + phase[i]) + 0.05 * r.uniform(-1, 1, L)).astype(np.float32)
+
+    mine = shard_sources(n, rank, world)
+    out = {"sources": n, "callbacks": callbacks}
+    with torch.cuda.stream(stream):
+        def shard_scene():
+            ctl, sc = odb.SpatialScene.new(rig.ctx)
+            sc.set_kernel_variant(rig.args.variant)
+            for i in mine:
+                ctl.play(odb.FramesSignal(odb.Frames.from_slice(RATE, block(i), rig.ctx), float(start[i])),
+                         odb.SpatialOptions(pos[i], vel[i], 0.1))
+            return ctl, sc
+        _c1, plain = shard_scene()
+        _c2, fused = shard_scene()
+        exch = PeerExchange.from_torch(rig.ctx, M * 2, depth=2)
+        tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+        xt = torch.zeros((M, 2), device=dev, dtype=torch.float32)
+        ref_scene = None
+        if rank == 0:
+            from oracle import pyoracle as o
+
+            ref_scene = o.SpatialScene()
+            keep = []
+            for i in range(n):
+                fr = o.Frames.from_slice(RATE, block(i))
+                keep.append(fr)
+                ref_scene.play(o.FramesSignal(fr, float(start[i])), pos[i], vel[i], 0.1)
+        ok_sum, ok_same, worst = True, True, 0.0
+        for _ in range(callbacks):
+            plain.sample_device(rig.interval, tile.data_ptr(), M)
+            fused.sample_exchange(exch, rig.interval, xt.data_ptr(), M, lag=0)
+            torch.cuda.synchronize(dev)
+            parts = [torch.zeros_like(tile) for _ in range(world)]
+            dist.all_gather(parts, tile)
+            want = parts[0].clone()
+            for r in range(1, world):
+                want = want + parts[r]  # rank order, f32
+            ok_sum = ok_sum and bool(torch.equal(want, xt))
+            same = [torch.zeros_like(xt) for _ in range(world)]
+            dist.all_gather(same, xt)
+            ok_same = ok_same and all(bool(torch.equal(same[0], t)) for t in same)
+            if rank == 0:
+                ref = o.run(ref_scene, RATE, M).astype(np.float64)
+                ref64 = ref_scene.out64(M)
+                got = xt.cpu().numpy().astype(np.float64)
+                rms = float(np.sqrt(np.mean(ref64 ** 2)))
+                worst = max(worst, float(np.max(np.abs(got - ref) / (1e-5 * np.maximum(np.abs(ref), rms) + 1e-30))),
+                            float(np.max(np.abs(got - ref64) / (1e-5 * np.maximum(np.abs(ref64), rms) + 1e-30))))
+        flags = torch.tensor([int(ok_sum), int(ok_same)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        plain.close(); fused.close(); exch.close()
+    out.update({"exchanged_equals_rank_order_sum_bit_exact": bool(flags[0].item()), "identical_on_all_ranks": bool(flags[1].item()),
+                "vs_oracle_worst_over_tolerance": worst, "tolerance": "1e-5 * max(|ref|, RMS) vs the reference-order f32 sum and the f64 truth",
+                "vs_oracle_ok": worst <= 1.0})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -221,268 +596,62 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = odb.Context(local, stream=stream.cuda_stream)  # our kernels and NCCL share one stream: no extra events
     clk = ClockSampler(local, enabled=(rank == 0)).start()  # initialises during the set-up below, far from the timed region
+    M = args.frames
+    mode = args.exchange if world > 1 else "none"
 
-    from oddio_b200.sharding import shard_sources
-
-    M, K, W = args.frames, args.steps, args.warmup
-    N = args.sources * world if args.scaling == "weak" else args.sources  # sources of the whole job
-    pos, vel, freq, phase = scene_geometry(N)
-    mine = shard_sources(N, rank, world)  # round-robin shard
-    n_local = len(mine)
-    # Every source plays its own PCM and every callback reads fresh samples, so the PCM resident in HBM grows with
-    # K + W (19.6 GB for the default 16 + 3). If the requested number of steps does not fit this GPU, the timed
-    # steps are cut to what fits and the JSON line says so in "steps" and config.note - a shorter honest run
-    # instead of an allocation failure.
-    steps_note = ""
-    free_b, _total_b = torch.cuda.mem_get_info(dev)
-    per_callback = int(np.ceil(DS_MAX * M)) * 4 * max(1, n_local)
-    fit = int((0.8 * free_b - pcm_len(M, 0) * 4 * max(1, n_local)) // per_callback)
-    if world > 1:  # every rank must time the same number of steps
-        t_fit = torch.tensor([fit], device=dev, dtype=torch.int64)
-        dist.all_reduce(t_fit, op=dist.ReduceOp.MIN)
-        fit = int(t_fit.item())
-    if K + W > fit:
-        if fit - W < 1:
-            raise SystemExit(f"bench: {n_local} sources x {M} frames do not fit this GPU even for one timed step")
-        steps_note = f"--steps {K} needs more PCM than fits in HBM; timed {fit - W} steps instead"
-        K = fit - W
-    L = pcm_len(M, K + W)
-
-    # ---- synthetic PCM, generated on the device, one private Frames block per source ------------------
-    t_setup = time.time()
-    frames = []
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(0x0DD10 + rank)
-    kk = torch.arange(L, device=dev, dtype=torch.float32)
-    B = 512
-    for b0 in range(0, n_local, B):
-        ids = mine[b0:b0 + B]
-        w = torch.tensor(2 * np.pi * freq[ids] / RATE, device=dev, dtype=torch.float32)[:, None]
-        ph = torch.tensor(phase[ids], device=dev, dtype=torch.float32)[:, None]
-        x = 0.5 * torch.sin(w * kk[None, :] + ph) + 0.05 * (2 * torch.rand((len(ids), L), device=dev, generator=gen) - 1)
-        x = x.contiguous()
-        torch.cuda.synchronize(dev)
-        for r in range(len(ids)):
-            frames.append(odb.Frames.from_device(RATE, 1, x[r].data_ptr(), L, ctx))
-        del x
-    pcm_gb = n_local * L * 4 / 1e9
-
-    def new_scene():
-        ctl, scene = odb.SpatialScene.new(ctx)
-        scene.set_kernel_variant(args.variant)
-        handles = []
-        for i, g in enumerate(mine):
-            handles.append(ctl.play(odb.FramesSignal(frames[i], START_S), odb.SpatialOptions(pos[g], vel[g], 0.1)))
-        return ctl, scene, handles
-
-    interval = float(np.float32(1.0) / np.float32(RATE))  # oddio::run, lib.rs:91
-    # Offline rendering batches R consecutive callbacks per exchange: the sum over ranks is linear, so one
-    # all-reduce of R tiles equals R all-reduces of one tile. R = 1 is the live-playback shape.
-    # --exchange peer (default): the library's own one-kernel push/sum over NVLink peer memory; --exchange nccl:
-    # torch.distributed all-reduce. Either way R tiles per exchange (--reduce-every; 1 = the live-playback shape).
-    peer = world > 1 and args.exchange == "peer"
-    R = 1 if world == 1 else max(1, args.reduce_every)
-    # NG group buffers in flight: a rank may run up to NG - 1 exchanges ahead of the slowest one, which absorbs the
-    # host-side jitter of the other ranks instead of paying max-over-ranks at every exchange
-    NG = max(2, min(8, args.exchange_depth)) if world > 1 else 2
-    groups = [torch.zeros((R, M, 2), device=dev, dtype=torch.float32) for _ in range(NG)]
-    comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
-    exch = None
-    exchange_note = ""
-    if peer:
-        from oddio_b200.sharding import PeerExchange
-
-        try:
-            exch = PeerExchange.from_torch(ctx, R * M * 2, depth=NG)
-        except odb.OddioError as e:  # raised on every rank alike (e.g. CUDA IPC not permitted in this container)
-            peer, exch = False, None
-            exchange_note = f" (peer-memory exchange unavailable, fell back: {str(e)[:120]})"
-
-    pending = [False] * NG  # peer exchange: group g has been pushed and not yet pulled
-
-    def exchange(g):
-        """Sum of group g over the ranks, started on the `comm` stream. Peer exchange: only the push half (it never
-        waits for another rank); the pull half is queued one group later, right before group g's buffer is reused,
-        when every rank has long pushed - a pipelined renderer consumes the summed tiles one group late."""
-        if peer:
-            exch.push(groups[g].data_ptr(), R * M * 2, comm.cuda_stream)
-            pending[g] = True
-        else:
-            with torch.cuda.stream(comm):
-                dist.all_reduce(groups[g])
-
-    def finish_exchange(g):
-        if peer and pending[g]:
-            exch.pull(groups[g].data_ptr(), R * M * 2, 0, stream.cuda_stream)
-            pending[g] = False
-    mixed = [torch.cuda.Event() for _ in range(NG)]
-    reduced = [torch.cuda.Event() for _ in range(NG)]
-    step_no = [0]
-
-    def step_device(scene):
-        """One callback: mix this rank's shard into slot k%R of group (k/R)%2 on `stream`; after R callbacks
-        the NCCL sum of the group runs on `comm` and overlaps the next group's mixes."""
-        k = step_no[0]
-        step_no[0] += 1
-        g, slot = (k // R) % NG, k % R
-        if world > 1 and slot == 0:
-            stream.wait_event(reduced[g])  # the group buffer is free again once its previous exchange has left
-            finish_exchange(g)             # (peer exchange: the sum of the group's previous contents lands here)
-        scene.sample_device(interval, groups[g][slot].data_ptr(), M)
-        if world > 1 and slot == R - 1:
-            mixed[g].record(stream)
-            comm.wait_event(mixed[g])
-            exchange(g)
-            reduced[g].record(comm)
-
-    def drain():
+    def maxr(x):
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
         if world > 1:
-            k = step_no[0]
-            if k % R:  # flush a partial group
-                g = (k // R) % NG
-                mixed[g].record(stream)
-                comm.wait_event(mixed[g])
-                exchange(g)
-                reduced[g].record(comm)
-                step_no[0] += R - k % R
-            stream.wait_stream(comm)
-            for i in range(NG):  # oldest first: pulls follow push order
-                finish_exchange((step_no[0] // R + i) % NG)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-
-    # ---- (1) device-resident throughput ------------------------------------------------------------------
-    with torch.cuda.stream(stream):
-        ctl, scene, handles = new_scene()
-        setup_s = time.time() - t_setup
-        for _ in range(W):
-            step_device(scene)
-        drain()
-        if world > 1:  # both buffers / inbox parities of the exchange have been through it once before the clock starts
-            first = (step_no[0] // R) % NG  # keep the rotation: the timed loop continues with this group
-            for i in range(NG):
-                g = (first + i) % NG
-                mixed[g].record(stream)
-                comm.wait_event(mixed[g])
-                exchange(g)
-                reduced[g].record(comm)
-            stream.wait_stream(comm)
-            for i in range(NG):
-                finish_exchange((first + i) % NG)
-        # our kernels per callback: the scene's own, plus the exchange's push and pull once per R callbacks (an NCCL
-        # all-reduce is not ours and is not counted)
-        launches_per_step = scene.last_launch_count() + ((2.0 / R) if peer else 0.0)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with clk:
-            e0.record(stream)
-            h0 = time.perf_counter()
-            for _ in range(K):
-                step_device(scene)
-            drain()
-            host_enqueue_us = (time.perf_counter() - h0) / K * 1e6  # CPU time to queue one callback (GPU runs behind)
-            e1.record(stream)
-            barrier()
-        ms = e0.elapsed_time(e1)
-        counters = scene.last_job_counters()
-        # the rare source with exactly one ear on FramesSignal's ds ~= 1 path takes the literal kernel
-        assert counters["general"] <= max(1, n_local // 1000), f"{counters['general']} jobs fell back to the general kernel"
-        assert scene.len() == n_local, "a source finished during the timed region"
-        checksum = float(groups[((step_no[0] - 1) // R) % NG][(step_no[0] - 1) % R].abs().sum().item())
-        clk.stop()
-        scene.close()
-
-        # ---- (2) mix-kernel device time for the roofline (separate pass: events around the kernel) ------------
-        ctl, scene, handles = new_scene()
-        scene.set_profiling(True)
-        kms = []
-        for i in range(W + K):
-            step_device(scene)
-            if i >= W:
-                kms.append(scene.last_mix_kernel_ms())
-        drain()
-        scene.close()
-
-        # ---- (3) end to end through the host-buffer call --------------------------------------------------------
-        def run_e2e():
-            ctl, scene, handles = new_scene()
-            host_out = np.zeros((M, 2), dtype=np.float32)
-            n_upd = max(1, n_local // 16)
-            ids_all = [h._src for h in handles]
-            rng = np.random.default_rng(7 + rank)
-            upd = []
-            for s in range(W + K):
-                sel = rng.choice(n_local, n_upd, replace=False)
-                gl = mine[sel]
-                ids = (C.c_uint64 * n_upd)(*[ids_all[i] for i in sel])
-                # the game thread nudges positions along the trajectory it already announced
-                p = (pos[gl] + vel[gl] * np.float32((s + 1) * M / RATE)).astype(np.float32)
-                upd.append((ids, p, vel[gl].copy()))
-
-            # The reference's architecture has two threads: a control ("game") thread that calls set_motion and the
-            # audio thread that calls run (README, examples/realtime.rs). Same here: the control thread queues the
-            # updates of callback s while the audio thread is inside odb_scene_run of callback s (ctypes releases the GIL).
-            # The audio thread paces the control thread with a semaphore (one batch of updates per callback) and never
-            # waits for it.
-            go = threading.Semaphore(0)
-
-            def control_thread():
-                for s in range(W + K):
-                    go.acquire()
-                    ids, p, v = upd[s]
-                    ctl.set_motion_ids(ids, n_upd, p, v)
-
-            e2e_tile = torch.zeros((M, 2), device=dev, dtype=torch.float32)
-
-            def step_e2e(s):
-                go.release()
-                if world == 1:
-                    odb.run(scene, RATE, host_out)  # host tile: H2D of the queued updates and D2H of the result inside
-                else:  # this rank's shard into a device tile, summed over the ranks, then read back
-                    scene.sample_device(interval, e2e_tile.data_ptr(), M)
-                    if peer:
-                        exch.allreduce(e2e_tile.data_ptr(), M * 2, 0, stream.cuda_stream)
-                    else:
-                        dist.all_reduce(e2e_tile)
-                    host_out[:] = e2e_tile.cpu().numpy()
-
-            th = threading.Thread(target=control_thread, daemon=True)
-            th.start()
-            for s in range(W):
-                step_e2e(s)
-            barrier()
-            t0 = time.perf_counter()
-            for s in range(W, W + K):
-                step_e2e(s)
-            th.join()
-            barrier()
-            e2e_s = time.perf_counter() - t0
-            scene.close()
-            return e2e_s
-
-
-        e2e_s = float("nan") if args.skip_e2e else run_e2e()
-        n_upd = max(1, n_local // 16)
-
-    # max over ranks
-    times = torch.tensor([ms, e2e_s * 1e3, float(np.mean(kms))], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = [float(x) for x in times.tolist()]
+    # ---- the headline: the fixed scene of --sources sources split over the ranks (strong scaling), or --sources per rank
+    N = args.sources * world if args.scaling == "weak" else args.sources
+    spare = 0 if world == 1 else 8 * max(2, min(8, args.exchange_depth)) + 8
+    rig = Rig(args, odb, torch, dist, ctx, stream, dev, rank, world, N, args.steps, args.warmup, spare)
+    K, W = rig.K, rig.W
+    main = timed_device_pass(rig, clk, mode, reduce_every=args.reduce_every, depth=args.exchange_depth, lag=args.lag)
+    clk.stop()
+    ms = maxr(main["ms"])
+    kernel_ms = maxr(kernel_time_pass(rig))
+    e2e_s, n_upd = (float("nan"), max(1, rig.n_local // 16)) if args.skip_e2e else e2e_pass(rig, mode)
+    e2e_ms = maxr(e2e_s * 1e3)
+    extras = {}
+    parity = None
+    if world > 1 and not args.skip_extras:
+        parity = parity_pass(rig)
+        # the offline-rendering shape: stand-alone exchange of 8 callbacks at a time, overlapped with the next mixes
+        off = timed_device_pass(rig, ClockSampler(local, enabled=False), "peer", reduce_every=8, depth=args.exchange_depth)
+        extras["strong_reduce_every_8"] = {"value": N * M / (maxr(off["ms"]) / K * 1e-3), "unit": "source-frames/s",
+                                           "note": "same scene; tiles summed by the stand-alone push / pull kernels once per 8 callbacks"}
+        if args.scaling == "strong":
+            rig.release()
+            rig_w = Rig(args, odb, torch, dist, ctx, stream, dev, rank, world, args.sources * world, args.steps, args.warmup,
+                        max(args.reduce_every, 1) * max(2, min(8, args.exchange_depth)) + 8)
+            wk = timed_device_pass(rig_w, ClockSampler(local, enabled=False), mode, reduce_every=args.reduce_every,
+                                   depth=args.exchange_depth, lag=args.lag)
+            extras["weak"] = {"value": rig_w.N * M / (maxr(wk["ms"]) / rig_w.K * 1e-3), "unit": "source-frames/s",
+                              "sources": rig_w.N, "sources_per_gpu": rig_w.n_local, "steps": rig_w.K,
+                              "note": f"{args.sources} sources per GPU, exchange every callback (in the callback kernel)"}
+            rig_w.release()
 
     out = None
     if rank == 0:
         peak, peak_src = peaks()
-        # algorithmic bytes (SURVEY.md §8d): the PCM window, once per source per callback: 4 B * M * mean(ds)
-        r = pos[mine] / np.linalg.norm(pos[mine], axis=1, keepdims=True)
-        ds_mean = float(np.mean(1.0 - np.sum(vel[mine] * r, axis=1) / 343.0))
-        alg_bytes = 4.0 * M * ds_mean * n_local
+        # algorithmic bytes: the PCM window, once per source per callback: 4 B * M * mean(ds)
+        mine = rig.mine
+        r = rig.pos[mine] / np.linalg.norm(rig.pos[mine], axis=1, keepdims=True)
+        ds_mean = float(np.mean(1.0 - np.sum(rig.vel[mine] * r, axis=1) / 343.0))
+        alg_bytes = 4.0 * M * ds_mean * rig.n_local
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         value = N * M / (ms / K * 1e-3)
+        how = {"none": "", "kernel": f", tiles summed every callback from inside the callback kernel: its reduce phase stores the rank's sum "
+                                     f"into every rank's inbox over NVLink peer memory ({M * 8} B per rank pair) and sums callback k - {args.lag} "
+                                     "in rank order (odb_scene_sample_exchange)",
+               "peer": f", tiles summed by the library's stand-alone peer-memory kernels over NVLink, one exchange per {args.reduce_every} callbacks, overlapped with the next mixes",
+               "nccl": f", one NCCL all-reduce per {args.reduce_every} callbacks, overlapped with the next mixes"}[mode] + main["note"]
+        legacy = bool(args.variant & 0x200)
+        kname = ("k_mix_fast" if legacy else "k_scene_mix") + ("<strict>" if (args.variant & 0xFF) == 0 else "<fma>")
         out = {
             "metric": "source-frames/sec (N sources x buffer frames) spatial mix",
             "value": value, "unit": "source-frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -490,29 +659,34 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
                                    f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
-                       "sources": N, "sources_per_gpu": n_local, "frames": M, "rate": RATE,
-                       "parallelism": f"source-shard x{world}" + ("" if world == 1 else (
-                           f", tiles summed by the library's peer-memory kernel over NVLink, one exchange per {R} callbacks ({R * M * 8} B per rank pair), overlapped with the next mixes"
-                           if peer else f", one NCCL all-reduce per {R} callbacks ({R * M * 8} B), overlapped with the next mixes{exchange_note}")),
+                       "sources": N, "sources_per_gpu": rig.n_local, "frames": M, "rate": RATE,
+                       "parallelism": f"source-shard x{world}" + how,
                        "l2": "inputs larger than L2: every callback reads fresh PCM "
-                             f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {pcm_gb:.1f} GB PCM resident per GPU)",
-                       "kernel_variant": ("staged, strict (bit-exact per-source contributions)" if args.variant == 0 else
-                                          "staged, value multiply-adds contracted to FMA (cursors and indices bit-exact)"),
-                       "jobs_last_callback": counters, **({"note": steps_note} if steps_note else {}), "host_enqueue_us_per_step": round(host_enqueue_us, 1),
-                       "setup_s": round(setup_s, 1)},
+                             f"({alg_bytes / 1e6:.0f} MB per callback per GPU; {rig.pcm_gb:.1f} GB PCM resident per GPU)",
+                       "kernel_variant": ("one-launch callback kernel" if not legacy else "round 1's multi-kernel callback") + (
+                           ", strict (bit-exact per-source contributions)" if (args.variant & 0xFF) == 0 else
+                           ", value multiply-adds contracted to FMA (cursors and indices bit-exact; the library default)"),
+                       "jobs_last_callback": main["counters"], **({"note": rig.note} if rig.note else {}),
+                       "host_enqueue_us_per_step": round(main["host_us"], 1), "setup_s": round(rig.setup_s, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
-                    "h2d_bytes_per_step": n_upd * 32, "d2h_bytes_per_step": M * 8 + 4,
+                    "h2d_bytes_per_step": n_upd * 32, "d2h_bytes_per_step": M * 8 + 8,
                     "note": ("audio thread: odb_scene_run with a host tile" if world == 1 else
-                             "audio thread: odb_scene_sample_device on this rank's shard, the tiles summed over the ranks every callback (push + pull), read back to the host")
+                             "audio thread: odb_scene_sample_exchange (lag 0) on this rank's shard, the summed tile written to pinned host memory by the kernel"
+                             if mode != "nccl" else "audio thread: sample_device + NCCL all-reduce + D2H copy")
                             + "; control thread: set_motion on 1/16 of the sources every callback"},
-            "gpu_launches": int(round(launches_per_step * K)),
+            "gpu_launches": int(round(main["launches_per_step"] * K)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("k_mix_fast", n_local), "kernel": "k_mix_fast<strict>" if args.variant == 0 else "k_mix_fast<fma>", "kernel_ms": kernel_ms,
-                         "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "kernel_share_of_step": kernel_ms / (ms / K)},
-            "checksum": checksum,
+                         "traffic": ncu_traffic("k_scene_mix" if not legacy else "k_mix_fast", rig.n_local), "kernel": kname,
+                         "kernel_ms": kernel_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "kernel_share_of_step": kernel_ms / (ms / K),
+                         "whole_callback_frac": alg_bytes / (ms / K * 1e-3) / 1e9 / peak},
+            "checksum": main["checksum"],
         }
+        if parity is not None:
+            out["parity"] = parity
+        if extras:
+            out["extra"] = extras
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, threads=1, n=args.cpu_sources)
         emit(out)
@@ -593,12 +767,15 @@ def main():
     ap.add_argument("--cpu-sources", type=int, default=2048, help="sources in the bounded CPU sample")
     ap.add_argument("--ref-sources", type=int, default=8192, help="sources in the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = --sources per GPU (default), strong = --sources in total")
-    ap.add_argument("--reduce-every", type=int, default=8, help="N > 1: callbacks per exchange of the tiles (1 = live playback)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = the fixed scene of --sources sources split over the ranks, weak = --sources per GPU")
+    ap.add_argument("--lag", type=int, default=1, help="N > 1, --exchange kernel: callback k receives the summed tile of callback k - lag")
+    ap.add_argument("--skip-extras", action="store_true", help="N > 1: headline only (no parity pass, no weak-scaling / reduce-every-8 passes)")
+    ap.add_argument("--reduce-every", type=int, default=1, help="N > 1, --exchange peer|nccl: callbacks per exchange of the tiles")
     ap.add_argument("--exchange-depth", type=int, default=4, help="N > 1: group buffers (exchanges) in flight, 2..8")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how the per-GPU tiles are summed (peer = the library's NVLink peer-memory kernel, every callback)")
+    ap.add_argument("--exchange", default="kernel", choices=["kernel", "peer", "nccl"],
+                    help="N > 1: how the per-GPU tiles are summed: kernel (default) = from inside the callback kernel over NVLink peer "
+                         "memory, every callback; peer = the library's stand-alone push / pull kernels; nccl = torch.distributed")
     ap.add_argument("--variant", type=lambda v: int(v, 0), default=2,
                     help="2 (default, also the library's) = value ops contracted to FMA, 0 = strict (bit-exact per-source "
                          "contributions); | 0x200 = round 1's multi-kernel callback instead of the one-launch kernel")

@@ -253,7 +253,10 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
     // inserts: set.rs:159-165 — appended to the table in send order
     size_t ni = ins_slot.size();
     if (ni) {
-        ODB_TRY(d_src.ensure(slots.size(), st, true));
+        if (slots.size() > d_src.cap) {
+            std::lock_guard<std::mutex> gl(grow_mu);
+            ODB_TRY(d_src.ensure(slots.size(), st, true));
+        }
         ODB_TRY(h_stage_src.ensure(ni));
         ODB_TRY(h_stage_slot.ensure(ni));
         ODB_TRY(d_stage_src.ensure(ni, st, false));
@@ -308,8 +311,24 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
         ODB_CUDA(cudaMemcpyAsync(d_params.p, h_params.p, np * sizeof(OdbParamMsg), cudaMemcpyHostToDevice, st));
         odb_launch_scatter_params(d_src.p, d_params.p, (int)np, st);
         (*launches)++;
-        for (auto& m : params) { slots[m.slot].speed_idx = -1; slots[m.slot].gain_idx = -1; }
+        for (auto& m : params)
+            if (m.slot != 0xFFFFFFFFu) { slots[m.slot].speed_idx = -1; slots[m.slot].gain_idx = -1; }
         params.clear();
+    }
+    // removal report ring: every live source reports at most once, so a ring of >= order.size() never overflows
+    if (removed_cap < order.size() + ins_slot.size() || !d_removed.p) {
+        if (d_removed.p) ODB_TRY(fold_removed(ctx, st, true, nullptr));
+        uint32_t ncap = 1024;
+        while (ncap < 2 * (order.size() + ins_slot.size())) ncap *= 2;
+        d_removed.release();
+        ODB_TRY(d_removed.ensure((size_t)ncap + 1, st, false));
+        ODB_CUDA(cudaMemsetAsync(d_removed.p, 0, sizeof(uint32_t), st));
+        ODB_TRY(h_removed.ensure(ncap));
+        ODB_TRY(h_removed_count.ensure(1));
+        if (!ev_removed) ODB_CUDA(cudaEventCreateWithFlags(&ev_removed, cudaEventDisableTiming));
+        removed_cap = ncap;
+        removed_consumed = 0;
+        count_in_flight = false;
     }
     if (order_dirty) {
         size_t n = order.size();
@@ -322,21 +341,6 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
             ODB_CUDA(cudaMemcpyAsync(d_order.p, h_order.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         }
         order_dirty = false;
-    }
-    // removal report ring: every live source reports at most once, so a ring of >= order.size() never overflows
-    if (removed_cap < order.size() || !d_removed.p) {
-        if (d_removed.p) ODB_TRY(fold_removed(ctx, st, true, nullptr));
-        uint32_t ncap = 1024;
-        while (ncap < 2 * order.size()) ncap *= 2;
-        d_removed.release();
-        ODB_TRY(d_removed.ensure((size_t)ncap + 1, st, false));
-        ODB_CUDA(cudaMemsetAsync(d_removed.p, 0, sizeof(uint32_t), st));
-        ODB_TRY(h_removed.ensure(ncap));
-        ODB_TRY(h_removed_count.ensure(1));
-        if (!ev_removed) ODB_CUDA(cudaEventCreateWithFlags(&ev_removed, cudaEventDisableTiming));
-        removed_cap = ncap;
-        removed_consumed = 0;
-        count_in_flight = false;
     }
     return ODB_OK;
 }
@@ -363,13 +367,22 @@ int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait, std::mutex
         ODB_CUDA(q);
     }
     count_in_flight = false;
-    const uint32_t count = h_removed_count.p[0];
+    return fold_count(ctx, st, h_removed_count.p[0], mu);
+}
+
+int SourceSet::fold_count(odb_ctx* ctx, cudaStream_t st, uint32_t count, std::mutex* mu) {
     uint32_t n_new = count - removed_consumed;
     if (n_new == 0) return ODB_OK;
     if (n_new > removed_cap) return odb_fail(ODB_E_INVALID, "internal: removal ring overflow (%u reports)", n_new);
-    // from here on the membership (order, slots) changes: that is shared with the control side
+    // from here on the membership (order, slots) changes: that is shared with the control side. The audio thread
+    // only tries the lock (bounded): if a control call holds it, these removals are folded by the next callback.
     std::unique_lock<std::mutex> lk;
-    if (mu) lk = std::unique_lock<std::mutex>(*mu);
+    if (mu) {
+        lk = std::unique_lock<std::mutex>(*mu, std::defer_lock);
+        bool got = false;
+        for (int i = 0; i < 512 && !(got = lk.try_lock()); i++) odb_cpu_pause();
+        if (!got) return ODB_OK;
+    }
     // fetch the report entries (only happens on callbacks where sources actually finished)
     const uint32_t mask = removed_cap - 1, first = removed_consumed & mask;
     const uint32_t span1 = n_new < removed_cap - first ? n_new : removed_cap - first;
@@ -402,6 +415,10 @@ int SourceSet::fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait, std::mutex
             if (sh.motion_idx >= 0) h_mot[mot_buf].p[sh.motion_idx].slot = 0xFFFFFFFFu;
             else if (sh.motion_idx <= -2) motions[(size_t)(-sh.motion_idx - 2)].slot = 0xFFFFFFFFu;
             sh.motion_gen = 0;
+        }
+        if (sh.speed_idx >= 0 || sh.gain_idx >= 0 || sh.stop_requested) {  // ... nor may a queued set_speed / set_gain / stop
+            for (auto& m : params)
+                if (m.slot == slot) m.slot = 0xFFFFFFFFu;
         }
         sh.motion_idx = sh.speed_idx = sh.gain_idx = -1;
         if (sh.frames) ctx->frames_unref(sh.frames);

@@ -90,25 +90,32 @@ struct ArenaBlock {
     int live = 0;
 };
 
-// The audio thread announces itself before it takes a control-plane mutex; batched control calls check the flag
-// between chunks and stand back, so the callback never queues behind a long batch (std::mutex is not fair).
+static inline void odb_cpu_pause() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+}
+// The audio thread never blocks on the control plane (signal.rs:11-13): it announces itself - batched control calls
+// check the flag between chunks of 256 messages and stand back - and then TRIES the control-plane mutex a bounded
+// number of times. If a control call still holds it (a thread preempted inside a control call, say), the callback
+// goes ahead with the state it already has: what was queued is applied one callback later, which the reference's
+// swap / spsc transports allow as well (a message written while `refresh` runs is seen by the next one,
+// swap.rs:57-64). `held()` says whether the control-plane queues may be touched.
 struct AudioLock {
     std::mutex& mu;
-    AudioLock(std::mutex& m, std::atomic<int>& wants) : mu(m) {
+    bool got = false;
+    AudioLock(std::mutex& m, std::atomic<int>& wants, int tries = 512) : mu(m) {
         wants.fetch_add(1, std::memory_order_acq_rel);
-        mu.lock();
+        for (int i = 0; i < tries && !(got = mu.try_lock()); i++) odb_cpu_pause();
         wants.fetch_sub(1, std::memory_order_acq_rel);
     }
-    ~AudioLock() { mu.unlock(); }
+    bool held() const { return got; }
+    ~AudioLock() { if (got) mu.unlock(); }
     AudioLock(const AudioLock&) = delete;
     AudioLock& operator=(const AudioLock&) = delete;
 };
 static inline void odb_yield_to_audio(const std::atomic<int>& wants) {
-    while (wants.load(std::memory_order_acquire) > 0) {
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
+    while (wants.load(std::memory_order_acquire) > 0) odb_cpu_pause();
 }
 
 struct odb_ctx {
@@ -190,6 +197,8 @@ struct SourceSet {
     cudaEvent_t ev_removed = nullptr;   // recorded behind the count read-back
     bool count_in_flight = false;
     std::vector<int> pos_of_slot;       // position of a slot in `order`, -1 if not a member
+    std::mutex grow_mu;                 // held while the source table is reallocated (rare: the set outgrew it) and while a
+                                        // control-side read-back copies a record out of it
 
     uint32_t alloc_slot();
     odb_source handle_of(uint32_t slot, uint32_t tag) const;
@@ -207,5 +216,7 @@ struct SourceSet {
     // `mu` (may be NULL when the caller already holds it) is the owner's control-plane mutex: it is taken only
     // when there is something to fold, so a callback without removals never contends with the control thread.
     int fold_removed(odb_ctx* ctx, cudaStream_t st, bool wait, std::mutex* mu);
+    // the same with the report count already in hand (the callback kernel stored it into h_removed_count)
+    int fold_count(odb_ctx* ctx, cudaStream_t st, uint32_t count, std::mutex* mu);
     void release_all(odb_ctx* ctx);
 };

@@ -76,6 +76,8 @@ struct OdbSceneMixArgs {
     unsigned long long done_base;
     unsigned long long* host_flag;    // pinned host word that receives `seq` when the whole grid has stored its output
     unsigned long long seq;
+    const uint32_t* removed_count;    // optional: the walk kernel's removal-report count ...
+    uint32_t* removed_count_host;     // ... copied to this pinned host word before host_flag is raised
     unsigned long long nz;            // (-0.0, -0.0), see odb_f32x2.cuh mulx
     // Multi-GPU (odb_exchange.h; world <= 1: none of this is used). push_seq != 0: the grid's sum goes, without the
     // epilogue, into slot `rank` of every rank's inbox as exchange push_seq instead of `out`. pull_seq != 0: the

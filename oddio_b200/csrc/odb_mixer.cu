@@ -107,8 +107,10 @@ static int mixer_sample_impl(odb_mixer* mixer, float interval, float* dev_out, u
     uint32_t launches = 0;
     {
         AudioLock lk(mixer->mu, mixer->audio_wants);
-        ODB_TRY(mixer->set.fold_removed(ctx, st, false, nullptr));
-        ODB_TRY(mixer->set.apply(ctx, st, &launches));  // set.update(), mixer.rs:94
+        if (lk.held()) {  // otherwise: a control call is in progress; what it queues is applied by the next callback
+            ODB_TRY(mixer->set.fold_removed(ctx, st, false, nullptr));
+            ODB_TRY(mixer->set.apply(ctx, st, &launches));  // set.update(), mixer.rs:94
+        }
     }
     OdbCallback cb;
     memset(&cb, 0, sizeof cb);

@@ -51,6 +51,9 @@ struct odb_scene {
     unsigned long long arrive_total = 0, done_total = 0, pushed_total = 0;
     bool legacy = false;                 // odb_set_kernel_variant bit 9: the multi-kernel path of round 1
     bool flag_armed = false;             // the callback just queued publishes flag_seq to h_flag when its tile is stored
+    bool count_by_kernel = false;        // ... and the seek set's removal-report count to seek.h_removed_count
+    const void* pinned_probe = nullptr;  // the caller buffer odb_scene_sample last looked up, and what it found
+    float* pinned_dev = nullptr;
     PinBuf<unsigned long long> h_flag;   // sequence number of the last callback whose tile has landed in h_out
     unsigned long long flag_seq = 0;
     DevBuf<float> d_out;
@@ -348,6 +351,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     odb_ctx* ctx = scene->ctx;
     cudaStream_t st = ctx->stream, wst = scene->pipelined ? scene->wst : ctx->stream;
     scene->flag_armed = false;
+    scene->count_by_kernel = false;
     ODB_CUDA(cudaSetDevice(ctx->device));
     uint32_t launches = 0;
     const int p = (int)(scene->callback_no & 1);
@@ -360,14 +364,16 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         const double tl0 = g_trace ? now_us() : 0.0;
         AudioLock lk(scene->mu, scene->audio_wants);
         const double tl1 = g_trace ? now_us() : 0.0;
-        // removals reported by earlier callbacks whose read-back has landed (never waits for the device)
-        ODB_TRY(scene->seek.fold_removed(ctx, wst, false, nullptr));
-        ODB_TRY(scene->buffered.fold_removed(ctx, wst, false, nullptr));
-        ODB_TRY(scene->buffered.apply(ctx, wst, &launches));                // set.update(), spatial.rs:379
-        ODB_TRY(scene->seek.apply(ctx, wst, &launches));                    // set.update(), spatial.rs:437
-        if (g_trace && scene->callback_no > 4) { scene->tr_lock += tl1 - tl0; scene->tr_apply += now_us() - tl1; }
         cb.prev_rot = scene->rot_received;                                 // spatial.rs:382-386
-        if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
+        if (lk.held()) {  // otherwise: a control call is in progress; what it queues is applied by the next callback
+            // removals reported by earlier callbacks whose read-back has landed (never waits for the device)
+            ODB_TRY(scene->seek.fold_removed(ctx, wst, false, nullptr));
+            ODB_TRY(scene->buffered.fold_removed(ctx, wst, false, nullptr));
+            ODB_TRY(scene->buffered.apply(ctx, wst, &launches));            // set.update(), spatial.rs:379
+            ODB_TRY(scene->seek.apply(ctx, wst, &launches));                // set.update(), spatial.rs:437
+            if (scene->rot_fresh) { scene->rot_received = scene->rot_pending; scene->rot_fresh = false; }
+        }
+        if (g_trace && scene->callback_no > 4) { scene->tr_lock += tl1 - tl0; scene->tr_apply += now_us() - tl1; }
         cb.rot = scene->rot_received;
     }
     double ts = g_trace ? now_us() : 0.0;
@@ -469,12 +475,23 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             a.done_base = scene->done_total;
             scene->done_total += (unsigned long long)n_ctas;
         }
+        bool count_by_kernel = false;
         if (host_flag) {
-            ODB_TRY(scene->h_flag.ensure(1));
+            if (!scene->h_flag.p) {
+                ODB_TRY(scene->h_flag.ensure(1));
+                scene->h_flag.p[0] = 0ull;
+            }
             a.host_flag = scene->h_flag.p;
             a.seq = ++scene->flag_seq;
             scene->flag_armed = true;
+            if (scene->seek.d_removed.p && scene->seek.h_removed_count.p && !scene->seek.count_in_flight) {
+                // the grid's last CTA also hands the host the removal-report count: no copy-engine operation behind the kernel
+                a.removed_count = scene->seek.d_removed.p;
+                a.removed_count_host = scene->seek.h_removed_count.p;
+                count_by_kernel = true;
+            }
         }
+        scene->count_by_kernel = count_by_kernel;
         if (scene->profiling) ODB_CUDA(cudaEventRecord(scene->ev0, st));
         cudaError_t e = odb_launch_scene_mix(a, n_ctas, /*mode=*/scene->variant == 2 ? 1 : 0, st);
         if (e != cudaSuccess) return odb_fail(ODB_E_CUDA, "scene_mix launch failed: %s", cudaGetErrorString(e));
@@ -483,8 +500,7 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         seg(1);
         seg(2);
         if (scene->pipelined) ODB_CUDA(cudaEventRecord(scene->ev_mix[p], st));
-        ODB_TRY(scene->seek.post_callback(ctx, wst));
-        ODB_TRY(scene->buffered.post_callback(ctx, wst));
+        if (!count_by_kernel) ODB_TRY(scene->seek.post_callback(ctx, wst));
         seg(3);
         scene->last_launches = launches;
         ODB_CUDA(cudaGetLastError());
@@ -555,24 +571,65 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     return ODB_OK;
 }
 
+// Waits for the callback just queued: spins on the pinned word the grid's last CTA writes after the tile is stored
+// (no driver call on the way back), falling back to a stream synchronisation when the callback took a path that
+// does not publish the flag.
+static int scene_wait(odb_scene* scene) {
+    if (!scene->flag_armed) {
+        ODB_CUDA(cudaStreamSynchronize(scene->ctx->stream));
+        return ODB_OK;
+    }
+    volatile unsigned long long* flag = scene->h_flag.p;
+    for (unsigned long long spins = 1; *flag < scene->flag_seq; spins++) {
+        odb_cpu_pause();
+        if ((spins & 0xFFFFF) == 0) {  // every ~million polls: a failed launch would never raise the flag
+            cudaError_t q = cudaStreamQuery(scene->ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return odb_fail(ODB_E_CUDA, "callback failed: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && *flag < scene->flag_seq) return odb_fail(ODB_E_CUDA, "callback finished without publishing its flag");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return ODB_OK;
+}
+// Removals the callback reported (visible when sample returns, like the reference's).
+static int scene_fold_after(odb_scene* scene) {
+    odb_ctx* ctx = scene->ctx;
+    cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
+    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
+    if (scene->count_by_kernel) return scene->seek.fold_count(ctx, ws, scene->seek.h_removed_count.p[0], &scene->mu);
+    return scene->seek.fold_removed(ctx, ws, true, &scene->mu);
+}
+
 extern "C" int odb_scene_sample(odb_scene* scene, float interval, float* out, uint32_t n_frames) {
     ODB_TRY(scene_check(scene));
     if (!out && n_frames) return odb_fail(ODB_E_INVALID, "out is NULL");
     odb_ctx* ctx = scene->ctx;
     ODB_CUDA(cudaSetDevice(ctx->device));
     size_t n = (size_t)n_frames * 2;
-    ODB_TRY(scene->h_out.ensure(n ? n : 2));
     const double t0 = g_trace ? now_us() : 0.0;
-    // The reduce kernel stores the 8 KiB tile straight into the pinned host buffer (unified addressing: no
-    // device-side staging tile and no copy-engine operation between the last kernel and the host).
-    ODB_TRY(scene_sample_impl(scene, interval, scene->h_out.p, n_frames));
+    // A caller buffer that is pinned or registered host memory is rendered into directly; anything else goes through
+    // the scene's own pinned tile and one memcpy. Either way the kernel's reduce phase stores the tile straight
+    // into host memory (unified addressing: no device-side staging tile, no copy-engine operation).
+    if (out != scene->pinned_probe) {
+        scene->pinned_probe = out;
+        scene->pinned_dev = nullptr;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            scene->pinned_dev = (float*)at.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    float* target = scene->pinned_dev;
+    if (!target) {
+        ODB_TRY(scene->h_out.ensure(n ? n : 2));
+        target = scene->h_out.p;
+    }
+    ODB_TRY(scene_sample_impl(scene, interval, target, n_frames, false, /*host_flag=*/true));
     const double t1 = g_trace ? now_us() : 0.0;
-    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ODB_TRY(scene_wait(scene));
     const double t2 = g_trace ? now_us() : 0.0;
-    if (n) memcpy(out, scene->h_out.p, n * sizeof(float));
-    cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
-    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
-    int rc = scene->seek.fold_removed(ctx, ws, true, &scene->mu);  // like the reference, removals are visible when sample returns
+    if (n && target != out) memcpy(out, target, n * sizeof(float));
+    int rc = scene_fold_after(scene);
     if (g_trace && scene->callback_no > 4) {
         scene->tr_enqueue += t1 - t0; if (t1 - t0 > scene->tr_enqueue_max) scene->tr_enqueue_max = t1 - t0;
         scene->tr_wait += t2 - t1; scene->tr_tail += now_us() - t2;
@@ -589,12 +646,10 @@ extern "C" int odb_scene_sample_i16(odb_scene* scene, float interval, int16_t* o
     ODB_CUDA(cudaSetDevice(ctx->device));
     size_t n = (size_t)n_frames * 2;
     ODB_TRY(scene->h_out.ensure(n ? n : 2));
-    ODB_TRY(scene_sample_impl(scene, interval, scene->h_out.p, n_frames, /*as_i16=*/true));
-    ODB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ODB_TRY(scene_sample_impl(scene, interval, scene->h_out.p, n_frames, /*as_i16=*/true, /*host_flag=*/true));
+    ODB_TRY(scene_wait(scene));
     if (n) memcpy(out, scene->h_out.p, n * sizeof(int16_t));
-    cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
-    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
-    return scene->seek.fold_removed(ctx, ws, true, &scene->mu);
+    return scene_fold_after(scene);
 }
 // oddio::run, lib.rs:90-93
 extern "C" int odb_scene_run(odb_scene* scene, uint32_t sample_rate, float* out, uint32_t n_frames) {
@@ -638,21 +693,26 @@ static int owner_set(void* owner, odb_source src, odb_ctx** ctx, std::mutex** mu
 static int read_source(void* owner, odb_source src, OdbSource* out, bool* stale, SlotHost* shost) {
     odb_ctx* ctx; std::mutex* mu; SourceSet* set; uint32_t tag, slot;
     ODB_TRY(owner_set(owner, src, &ctx, &mu, &set, &tag));
-    std::lock_guard<std::mutex> lk(*mu);
-    ODB_TRY(set->lookup(src, tag, &slot, stale));
-    if (shost) *shost = set->slots[slot];
-    if (*stale) return ODB_OK;
-    ODB_CUDA(cudaSetDevice(ctx->device));
-    if (slot >= set->d_src.cap) {  // queued but not yet applied: answer from the queue
-        for (size_t i = 0; i < set->ins_slot.size(); i++)
-            if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
-    }
-    for (size_t i = 0; i < set->ins_slot.size(); i++)
-        if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
-    // the source table is written on the scene's walk stream (on the context's stream for a mixer)
+    const OdbSource* dev = nullptr;
     cudaStream_t rs = ctx->stream;
-    if (*(uint32_t*)owner == ODB_KIND_SCENE && ((odb_scene*)owner)->pipelined) rs = ((odb_scene*)owner)->wst;
-    ODB_CUDA(cudaMemcpyAsync(out, set->d_src.p + slot, sizeof(OdbSource), cudaMemcpyDeviceToHost, rs));
+    {   // resolve the handle under the control-plane lock ...
+        std::lock_guard<std::mutex> lk(*mu);
+        ODB_TRY(set->lookup(src, tag, &slot, stale));
+        if (shost) *shost = set->slots[slot];
+        if (*stale) return ODB_OK;
+        for (size_t i = 0; i < set->ins_slot.size(); i++)  // queued but not yet applied: answer from the queue
+            if (set->ins_slot[i] == slot) { *out = set->ins_src[i]; return ODB_OK; }
+        dev = set->d_src.p + slot;
+        // the source table is written on the scene's walk stream (on the context's stream for a mixer)
+        if (*(uint32_t*)owner == ODB_KIND_SCENE && ((odb_scene*)owner)->pipelined) rs = ((odb_scene*)owner)->wst;
+    }
+    // ... and read the record without it: a poll from the game thread must not hold the lock the audio thread's
+    // callback wants for the length of an in-flight callback (the reference's FramesSignalControl reads are atomics).
+    // The table is reallocated only when the set outgrows it, under grow_mu.
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> gl(set->grow_mu);
+    dev = set->d_src.p + slot;
+    ODB_CUDA(cudaMemcpyAsync(out, dev, sizeof(OdbSource), cudaMemcpyDeviceToHost, rs));
     ODB_CUDA(cudaStreamSynchronize(rs));
     return ODB_OK;
 }

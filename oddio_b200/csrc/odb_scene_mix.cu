@@ -635,7 +635,13 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
                 uint32_t* ack = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.acks_off) + (size_t)A.xg.rank * A.xg.max_slices;
                 for (int sl = 0; sl < A.xg.max_slices; sl++) st_release_sys(ack + sl, A.pull_seq);
             }
-            if (A.host_flag && threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
+            if (A.host_flag && threadIdx.x == 0) {
+                if (A.removed_count_host) {
+                    *reinterpret_cast<volatile uint32_t*>(A.removed_count_host) = __ldcg(A.removed_count);
+                    __threadfence_system();
+                }
+                *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
+            }
         }
     }
 }

@@ -40,6 +40,7 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     OdbParamMsg m = msgs[i];
+    if (m.slot == 0xFFFFFFFFu) return;  // withdrawn: its source was removed after the message was queued
     OdbSource* s = src + m.slot;
     if (m.what == ODB_PARAM_SPEED) s->speed = m.value;               // SpeedControl::set_speed speed.rs:52-54
     else if (m.what == ODB_PARAM_GAIN) s->gain_shared = m.value;     // GainControl::set_amplitude_ratio gain.rs:157-159
