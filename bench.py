@@ -500,6 +500,32 @@ def e2e_pass(rig, exchange_mode):
     return e2e_s, n_upd
 
 
+def native_e2e(args, callbacks):
+    """The e2e pass from compiled code: tools/e2e_native.c drives the C ABI exactly like e2e_pass (audio thread:
+    odb_scene_run with a host tile; control thread: set_motion on 1/16 of the sources per callback) without an
+    interpreter between the calls - what a Rust or C host sees. Built in-tree by __graft_entry__.build(); here only if
+    the binary is missing and gcc is present. Returns its JSON line or None."""
+    exe = os.path.join(ROOT, "tools", "e2e_native")
+    if not os.path.exists(exe):
+        try:
+            import __graft_entry__ as ge
+
+            ge.build_native_tools()
+        except Exception:
+            return None
+    if not os.path.exists(exe):
+        return None
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "oddio_b200") + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    env["ODB_VARIANT"] = str(args.variant)
+    try:
+        r = subprocess.run([exe, str(args.sources), str(callbacks), str(args.frames)], env=env, capture_output=True, text=True, timeout=600)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)
+    except Exception:
+        return None
+
+
 def parity_pass(rig, n_sample=4096, callbacks=2):
     """N > 1, after the timed passes: a 4096-source scene sharded over the ranks like the timed one. Per callback,
     (i) the exchanged tile is bit-identical on every rank and equals the rank-order f32 sum of the per-rank tiles
@@ -616,6 +642,10 @@ def run_ours(args):
     kernel_ms = maxr(kernel_time_pass(rig))
     e2e_s, n_upd = (float("nan"), max(1, rig.n_local // 16)) if args.skip_e2e else e2e_pass(rig, mode)
     e2e_ms = maxr(e2e_s * 1e3)
+    native = None
+    if world == 1 and not args.skip_e2e and args.scaling == "strong":
+        rig.release()  # its PCM makes room for the compiled harness's own scene
+        native = native_e2e(args, K)
     extras = {}
     parity = None
     if world > 1 and not args.skip_extras:
@@ -669,8 +699,11 @@ def run_ours(args):
                        "jobs_last_callback": main["counters"], **({"note": rig.note} if rig.note else {}),
                        "host_enqueue_us_per_step": round(main["host_us"], 1), "setup_s": round(rig.setup_s, 1)},
             "clocks": clk.summary(),
-            "e2e": {"value": N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
+            "e2e": {"value": native["source_frames_per_s"] if native else N * M / (e2e_ms / K * 1e-3), "unit": "source-frames/s",
                     "h2d_bytes_per_step": n_upd * 32, "d2h_bytes_per_step": M * 8 + 8,
+                    "driver": ("compiled C harness over the C ABI (tools/e2e_native.c): what a Rust / C host sees" if native else
+                               "Python (ctypes) over the C ABI"),
+                    **({"us_per_callback": native["us_per_callback"], "python_driven_value": N * M / (e2e_ms / K * 1e-3)} if native else {}),
                     "note": ("audio thread: odb_scene_run with a host tile" if world == 1 else
                              "audio thread: odb_scene_sample_exchange (lag 0) on this rank's shard, the summed tile written to pinned host memory by the kernel"
                              if mode != "nccl" else "audio thread: sample_device + NCCL all-reduce + D2H copy")
@@ -697,56 +730,299 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+# BASELINE.json's other configurations (`--config`): parity-test cases first, but each with a reproducible number.
+CONFIGS = {
+    "C1": "Mixer: 8 Sine sources -> 1024 stereo frames @48 kHz on CPU (examples/offline.rs path); CPU only by SURVEY.md section 8",
+    "C2": "SpatialScene: 1024 moving point sources, 256-frame callback @48 kHz",
+    "C3": "SpatialScene: 65536 moving point sources, 1024-frame callback @48 kHz (the headline; default)",
+    "C3b": "SpatialScene: the C3 sources through play_buffered(max_distance 350 m, 48 kHz, 0.1 s)",
+    "C4": "Mixer: 262144 static stereo FramesSignal sources + Gain + Tanh, 1024 frames @96 kHz",
+    "C5": "Mixer: 4096 Speed<FramesSignal> sources, ratio U[0.5, 2.0), 4096 frames @48 kHz",
+}
+
+
+def run_config(args):
+    """One JSON line for C1 / C2 / C3b / C4 / C5 on one GPU: device-resident source-frames/s (CUDA events on the launch
+    stream, L2 flushed between callbacks where the working set fits in it), the whole callback's algorithmic HBM
+    fraction, the host-buffer call timed end to end, and the CPU oracle on a bounded sample."""
+    from oracle import pyoracle as o
+
+    cfg = args.config
+    K, W = args.steps, max(3, args.warmup)
+    if cfg == "C1":  # 8 x MonoToStereo(Sine) under a Mixer<[f32; 2]>, CPU only
+        rng = np.random.default_rng(1)
+        mx = o.Mixer(2)
+        for _ in range(8):
+            mx.play(o.MonoToStereo(o.Sine(float(rng.uniform(0, 2 * np.pi)), float(rng.uniform(100.0, 1000.0)))))
+        reps = 2000
+        secs = o.time_run(mx, RATE, 1024, 20, reps)  # best single callback
+        line = {"metric": "source-frames/sec (N sources x buffer frames)", "value": 8 * 1024 / secs, "unit": "source-frames/s", "n_gpus": 0,
+                "steps": reps, "warmup": 20, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": "C1 " + CONFIGS["C1"], "cpu_only": True},
+                "gpu_launches": 0, "roofline": None,
+                "cpu_baseline": {"value": 8 * 1024 / secs, "unit": "source-frames/s", "cores": 1, "kind": "port",
+                                 "sample": f"the whole configuration, {reps} callbacks; C++ restatement of the Rust reference (no rustc here)"}}
+        emit(line)
+        return line
+    import torch
+
+    import oddio_b200 as odb
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = odb.Context(0, stream=stream.cuda_stream)
+    clk = ClockSampler(0).start()
+    rng = np.random.default_rng({"C2": 2, "C3b": 3, "C4": 4, "C5": 5}[cfg])
+    scene_like = cfg in ("C2", "C3b")
+    if cfg == "C2":
+        N, M, rate, ch, ds_max = args.sources_cfg or 1024, 256, 48000, 1, DS_MAX
+    elif cfg == "C3b":
+        N, M, rate, ch, ds_max = args.sources_cfg or 65536, 1024, 48000, 1, 1.0
+        W = max(W, 56)  # the delay rings fill for >= max_delay (1.12 s) before the output is non-trivial
+    elif cfg == "C4":
+        N, M, rate, ch, ds_max = args.sources_cfg or 262144, 1024, 96000, 2, 1.0
+    else:
+        N, M, rate, ch, ds_max = args.sources_cfg or 4096, 4096, 48000, 1, 2.0
+    start_s = START_S if cfg == "C2" else 0.0
+    L = int(start_s * rate + np.ceil(ds_max * M * (2 * (K + W) + 4))) + 2048   # device pass + e2e pass read disjoint PCM
+    pos, vel, freq, phase = scene_geometry(N)
+    if cfg == "C2":  # SURVEY 8d: ball shell 2-100 m, velocities U[-30, 30] per axis
+        d = pos / np.linalg.norm(pos, axis=1, keepdims=True)
+        pos = (d * rng.uniform(2.0, 100.0, (N, 1))).astype(np.float32)
+        vel = rng.uniform(-30, 30, (N, 3)).astype(np.float32)
+    speeds = rng.uniform(0.5, 2.0, N).astype(np.float32) if cfg == "C5" else None
+    gains = (rng.uniform(0.05, 1.0, N) * 1e-3).astype(np.float32) if cfg == "C4" else None
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    frames, host_pcm = [], {}
+    n_cpu = {"C2": N, "C3b": 1024, "C4": 8192, "C5": 256}[cfg]
+    kk = torch.arange(L, device=dev, dtype=torch.float32)
+    t0 = time.time()
+    B = 256
+    for b0 in range(0, N, B):
+        nb = min(B, N - b0)
+        w = torch.tensor(2 * np.pi * freq[b0:b0 + nb] / rate, device=dev, dtype=torch.float32)[:, None, None]
+        x = (0.5 * torch.sin(w * kk[None, :, None] + torch.arange(ch, device=dev)[None, None, :])
+             + 0.05 * (2 * torch.rand((nb, L, ch), device=dev, generator=gen) - 1)).contiguous()
+        torch.cuda.synchronize(dev)
+        if b0 < n_cpu:
+            xh = x[: max(0, min(nb, n_cpu - b0))].cpu().numpy()
+            for r in range(xh.shape[0]):
+                host_pcm[b0 + r] = xh[r, :, 0].copy() if ch == 1 else xh[r].copy()
+        for r in range(nb):
+            frames.append(odb.Frames.from_device(rate, ch, x[r].data_ptr(), L, ctx))
+        del x
+    setup_s = time.time() - t0
+
+    def build(api, frames_of, n):
+        """The configuration with `api` (the device mirror or the oracle) over its first n sources."""
+        if scene_like:
+            if api is odb:
+                ctl, top = api.SpatialScene.new(ctx)
+            else:
+                top = api.SpatialScene()
+                ctl = top
+            for i in range(n):
+                sig = api.FramesSignal(frames_of(i), start_s)
+                if cfg == "C2":
+                    ctl.play(sig, api.SpatialOptions(pos[i], vel[i], 0.1)) if api is odb else ctl.play(sig, pos[i], vel[i], 0.1)
+                elif api is odb:
+                    ctl.play_buffered(sig, api.SpatialOptions(pos[i], vel[i], 0.1), 350.0, rate, 0.1)
+                else:
+                    ctl.play_buffered(sig, pos[i], vel[i], 0.1, 350.0, rate, 0.1)
+            return top, top
+        if api is odb:
+            ctl, mx = api.Mixer.new(ch, ctx)
+        else:
+            mx = api.Mixer(ch)
+            ctl = mx
+        top = api.Tanh(mx) if cfg == "C4" else mx
+        for i in range(n):
+            sig = api.FramesSignal(frames_of(i), 0.0)
+            if cfg == "C4":
+                if api is odb:
+                    sig = api.Gain(sig)
+                    sig.set_amplitude_ratio(float(gains[i]))
+                else:
+                    sig = api.Gain(sig)
+                    sig.set_amplitude_ratio(float(gains[i]))
+            else:
+                if api is odb:
+                    sc, sig = api.Speed.new(sig)
+                    sc.set_speed(float(speeds[i]))
+                else:
+                    sig = api.Speed(sig)
+                    sig.set_speed(float(speeds[i]))
+            ctl.play(sig)
+        return top, mx
+
+    interval = float(np.float32(1.0) / np.float32(rate))
+    flush = cfg in ("C2", "C5")  # working set per callback fits in the 126 MB L2: flush it between callbacks
+    with torch.cuda.stream(stream):
+        top, agg = build(odb, lambda i: frames[i], N)
+        tile = torch.zeros((M, 2 if scene_like else ch), device=dev, dtype=torch.float32)
+        scratch = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32) if flush else None  # 256 MB > L2
+        for _ in range(W):
+            top.sample_device(interval, tile.data_ptr(), M)
+        torch.cuda.synchronize(dev)
+        ms_list = []
+        with clk:
+            if flush:
+                for _ in range(K):
+                    scratch.fill_(1.0)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    top.sample_device(interval, tile.data_ptr(), M)
+                    e1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    ms_list.append(e0.elapsed_time(e1))
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(K):
+                    top.sample_device(interval, tile.data_ptr(), M)
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms_list = [e0.elapsed_time(e1) / K] * K
+        clk.stop()
+        ms = float(np.mean(ms_list))
+        launches = agg.last_launch_count()
+        counters = agg.last_job_counters()
+        checksum = float(tile.abs().sum().item())
+        # end to end: the host-buffer call, one callback at a time
+        host_out = np.zeros((M, 2 if scene_like else ch) if (scene_like or ch > 1) else (M,), dtype=np.float32)
+        t1 = time.perf_counter()
+        for _ in range(K):
+            odb.run(top, rate, host_out)
+        e2e_ms = (time.perf_counter() - t1) / K * 1e3
+    # algorithmic bytes (SURVEY.md section 8d): 4 B * channels * M * ds per source and callback (+ 8 B per ring sample written for C3b)
+    if cfg == "C2":
+        r = pos / np.linalg.norm(pos, axis=1, keepdims=True)
+        ds_mean = float(np.mean(1.0 - np.sum(vel * r, axis=1) / 343.0))
+    else:
+        ds_mean = float(speeds.mean()) if speeds is not None else 1.0
+    alg = 4.0 * ch * M * ds_mean * N
+    peak, peak_src = peaks()
+    # CPU oracle on a bounded sample
+    ofr = {}
+
+    def oframes(i):
+        if i not in ofr:
+            ofr[i] = o.Frames.from_slice(rate, host_pcm[i])
+        return ofr[i]
+    otop, _ = build(o, oframes, n_cpu)
+    reps = 3
+    secs = o.time_run(otop, rate, M, 1, reps)  # best single callback
+    line = {"metric": "source-frames/sec (N sources x buffer frames)", "value": N * M / (ms * 1e-3), "unit": "source-frames/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{cfg} {CONFIGS[cfg]}", "sources": N, "frames": M, "rate": rate, "channels": ch,
+                       "l2": "L2 flushed between callbacks (a 256 MB fill)" if flush else "inputs larger than L2: every callback reads fresh PCM",
+                       "jobs_last_callback": counters, "setup_s": round(setup_s, 1)},
+            "clocks": clk.summary(),
+            "e2e": {"value": N * M / (e2e_ms * 1e-3), "unit": "source-frames/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(host_out.nbytes) + 8, "note": "odb_*_run with a host tile, Python (ctypes) over the C ABI"},
+            "gpu_launches": int(launches * K),
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "whole callback (all kernels of one *_sample)",
+                         "kernel_ms": ms, "alg_bytes_per_launch": alg, "peak_source": peak_src},
+            "checksum": checksum,
+            "cpu_baseline": {"value": n_cpu * M / secs, "unit": "source-frames/s", "cores": 1, "kind": "port",
+                             "sample": f"first {n_cpu} of the {N} sources x {M} frames, {reps} callbacks after 1 warm-up ({secs * 1e3:.1f} ms per "
+                                       "callback); C++ restatement of the Rust reference (no rustc here)"}}
+    emit(line)
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------
+def oracle_c3_scenes(args, n, shards, callbacks):
+    """The first `n` sources of the C3 scene in the CPU oracle, dealt round-robin to `shards` scenes. Every source
+    plays a private block trimmed to what `callbacks` callbacks can touch (block i starts off[i] frames into the sound
+    and its FramesSignal starts at START_S - off[i] / rate, frames.rs:156), so the full 65 536-source scene is 6 GB of
+    host memory instead of 19 GB and every callback still streams fresh PCM per source."""
+    from oracle import pyoracle as o
+
+    M = args.frames
+    pos, vel, freq, phase = scene_geometry(args.sources)
+    dist_m = np.linalg.norm(pos[:n].astype(np.float64), axis=1)
+    off = np.floor(RATE * (START_S - dist_m / 343.0)).astype(np.int64) - 128
+    start = START_S - off.astype(np.float64) / RATE
+    L = 128 + int(DS_MAX * M * callbacks) + 512
+    kk = np.arange(L, dtype=np.float32)
+    rng = np.random.default_rng(1)
+    scenes = [o.SpatialScene() for _ in range(shards)]
+    keep = []
+    B = 1024
+    for b0 in range(0, n, B):
+        ids = np.arange(b0, min(n, b0 + B))
+        w = (2 * np.pi * freq[ids] / RATE).astype(np.float32)[:, None]
+        ph = (phase[ids] + 2 * np.pi * freq[ids] / RATE * off[ids]).astype(np.float32)[:, None]
+        x = (0.5 * np.sin(w * kk[None, :] + ph) + 0.05 * (2 * rng.random((len(ids), L), dtype=np.float32) - 1)).astype(np.float32)
+        for r, i in enumerate(ids):
+            fr = o.Frames.from_slice(RATE, x[r])
+            keep.append(fr)
+            scenes[i % shards].play(o.FramesSignal(fr, float(start[i])), pos[i], vel[i], 0.1)
+    return scenes, keep
+
+
 def cpu_baseline(args, threads: int, n: int, reps: int = 3, warm: int = 1):
-    """Times the CPU oracle (oracle/, the restatement of the Rust reference) on a bounded sample of the
-    same workload: the first `n` sources of the same scene, same frames per callback."""
+    """Times the CPU oracle (oracle/, the restatement of the Rust reference) on the first `n` sources of the same
+    scene, same frames per callback. threads = 1 is the reference's behaviour (one Signal graph, one thread,
+    signal.rs:19); more threads shard the sources - not reference behaviour, labelled as such."""
     from oracle import pyoracle as o
 
     M = args.frames
     n = min(n, args.sources)
-    pos, vel, freq, phase = scene_geometry(args.sources)
-    L = pcm_len(M, reps + warm)
-    rng = np.random.default_rng(1)
-    kk = np.arange(L, dtype=np.float32)
-    scenes = [o.SpatialScene() for _ in range(threads)]
-    keep = []
-    for i in range(n):
-        x = (0.5 * np.sin(np.float32(2 * np.pi * freq[i] / RATE) * kk + np.float32(phase[i]))
-             + 0.05 * (2 * rng.random(L, dtype=np.float32) - 1)).astype(np.float32)
-        fr = o.Frames.from_slice(RATE, x)
-        keep.append(fr)
-        scenes[i % threads].play(o.FramesSignal(fr, START_S), pos[i], vel[i], 0.1)
-    secs, tile = o.time_run_sharded(scenes, RATE, M, warm, reps)
-    per_cb = secs / reps
+    scenes, keep = oracle_c3_scenes(args, n, threads, reps + warm)
+    if threads == 1:
+        t0 = time.perf_counter()
+        for _ in range(warm):
+            o.run(scenes[0], RATE, M)
+        t1 = time.perf_counter()
+        for _ in range(reps):
+            o.run(scenes[0], RATE, M)
+        per_cb = (time.perf_counter() - t1) / reps
+        del t0
+    else:
+        secs, _tile = o.time_run_sharded(scenes, RATE, M, warm, reps)
+        per_cb = secs / reps
+    what = "all" if n == args.sources else "first"
     return {"value": n * M / per_cb, "unit": "source-frames/s", "cores": threads,
-            "kind": "port", "sample": f"first {n} of the {args.sources} sources x {M} frames, {reps} callbacks after {warm} warm-up "
-                                      f"({per_cb * 1e3:.1f} ms per callback); C++ restatement of the Rust reference (no rustc here)",
-            "host_cores_available": os.cpu_count()}
+            "kind": "port", "sample": f"{what} {n} of the {args.sources} sources x {M} frames, {reps} callbacks after {warm} warm-up "
+                                      f"({per_cb * 1e3:.1f} ms per callback); C++ restatement of the Rust reference (no rustc here)"
+                                      + ("" if threads == 1 else f"; sources sharded over {threads} threads - not reference behaviour"),
+            "same_config": n == args.sources, "host_cores_available": os.cpu_count()}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path (the oracle port; the Rust crate
-    cannot be built here) with all host threads, sources sharded over threads."""
+    """`--impl reference`: the reference's CPU implementation of the path - the oracle port (the Rust crate cannot be
+    built here). The line's value is the reference's own behaviour: ONE thread over the FULL scene (65 536 sources,
+    every step a whole callback); the all-host-threads run (sources sharded, not reference behaviour) is an extra key."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     t0 = time.time()
-    base = cpu_baseline(args, threads=threads, n=args.ref_sources, reps=args.steps, warm=args.warmup)
     M = args.frames
-    N = args.sources * args.gpus if args.scaling == "weak" else args.sources
+    N = args.sources  # the fixed scene; its CPU time does not depend on how many GPUs the other arm uses
+    steps, warm = max(1, min(args.steps, args.ref_steps)), 1
+    base = cpu_baseline(args, threads=1, n=N, reps=steps, warm=warm)
+    threads = os.cpu_count() or 1
+    many = cpu_baseline(args, threads=threads, n=N, reps=steps, warm=warm) if threads > 1 else None
     line = {
         "impl": "reference", "metric": "source-frames/sec (N sources x buffer frames) spatial mix",
-        "value": base["value"], "unit": "source-frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "value": base["value"], "unit": "source-frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": N * M / base["value"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C3 SpatialScene: {N} moving point sources (doppler + propagation delay), "
                                f"{M}-frame stereo callback @{RATE} Hz, seek path (play)",
-                   "sources": N, "frames": M, "rate": RATE, "parallelism": f"{threads} host threads, sources sharded"},
+                   "sources": N, "frames": M, "rate": RATE, "parallelism": "1 host thread (the reference's Signal graph is single-threaded)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "source-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(time.time() - t0, 1),
     }
+    if many:
+        line["extra"] = {"all_host_threads": many}
     emit(line)
 
 
@@ -762,10 +1038,12 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS), help="; ".join(f"{k}: {v}" for k, v in sorted(CONFIGS.items())))
+    ap.add_argument("--sources-cfg", type=int, default=0, help="--config other than C3: source count (0 = the configuration's own)")
     ap.add_argument("--sources", type=int, default=65536)
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--cpu-sources", type=int, default=2048, help="sources in the bounded CPU sample")
-    ap.add_argument("--ref-sources", type=int, default=8192, help="sources in the --impl reference sample")
+    ap.add_argument("--ref-steps", type=int, default=5, help="--impl reference: timed whole-scene callbacks (about 0.9 s each on one thread)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong (default) = the fixed scene of --sources sources split over the ranks, weak = --sources per GPU")
@@ -783,7 +1061,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.config != "C3":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_config(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -72,7 +72,7 @@ struct OdbSceneMixArgs {
     uint32_t* zero_counters;          // the other parity's counters, reset for the next callback (may be NULL)
     unsigned long long* arrive;       // monotonic count of (CTA, tile) arrivals over the life of the scene
     unsigned long long arrive_base;   // its value before this launch
-    unsigned long long* done;         // monotonic count of finished CTAs (NULL: no host flag)
+    unsigned long long* done;         // monotonic count of finished CTAs (NULL: the reduce phase stores the output itself)
     unsigned long long done_base;
     unsigned long long* host_flag;    // pinned host word that receives `seq` when the whole grid has stored its output
     unsigned long long seq;
@@ -86,8 +86,7 @@ struct OdbSceneMixArgs {
     odbk::ExchangePeers peers;
     odbk::ExchangeGeom xg;
     uint32_t push_seq, pull_seq;
-    unsigned long long* pushed;       // monotonic count of CTAs whose pushes are out (d_sync[2])
-    unsigned long long pushed_base;
+    float* xtile;                     // [n_tiles][2 * ODB_TILE_FRAMES] raw sum of this rank, for the grid's last CTA (exchange / host tile)
 };
 int odb_scene_mix_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mode, cudaStream_t st);

@@ -47,8 +47,9 @@ struct odb_scene {
     // callback parity (the next callback's CTAs may start while this one's reducers still read), the grid's
     // arrive / done counters and the running totals the kernel compares them with.
     DevBuf<float> d_partials_fused[2];
+    DevBuf<float> d_xtile[2];            // this rank's raw sum, handed to the grid's last CTA (exchange / host tile)
     DevBuf<unsigned long long> d_sync;   // [0] arrivals, [1] finished CTAs, [2] CTAs whose exchange pushes are out
-    unsigned long long arrive_total = 0, done_total = 0, pushed_total = 0;
+    unsigned long long arrive_total = 0, done_total = 0;
     bool legacy = false;                 // odb_set_kernel_variant bit 9: the multi-kernel path of round 1
     bool flag_armed = false;             // the callback just queued publishes flag_seq to h_flag when its tile is stored
     bool count_by_kernel = false;        // ... and the seek set's removal-report count to seek.h_removed_count
@@ -113,6 +114,7 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     cudaStreamDestroy(scene->wst);
     scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_partials_ring.release();
     scene->d_partials_fused[0].release(); scene->d_partials_fused[1].release(); scene->d_sync.release(); scene->h_flag.release();
+    scene->d_xtile[0].release(); scene->d_xtile[1].release();
     scene->d_out.release();
     scene->h_out.release();
     if (scene->ev0) { cudaEventDestroy(scene->ev0); cudaEventDestroy(scene->ev1); }
@@ -462,15 +464,14 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             a.epilogue = xr->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0);
             a.push_seq = ++ex->seq;
             ex->pushed_floats[ex->seq % (uint32_t)ex->depth] = n_frames * 2;
-            a.pushed = scene->d_sync.p + 2;
-            a.pushed_base = scene->pushed_total;
-            scene->pushed_total += (unsigned long long)n_ctas;
             if (ex->seq - ex->pulled > (uint32_t)xr->lag) {
                 a.pull_seq = ++ex->pulled;
                 xr->written = 1;
             }
         }
-        if (host_flag || a.pull_seq) {
+        if (host_flag || xr) {  // the grid's last CTA finishes the callback from the raw sum in xtile
+            ODB_TRY(ensure_idle(scene, scene->d_xtile[p], (size_t)nt * 2 * ODB_TILE_FRAMES));
+            a.xtile = scene->d_xtile[p].p;
             a.done = scene->d_sync.p + 1;
             a.done_base = scene->done_total;
             scene->done_total += (unsigned long long)n_ctas;

@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    pdl_launch_dependents();
-    pdl_wait();           // job records and counters come from the walk kernel launched just before
+    pdl_wait();               // job records and counters come from the walk kernel launched just before
+    pdl_launch_dependents();  // after the wait: whatever starts early (the next callback's walk) finds this callback's walk complete
     if (A.zero_counters && blockIdx.x == 0 && threadIdx.x < ODB_CNT_WORDS) A.zero_counters[threadIdx.x] = 0u;
     uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
     uint32_t buf = 0;
@@ -519,25 +519,21 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
                 sum = sum + *reinterpret_cast<const float*>(smem_raw + (w * SPLIT + h) * CFG::WARP_BYTES + fh * 4);
             __stcg(pdst + f, sum);
         }
-        __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(A.arrive, 1ull);
-        // 5. when every CTA has arrived: sum slices of the partial tiles in index order; then either epilogue + store
-        //    (one GPU) or the raw sum into slot `rank` of every rank's inbox over NVLink (exchange push_seq)
+        if (threadIdx.x == 0) {  // one device-scope fence per CTA, cumulative over the CTA's stores through the barrier
+            __threadfence();
+            atomicAdd(A.arrive, 1ull);
+        }
+        // 5. when every CTA has arrived: sum slices of the partial tiles in index order. A plain device-resident
+        //    callback applies the epilogue and stores the output here; one that ends in an exchange or in host memory
+        //    leaves the raw sum in `xtile` for the grid's last CTA (below)
         const unsigned long long target = A.arrive_base + (unsigned long long)(tl + 1) * (unsigned long long)G;
-        float* red = reinterpret_cast<float*>(smem_raw);  // [RGROUPS][SMX_SLICE], then [SMX_SLICE] totals
-        const bool pushing = A.push_seq != 0u;
+        float* red = reinterpret_cast<float*>(smem_raw);  // [RGROUPS][SMX_SLICE]
         bool waited = false;
         for (int sl = blockIdx.x; sl < SMX_SLICES; sl += G) {
             if (!waited) {
                 if (threadIdx.x == 0)
                     while (ld_acquire_u64(A.arrive) < target) __nanosleep(40);
-                // the inbox slots about to be overwritten held exchange push_seq - depth: every peer must have pulled it
-                if (pushing && threadIdx.x >= 32 && threadIdx.x < 32 + A.xg.world && A.push_seq > (uint32_t)A.xg.depth) {
-                    const uint32_t* ack = reinterpret_cast<const uint32_t*>(A.peers.inbox[A.xg.rank] + A.xg.acks_off) +
-                                          (size_t)(threadIdx.x - 32) * A.xg.max_slices + tl;
-                    while ((int)(ld_acquire_sys(ack) - (A.push_seq - (uint32_t)A.xg.depth)) < 0) __nanosleep(20);
-                }
                 __syncthreads();
                 waited = true;
             }
@@ -548,101 +544,92 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             for (int i = grp; i < G; i += RGROUPS) sum = sum + __ldcg(p + (size_t)i * (2 * ODB_TILE_FRAMES));
             red[grp * SMX_SLICE + fl] = sum;
             __syncthreads();
-            float total = 0.0f;
             if (threadIdx.x < SMX_SLICE) {
+                float total = 0.0f;
 #pragma unroll
                 for (int g = 0; g < RGROUPS; g++) total = total + red[g * SMX_SLICE + fl];
-            }
-            if (pushing) {
-                __syncthreads();
-                if (threadIdx.x < SMX_SLICE) red[fl] = total;
-                __syncthreads();
-                if (threadIdx.x < SMX_SLICE * A.xg.world) {  // thread (peer, float): one 64-byte run per peer
-                    const int peer = threadIdx.x / SMX_SLICE;
-                    const uint32_t par = A.push_seq % (uint32_t)A.xg.depth;
-                    float* dst = reinterpret_cast<float*>(A.peers.inbox[peer]) + ((size_t)par * A.xg.world + A.xg.rank) * A.xg.cap +
-                                 (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
-                    *dst = red[fl];
-                }
-            } else if (threadIdx.x < SMX_SLICE) {
-                store_output(A, tl, f, total);
+                if (A.xtile) __stcg(A.xtile + (size_t)tl * (2 * ODB_TILE_FRAMES) + f, total);
+                else store_output(A, tl, f, total);
             }
             __syncthreads();
         }
         __syncthreads();  // the warp regions are reused by the next tile
     }
+    if (!A.done) return;
+    // ---- the grid's last CTA finishes the callback: the exchange over NVLink and / or the hand-over to the host. Every
+    // other CTA leaves here, so its SM is free for the next callback's kernels while the last one waits on fences and peers.
+    __shared__ int last_done;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // one device-scope fence per CTA, cumulative over its xtile stores through the barrier
+        const unsigned long long d = atomicAdd(A.done, 1ull) + 1ull;
+        last_done = d == A.done_base + (unsigned long long)G;
+        if (last_done) __threadfence();
+    }
+    __syncthreads();
+    if (!last_done) return;
+    const int n_floats = 2 * A.n_frames;        // what the callback renders ...
+    const int n_float4 = (n_floats + 3) / 4;    // ... moved in 16-byte words (inbox slots and xtile are padded to a multiple of 32 floats)
     if (A.push_seq != 0u) {
-        // every CTA's pushes are out (system-scope fence, then a device-scope count); the last one publishes the
-        // exchange's sequence number in every rank's inbox - one flag per tile, the stand-alone kernels' protocol
-        __threadfence_system();
-        __syncthreads();
-        __shared__ int last_pusher;
-        if (threadIdx.x == 0) {
-            const unsigned long long d = atomicAdd(A.pushed, 1ull) + 1ull;
-            last_pusher = d == A.pushed_base + (unsigned long long)G;
-            if (last_pusher) __threadfence_system();
+        // push: this rank's sum (no epilogue) into slot `rank` of every rank's inbox, then the sequence number in the
+        // slot's flags - the stand-alone kernels' protocol (odb_exchange.cu). The slots about to be overwritten held
+        // exchange push_seq - depth: every peer must have pulled that one (practically never a wait).
+        const uint32_t par = A.push_seq % (uint32_t)A.xg.depth;
+        if (threadIdx.x < A.xg.world && A.push_seq > (uint32_t)A.xg.depth) {
+            const uint32_t* ack = reinterpret_cast<const uint32_t*>(A.peers.inbox[A.xg.rank] + A.xg.acks_off) + (size_t)threadIdx.x * A.xg.max_slices;
+            for (int tl = 0; tl < A.n_tiles; tl++)
+                while ((int)(ld_acquire_sys(ack + tl) - (A.push_seq - (uint32_t)A.xg.depth)) < 0) __nanosleep(20);
         }
         __syncthreads();
-        if (last_pusher && threadIdx.x < A.xg.world) {
-            const uint32_t par = A.push_seq % (uint32_t)A.xg.depth;
+        const size_t slot = ((size_t)par * A.xg.world + A.xg.rank) * A.xg.cap;
+        for (int p = 0; p < A.xg.world; p++) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(A.peers.inbox[p]) + slot);
+            for (int i = threadIdx.x; i < n_float4; i += blockDim.x) dst[i] = __ldcg(reinterpret_cast<const float4*>(A.xtile) + i);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < A.xg.world) {
             uint32_t* flag = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.flags_off) +
                              ((size_t)par * A.xg.world + A.xg.rank) * A.xg.max_slices;
             for (int tl = 0; tl < A.n_tiles; tl++) st_release_sys(flag + tl, A.push_seq);
         }
     }
     if (A.pull_seq != 0u) {
-        // sum of exchange pull_seq over the ranks, in rank order (bit-identical on every rank), epilogue, store.
-        // Every CTA has pushed before it waits here, so no rank can wait for a flag that depends on its own progress.
+        // pull: the sum of exchange pull_seq over the ranks, in rank order (bit-identical on every rank), epilogue, store.
+        // The push above is out before this waits, so no rank can wait for a flag that depends on its own progress.
         const uint32_t par = A.pull_seq % (uint32_t)A.xg.depth;
         const char* mine = A.peers.inbox[A.xg.rank];
-        for (int tl = 0; tl < A.n_tiles; tl++) {
-            bool waited = false;
-            for (int sl = blockIdx.x; sl < SMX_SLICES; sl += G) {
-                if (!waited) {
-                    if (threadIdx.x < A.xg.world) {
-                        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + A.xg.flags_off) +
-                                               ((size_t)par * A.xg.world + threadIdx.x) * A.xg.max_slices + tl;
-                        while ((int)(ld_acquire_sys(flag) - A.pull_seq) < 0) __nanosleep(20);
-                    }
-                    __syncthreads();
-                    waited = true;
-                }
-                if (threadIdx.x < SMX_SLICE) {
-                    const int f = sl * SMX_SLICE + threadIdx.x;
-                    const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * A.xg.world * A.xg.cap +
-                                      (size_t)tl * (2 * ODB_TILE_FRAMES) + f;
-                    float sum = 0.0f;
-                    for (int p = 0; p < A.xg.world; p++) sum = sum + __ldcv(in + (size_t)p * A.xg.cap);
-                    store_output(A, tl, f, sum);
-                }
-            }
+        if (threadIdx.x < A.xg.world) {
+            const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + A.xg.flags_off) + ((size_t)par * A.xg.world + threadIdx.x) * A.xg.max_slices;
+            for (int tl = 0; tl < A.n_tiles; tl++)
+                while ((int)(ld_acquire_sys(flag + tl) - A.pull_seq) < 0) __nanosleep(20);
         }
+        __syncthreads();
+        const float* in = reinterpret_cast<const float*>(mine) + (size_t)par * A.xg.world * A.xg.cap;
+        for (int i = threadIdx.x; i < n_floats; i += blockDim.x) {
+            float sum = 0.0f;
+            for (int p = 0; p < A.xg.world; p++) sum = sum + __ldcv(in + (size_t)p * A.xg.cap + i);
+            store_output(A, i / (2 * ODB_TILE_FRAMES), i % (2 * ODB_TILE_FRAMES), sum);
+        }
+    } else if (A.push_seq == 0u) {
+        // one GPU, host tile: epilogue and store into (pinned) host memory, 512 coalesced lanes
+        for (int i = threadIdx.x; i < n_floats; i += blockDim.x)
+            store_output(A, i / (2 * ODB_TILE_FRAMES), i % (2 * ODB_TILE_FRAMES), __ldcg(A.xtile + i));
     }
-    // the last CTA to get here acknowledges the pulled exchange to the peers and tells the host (both optional):
-    // everything the grid stored or read is ordered before the flags
-    if (A.done) {
-        __threadfence_system();
-        __syncthreads();
-        __shared__ int last_done;
-        if (threadIdx.x == 0) {
-            const unsigned long long d = atomicAdd(A.done, 1ull) + 1ull;
-            last_done = d == A.done_base + (unsigned long long)G;
-            if (last_done) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();  // cumulative over the CTA's output stores and inbox reads
+    __syncthreads();
+    if (A.pull_seq != 0u && threadIdx.x < A.xg.world) {  // the peers may overwrite this slot `depth` exchanges on
+        uint32_t* ack = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.acks_off) + (size_t)A.xg.rank * A.xg.max_slices;
+        for (int sl = 0; sl < A.xg.max_slices; sl++) st_release_sys(ack + sl, A.pull_seq);
+    }
+    if (A.host_flag && threadIdx.x == 0) {
+        if (A.removed_count_host) {
+            *reinterpret_cast<volatile uint32_t*>(A.removed_count_host) = __ldcg(A.removed_count);
+            __threadfence_system();
         }
-        __syncthreads();
-        if (last_done) {
-            if (A.pull_seq != 0u && threadIdx.x < A.xg.world) {  // the peers may overwrite this slot `depth` exchanges on
-                uint32_t* ack = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.acks_off) + (size_t)A.xg.rank * A.xg.max_slices;
-                for (int sl = 0; sl < A.xg.max_slices; sl++) st_release_sys(ack + sl, A.pull_seq);
-            }
-            if (A.host_flag && threadIdx.x == 0) {
-                if (A.removed_count_host) {
-                    *reinterpret_cast<volatile uint32_t*>(A.removed_count_host) = __ldcg(A.removed_count);
-                    __threadfence_system();
-                }
-                *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
-            }
-        }
+        *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
     }
 }
 

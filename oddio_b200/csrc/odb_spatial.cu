@@ -54,9 +54,12 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk_seek(OdbSource* __restric
                                                              OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
                                                              int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
     __shared__ __align__(16) unsigned char smem[WalkSmem<WALK_THREADS>::BYTES];
+    // Launched behind the previous callback's mix kernel, which lets its dependents start once ITS walk is complete:
+    // this grid's blocks run as SMs come free, under the tail of that kernel (its last CTA's exchange), and wait for it
+    // only before they touch the job counters (odb_walk.cuh). Control-plane scatter kernels are ordinary launches
+    // and therefore complete before this grid starts.
     pdl_launch_dependents();  // the mix kernel may be set up now; it waits for this grid before reading jobs
-    pdl_wait();               // the previous callback's kernels are done with the source table and the counters
-    walk_seek_block<WALK_THREADS>(src, order, jobs, removed, removed_cap, counters, cb, blockIdx.x * (WALK_THREADS / 2), smem,
+    walk_seek_block<WALK_THREADS, true>(src, order, jobs, removed, removed_cap, counters, cb, blockIdx.x * (WALK_THREADS / 2), smem,
                                   threadIdx.x);
 }
 

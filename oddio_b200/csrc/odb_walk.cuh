@@ -37,7 +37,7 @@ struct WalkSmem {
 
 // Walks sources [first, first + THREADS / 2) of the active list (indices beyond cb.n_sources are idle lanes).
 // Must be called by all THREADS threads of the block (it synchronises the block); `tid` = thread index within them.
-template <int THREADS>
+template <int THREADS, bool LATE_WAIT>
 __device__ __forceinline__ void walk_seek_block(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                 OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed, const int removed_cap,
                                                 uint32_t* __restrict__ counters, const OdbCallback& cb, const int first,
@@ -249,7 +249,10 @@ __device__ __forceinline__ void walk_seek_block(OdbSource* __restrict__ src, con
         te = te + (double)elapsed;                                      // :468
         sp->t = te;
     }
-    // job counters: one atomic per warp into shared memory, one per block into HBM
+    // job counters: one atomic per warp into shared memory, one per block into HBM. Everything above only touches
+    // what no earlier kernel still uses (this callback's job records, the source table); the counters are reset by the
+    // previous callback's mix kernel, so this is where the grid waits for it (and, through it, for everything before).
+    if (LATE_WAIT) pdl_wait();
     n_general = __reduce_add_sync(full, n_general);
     n_fast = __reduce_add_sync(full, n_fast);
     if (lane == 0 && n_general) atomicAdd(cnt_sm + 0, n_general);

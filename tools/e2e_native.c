@@ -3,7 +3,8 @@
  * the sources during every callback (paced by a semaphore, as in bench.py's e2e pass). Developer tool for the GPU box:
  *
  *   gcc -std=gnu11 -O2 -Iinclude tools/e2e_native.c -Loddio_b200 -loddio_b200 -lm -lpthread -o /tmp/e2e_native
- *   LD_LIBRARY_PATH=oddio_b200 /tmp/e2e_native [sources=65536] [callbacks=32]
+ *   LD_LIBRARY_PATH=oddio_b200 /tmp/e2e_native [sources=65536] [callbacks=32] [frames=1024]
+ * (bench.py runs the in-tree build of this file, tools/e2e_native, for its `e2e` figure at N = 1.)
  */
 #include <math.h>
 #include <pthread.h>
@@ -17,7 +18,7 @@
 #include "oddio_b200.h"
 
 #define RATE 48000u
-#define FRAMES 1024u
+static uint32_t FRAMES = 1024u;
 #define WARMUP 3
 
 #define CHECK(call)                                                           \
@@ -73,13 +74,14 @@ static void* control_thread(void* arg) {
 int main(int argc, char** argv) {
     const uint32_t n_src = argc > 1 ? (uint32_t)atoi(argv[1]) : 65536u;
     const uint32_t n_cb = argc > 2 ? (uint32_t)atoi(argv[2]) : 32u;
+    if (argc > 3) FRAMES = (uint32_t)atoi(argv[3]);
     const uint32_t total = n_cb + WARMUP;
     const uint32_t L = RATE + (uint32_t)(1.16f * FRAMES * (float)(total + 2)) + 2048u;  /* start 1 s in, ds <= 1.16 */
     odb_ctx* ctx = NULL;
     odb_scene* scene = NULL;
     CHECK(odb_ctx_create(0, &ctx));
     CHECK(odb_scene_create(ctx, &scene));
-    CHECK(odb_set_kernel_variant(scene, 2));  /* the variant bench.py measures */
+    if (getenv("ODB_VARIANT")) CHECK(odb_set_kernel_variant(scene, (int)strtol(getenv("ODB_VARIANT"), NULL, 0)));  /* default: the library's */
     Control c;
     memset(&c, 0, sizeof c);
     c.scene = scene; c.n_src = n_src; c.n_upd = n_src / 16u ? n_src / 16u : 1u; c.n_callbacks = total;
