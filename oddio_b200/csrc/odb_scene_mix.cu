@@ -86,6 +86,7 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
     constexpr int LSTEP = CFG::LOOP == 0 ? 1 : 2;                                       // frames per lane step
     auto frame_of = [](int u) { return CFG::LOOP == 0 ? 32 * u : 64 * (u >> 1) + (u & 1); };
     const u64 magic = pk2(ODB_MAGIC, ODB_MAGIC);
+    const u64 g0 = STRICT ? 0ull : fma2(pk2(fbase, fbase), dgp, pgp);
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += ILP) {
         if (!FULL && c * ODB_SPATIAL_CHUNK + frame_of(j0) >= nfr) break;  // warp-uniform
@@ -153,10 +154,15 @@ __device__ __forceinline__ void consume_chunk(u64* __restrict__ acc, const int c
         u64 g[ILP], s[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
-            const float fi = fbase + (float)frame_of(j0 + u);  // `i as f32` (spatial.rs:459); exact small integer
-            const u64 fi2 = pk2(fi, fi);
-            if (STRICT) g[u] = mulx(fi2, dgp, nz);
-            else g[u] = fma2(fi2, dgp, pgp);
+            if (STRICT) {
+                const float fi = fbase + (float)frame_of(j0 + u);  // `i as f32` (spatial.rs:459); exact small integer
+                g[u] = mulx(pk2(fi, fi), dgp, nz);
+            } else {
+                // prev_gain + i * d_gain as (prev_gain + i0 * d_gain) + (i - i0) * d_gain, i0 = the lane's first frame of the
+                // chunk: the second term's factor is a compile-time constant, so no per-frame `i as f32` is needed
+                const float cj = (float)frame_of(j0 + u);
+                g[u] = frame_of(j0 + u) == 0 ? g0 : fma2(pk2(cj, cj), dgp, g0);
+            }
         }
         if (STRICT) {
 #pragma unroll
@@ -586,9 +592,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(A.peers.inbox[p]) + slot);
             for (int i = threadIdx.x; i < n_float4; i += blockDim.x) dst[i] = __ldcg(reinterpret_cast<const float4*>(A.xtile) + i);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) __threadfence_system();
-        __syncthreads();
+        __syncthreads();  // the release stores below are cumulative over the CTA's data stores through this barrier
         if (threadIdx.x < A.xg.world) {
             uint32_t* flag = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.flags_off) +
                              ((size_t)par * A.xg.world + A.xg.rank) * A.xg.max_slices;
@@ -618,8 +622,10 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             store_output(A, i / (2 * ODB_TILE_FRAMES), i % (2 * ODB_TILE_FRAMES), __ldcg(A.xtile + i));
     }
     __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();  // cumulative over the CTA's output stores and inbox reads
-    __syncthreads();
+    if (A.host_flag) {
+        if (threadIdx.x == 0) __threadfence_system();  // cumulative over the CTA's output stores (host memory)
+        __syncthreads();
+    }
     if (A.pull_seq != 0u && threadIdx.x < A.xg.world) {  // the peers may overwrite this slot `depth` exchanges on
         uint32_t* ack = reinterpret_cast<uint32_t*>(A.peers.inbox[threadIdx.x] + A.xg.acks_off) + (size_t)A.xg.rank * A.xg.max_slices;
         for (int sl = 0; sl < A.xg.max_slices; sl++) st_release_sys(ack + sl, A.pull_seq);

@@ -249,6 +249,12 @@ __device__ __forceinline__ void walk_seek_block(OdbSource* __restrict__ src, con
         te = te + (double)elapsed;                                      // :468
         sp->t = te;
     }
+    __syncthreads();
+    // ---- scatter the updated records back -------------------------------------------------------------------------
+    for (int w = tid; w < SM::SOURCES * WALK_REC_WORDS; w += THREADS) {
+        const int i = w / WALK_REC_WORDS, k = w - i * WALK_REC_WORDS;
+        if (i < n_here) reinterpret_cast<uint4*>(src + slot_sm[i])[k] = reinterpret_cast<const uint4*>(rec_sm + i)[k];
+    }
     // job counters: one atomic per warp into shared memory, one per block into HBM. Everything above only touches
     // what no earlier kernel still uses (this callback's job records, the source table); the counters are reset by the
     // previous callback's mix kernel, so this is where the grid waits for it (and, through it, for everything before).
@@ -260,11 +266,6 @@ __device__ __forceinline__ void walk_seek_block(OdbSource* __restrict__ src, con
     __syncthreads();
     if (tid == 0 && cnt_sm[0]) atomicAdd(counters + ODB_CNT_GENERAL, cnt_sm[0]);
     if (tid == 1 && cnt_sm[1]) atomicAdd(counters + ODB_CNT_FAST, cnt_sm[1]);
-    // ---- scatter the updated records back -------------------------------------------------------------------------
-    for (int w = tid; w < SM::SOURCES * WALK_REC_WORDS; w += THREADS) {
-        const int i = w / WALK_REC_WORDS, k = w - i * WALK_REC_WORDS;
-        if (i < n_here) reinterpret_cast<uint4*>(src + slot_sm[i])[k] = reinterpret_cast<const uint4*>(rec_sm + i)[k];
-    }
 }
 
 }  // namespace odbk

@@ -231,3 +231,45 @@ def test_ear_state_appendix_b(oracle, p, left, right):
 def test_rate_reciprocal_fast_path():  # SURVEY Appendix B note: f32(1/r)*f32(r) == 1.0 for common rates
     for r in (44100, 48000, 96000):
         assert F32(1.0) / F32(r) * F32(r) == F32(1.0)
+
+
+def test_sine_phase_wrap_and_the_c1_scenario(oracle):
+    """sine.rs:25-40 (no test in the reference: `Sine` is pinned here against an independent float32 statement of its
+    three lines) and BASELINE.json's C1: 8 x MonoToStereo(Sine) under Mixer<[f32; 2]>, 1024-frame callbacks
+    (examples/offline.rs:25-45 shape). The arguments of sinf are compared exactly; sinf itself is libm (glibc here, as
+    for the Rust std build) and is only required to agree with numpy's float32 sine to 1 ulp."""
+    o = oracle
+    F = np.float32
+    TAU = F(6.28318530717958647692)
+    rate, n = 48000, 1024
+    interval = F(1.0) / F(rate)
+    rng = np.random.default_rng(18)
+    params = [(F(rng.uniform(0, 2 * np.pi)), F(rng.uniform(100.0, 1000.0))) for _ in range(8)]
+    sines = [o.Sine(float(ph), float(hz)) for ph, hz in params]
+    mono_ref = []
+    for (ph, hz), s in zip(params, sines):
+        freq = F(hz * TAU)                                            # sine.rs:21
+        phase = ph
+        blocks = []
+        for _ in range(3):                                            # three blocks: the phase wraps several times
+            i = np.arange(n, dtype=F)
+            arg = (interval * i).astype(F) * freq + phase             # :36-37, every operation rounded to f32
+            arg = arg.astype(F)
+            got = o.run(s, rate, n)
+            want = np.sin(arg.astype(np.float64))
+            assert np.max(np.abs(got.astype(np.float64) - want)) <= 1.2e-7   # <= 1 ulp at |x| <= 1
+            blocks.append(got)
+            phase = F(np.fmod(F(phase + F(F(interval * F(n)) * freq)), TAU))  # :25-28
+            assert 0.0 <= phase < TAU
+        mono_ref.append(blocks)
+    # C1: the same eight sources (fresh state), duplicated to stereo and mixed in reverse set order (mixer.rs:100)
+    mx = o.Mixer(2)
+    for ph, hz in params:
+        mx.play(o.MonoToStereo(o.Sine(float(ph), float(hz))))
+    for b in range(3):
+        out = o.run(mx, rate, n)
+        acc = np.zeros(n, dtype=F)
+        for k in reversed(range(8)):
+            acc = (acc + mono_ref[k][b]).astype(F)
+        np.testing.assert_array_equal(out[:, 0], acc)
+        np.testing.assert_array_equal(out[:, 1], acc)                  # signal.rs:73-80 duplicates the sample

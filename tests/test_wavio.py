@@ -49,8 +49,9 @@ def test_offline_example_matches_oracle_render(tmp_path, oracle):
     sys.path.insert(0, os.path.join(ROOT, "examples"))
     import offline
 
-    dev_path, ref_path = str(tmp_path / "dev.wav"), str(tmp_path / "ref.wav")
-    offline.main(dev_path)
+    dev_path, ref_path, fma_path = str(tmp_path / "dev.wav"), str(tmp_path / "ref.wav"), str(tmp_path / "fma.wav")
+    offline.main(dev_path, kernel_variant=0)   # strict arithmetic: bit-identical f32 blocks
+    offline.main(fma_path)                     # the library default (FMA-contracted values): within one 16-bit step
     from oddio_b200 import wavio
 
     scene = oracle.SpatialScene()
@@ -61,6 +62,8 @@ def test_offline_example_matches_oracle_render(tmp_path, oracle):
     with wave.open(dev_path) as a, wave.open(ref_path) as b:
         assert a.getnframes() == b.getnframes() == 258 * 512
         assert a.readframes(a.getnframes()) == b.readframes(b.getnframes())
+    (_, xf), (_, xr) = wavio.read_wav(fma_path), wavio.read_wav(ref_path)
+    assert xf.shape == xr.shape and float(np.abs(xf - xr).max()) <= 1.01 / 32767.0
 
 
 @pytest.mark.gpu
