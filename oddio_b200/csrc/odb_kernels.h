@@ -57,7 +57,7 @@ void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const u
 void odb_launch_scatter_motion(OdbSource* src, const OdbMotionMsg* msgs, int n, cudaStream_t st);
 void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, cudaStream_t st);
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
-                          uint32_t* counters, const OdbCallback& cb, cudaStream_t st);
+                          uint32_t* counters, uint32_t* zero_counters, int late_wait, const OdbCallback& cb, cudaStream_t st);
 int odb_mix_general_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
                                    int only_flagged, const uint32_t* counters, cudaStream_t st);
@@ -68,12 +68,12 @@ struct OdbSceneMixArgs {
     int epilogue;                     // 0 none, 1 Tanh, 2 Reinhard, | ODB_EPILOGUE_I16_BIT
     float* partials;                  // [n_tiles][grid][2 * ODB_TILE_FRAMES]
     float* out;                       // interleaved stereo, device or pinned host memory (f32, or int16 with the I16 bit)
-    const uint32_t* counters;         // this callback's job counters (NULL: always scan for flagged jobs)
-    uint32_t* zero_counters;          // the other parity's counters, reset for the next callback (may be NULL)
-    unsigned long long* arrive;       // monotonic count of (CTA, tile) arrivals over the life of the scene
+    unsigned long long* arrive;       // monotonic count of (CTA, tile) arrivals of this callback parity
     unsigned long long arrive_base;   // its value before this launch
-    unsigned long long* done;         // monotonic count of finished CTAs (NULL: the reduce phase stores the output itself)
+    unsigned long long* done;         // monotonic count of finished CTAs of this callback parity
     unsigned long long done_base;
+    unsigned long long* completed;    // sequence number of the last callback kernel that has finished entirely
+    unsigned long long my_seq;        // this launch's sequence number; it starts once `completed` >= my_seq - 2
     unsigned long long* host_flag;    // pinned host word that receives `seq` when the whole grid has stored its output
     unsigned long long seq;
     const uint32_t* removed_count;    // optional: the walk kernel's removal-report count ...

@@ -48,8 +48,12 @@ struct odb_scene {
     // arrive / done counters and the running totals the kernel compares them with.
     DevBuf<float> d_partials_fused[2];
     DevBuf<float> d_xtile[2];            // this rank's raw sum, handed to the grid's last CTA (exchange / host tile)
-    DevBuf<unsigned long long> d_sync;   // [0] arrivals, [1] finished CTAs, [2] CTAs whose exchange pushes are out
-    unsigned long long arrive_total = 0, done_total = 0;
+    DevBuf<unsigned long long> d_sync;   // [0..1] arrivals by callback parity, [2..3] finished CTAs by parity, [4] last completed launch
+    unsigned long long arrive_total[2] = {0, 0}, done_total[2] = {0, 0};
+    unsigned long long fused_seq = 0;    // launches of the one-launch kernel so far
+    DevBuf<uint32_t> d_counters_ring;    // four sets of job counters: callback k uses set k % 4 (see odb_walk.cuh)
+    uint32_t* last_counters = nullptr;   // the set the last callback counted into
+    DevBuf<OdbJob> d_jobs_ring[3];       // the one-launch callback's job records: launch k uses set k % 3
     bool legacy = false;                 // odb_set_kernel_variant bit 9: the multi-kernel path of round 1
     bool flag_armed = false;             // the callback just queued publishes flag_seq to h_flag when its tile is stored
     bool count_by_kernel = false;        // ... and the seek set's removal-report count to seek.h_removed_count
@@ -114,7 +118,8 @@ extern "C" int odb_scene_destroy(odb_scene* scene) {
     cudaStreamDestroy(scene->wst);
     scene->d_partials.release(); scene->d_partials_fast.release(); scene->d_partials_ring.release();
     scene->d_partials_fused[0].release(); scene->d_partials_fused[1].release(); scene->d_sync.release(); scene->h_flag.release();
-    scene->d_xtile[0].release(); scene->d_xtile[1].release();
+    scene->d_xtile[0].release(); scene->d_xtile[1].release(); scene->d_counters_ring.release();
+    for (int q = 0; q < 3; q++) scene->d_jobs_ring[q].release();
     scene->d_out.release();
     scene->h_out.release();
     if (scene->ev0) { cudaEventDestroy(scene->ev0); cudaEventDestroy(scene->ev1); }
@@ -425,11 +430,29 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
                                  counters, scene->d_ring_list[p].p, cbb, wst);
         launches++;
     }
-    if (ns > 0) {
+    const bool fused = nb == 0 && ns > 0 && nt > 0 && !scene->legacy;
+    if (fused && !scene->d_counters_ring.p) {
+        ODB_TRY(ensure_idle(scene, scene->d_counters_ring, 4 * ODB_CNT_WORDS));
+        ODB_CUDA(cudaMemsetAsync(scene->d_counters_ring.p, 0, 4 * ODB_CNT_WORDS * sizeof(uint32_t), wst));
+    }
+    OdbJob* fused_jobs = nullptr;
+    if (fused) {
+        // the one-launch callback: counters from a ring of four sets, job records from a ring of three, no wait in
+        // the walk (odb_walk.cuh, odb_scene_mix.cu)
+        const unsigned long long k = scene->fused_seq;
+        counters = scene->d_counters_ring.p + (k & 3) * ODB_CNT_WORDS;
+        ODB_TRY(ensure_idle(scene, scene->d_jobs_ring[k % 3], (size_t)ns * nt));
+        fused_jobs = scene->d_jobs_ring[k % 3].p;
+        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, fused_jobs, scene->seek.d_removed.p,
+                             (int)scene->seek.removed_cap, counters, scene->d_counters_ring.p + ((k + 2) & 3) * ODB_CNT_WORDS,
+                             /*late_wait=*/0, cb, wst);
+        launches++;
+    } else if (ns > 0) {
         odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs[p].p, scene->seek.d_removed.p,
-                             (int)scene->seek.removed_cap, counters, cb, wst);
+                             (int)scene->seek.removed_cap, counters, nullptr, /*late_wait=*/1, cb, wst);
         launches++;
     }
+    scene->last_counters = counters;
     seg(0);
     if (scene->pipelined) {
         ODB_CUDA(cudaEventRecord(scene->ev_walk[p], wst));
@@ -438,25 +461,29 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     }
     const bool use_fast = scene->variant != 1;
     // ---- the one-launch callback: staged mix + literal tail + grid reduce + epilogue (seek set only) ----------------
-    if (nb == 0 && ns > 0 && nt > 0 && !scene->legacy) {
+    if (fused) {
         const int n_ctas = odb_scene_mix_ctas(ns, ctx->sm_count);
-        ODB_TRY(ensure_idle(scene, scene->d_partials_fused[p], (size_t)nt * n_ctas * 2 * ODB_TILE_FRAMES));
+        ODB_TRY(ensure_idle(scene, scene->d_partials_fused[scene->fused_seq & 1], (size_t)nt * n_ctas * 2 * ODB_TILE_FRAMES));
         if (!scene->d_sync.p) {
-            ODB_TRY(ensure_idle(scene, scene->d_sync, 4));
-            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 4 * sizeof(unsigned long long), st));
+            ODB_TRY(ensure_idle(scene, scene->d_sync, 8));
+            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 8 * sizeof(unsigned long long), st));
         }
+        const int fp = (int)(scene->fused_seq & 1);  // parity of this launch among the one-launch kernels
         OdbSceneMixArgs a;
         memset(&a, 0, sizeof a);
-        a.jobs = scene->d_jobs[p].p;
+        a.jobs = fused_jobs;
         a.n_sources = ns; a.n_tiles = nt; a.n_frames = (int)n_frames;
         a.epilogue = scene->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0);
-        a.partials = scene->d_partials_fused[p].p;
+        a.partials = scene->d_partials_fused[fp].p;
         a.out = dev_out;
-        a.counters = counters;
-        a.zero_counters = scene->pipelined ? nullptr : scene->d_counters[p ^ 1].p;
-        a.arrive = scene->d_sync.p;
-        a.arrive_base = scene->arrive_total;
-        scene->arrive_total += (unsigned long long)nt * (unsigned long long)n_ctas;
+        a.arrive = scene->d_sync.p + fp;
+        a.arrive_base = scene->arrive_total[fp];
+        scene->arrive_total[fp] += (unsigned long long)nt * (unsigned long long)n_ctas;
+        a.done = scene->d_sync.p + 2 + fp;
+        a.done_base = scene->done_total[fp];
+        scene->done_total[fp] += (unsigned long long)n_ctas;
+        a.completed = scene->d_sync.p + 4;
+        a.my_seq = ++scene->fused_seq;
         if (xr) {  // multi-GPU: the reduce phase pushes (and pulls) over NVLink peer memory
             odb_exchange* ex = xr->ex;
             a.peers = ex->peers;
@@ -470,11 +497,8 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
             }
         }
         if (host_flag || xr) {  // the grid's last CTA finishes the callback from the raw sum in xtile
-            ODB_TRY(ensure_idle(scene, scene->d_xtile[p], (size_t)nt * 2 * ODB_TILE_FRAMES));
-            a.xtile = scene->d_xtile[p].p;
-            a.done = scene->d_sync.p + 1;
-            a.done_base = scene->done_total;
-            scene->done_total += (unsigned long long)n_ctas;
+            ODB_TRY(ensure_idle(scene, scene->d_xtile[fp], (size_t)nt * 2 * ODB_TILE_FRAMES));
+            a.xtile = scene->d_xtile[fp].p;
         }
         bool count_by_kernel = false;
         if (host_flag) {
@@ -820,11 +844,10 @@ extern "C" int odb_last_job_counters(void* owner, uint32_t out[4]) {
     if (kind != ODB_KIND_SCENE) return odb_fail(ODB_E_INVALID, "owner is neither a scene nor a mixer");
     odb_scene* sc = (odb_scene*)owner;
     for (int i = 0; i < 4; i++) out[i] = 0;
-    const int p = (int)((sc->callback_no + 1) & 1);  // parity of the last callback
-    if (sc->callback_no == 0 || !sc->d_counters[p].p) return ODB_OK;
+    if (sc->callback_no == 0 || !sc->last_counters) return ODB_OK;
     ODB_CUDA(cudaSetDevice(sc->ctx->device));
     ODB_CUDA(cudaStreamSynchronize(sc->ctx->stream));
-    ODB_CUDA(cudaMemcpyAsync(out, sc->d_counters[p].p, ODB_CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    ODB_CUDA(cudaMemcpyAsync(out, sc->last_counters, ODB_CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
     ODB_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return ODB_OK;
 }

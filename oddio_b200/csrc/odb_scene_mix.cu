@@ -337,9 +337,20 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    pdl_wait();               // job records and counters come from the walk kernel launched just before
-    pdl_launch_dependents();  // after the wait: whatever starts early (the next callback's walk) finds this callback's walk complete
-    if (A.zero_counters && blockIdx.x == 0 && threadIdx.x < ODB_CNT_WORDS) A.zero_counters[threadIdx.x] = 0u;
+    pdl_wait();               // the job records come from the walk kernel launched just before
+    // Neither this kernel nor the walk waits for the PREVIOUS callback's kernel to finish (its last CTA may still be
+    // exchanging tiles with the other GPUs while this grid mixes). What consecutive callbacks share is double-buffered
+    // by callback parity - partial tiles, xtile, the arrive / done counters - and the job records live in a ring of
+    // three, so the one thing to wait for is the callback before the previous one (almost never an actual wait).
+    if (A.my_seq > 2ull) {
+        if (threadIdx.x == 0)
+            while (ld_acquire_u64(A.completed) < A.my_seq - 2ull) __nanosleep(40);
+        __syncthreads();
+    }
+    // Only now may the next callback's walk start: it finds this callback's walk complete (the wait above) and callback
+    // my_seq - 2 finished entirely, whose job records it overwrites.
+    pdl_launch_dependents();
+    bool saw_flagged = false;  // one of this warp's jobs needs the literal path
     uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
     uint32_t buf = 0;
 
@@ -367,6 +378,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
         u64 acc[NACC];
 #pragma unroll
         for (int j = 0; j < NACC; j++) acc[j] = 0ull;
+        saw_flagged = false;
         const float lanef = (float)(tl * ODB_TILE_FRAMES + (CFG::LOOP == 0 ? lane : 2 * lane));
         const OdbJob* tile_jobs = A.jobs + (size_t)tl * n_sources;
 
@@ -381,11 +393,12 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             }
             __syncwarp();
             // lane q < BATCH derives what this part needs of source q and rewrites its private record (SJ_* words)
-            bool mine = false;
+            bool mine = false, flagged = false;
             if (lane < BATCH) {
                 const uint4 h = lds_u128(rec(lane, 0));                                     // pcm lo/hi, len, flags
                 const int nfr = (int)lds_u32(rec(lane, ODB_JW_N_FRAMES));
                 mine = !(h.w & (ODB_JF_SKIP | ODB_JF_GENERAL)) && nfr > first_frame;
+                flagged = (h.w & ODB_JF_GENERAL) && !(h.w & (ODB_JF_SKIP | ODB_JF_RING));
                 if (mine) {
                     int w_start, w_len;
                     if (SPLIT == 2) {
@@ -419,6 +432,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             }
             __syncwarp();
             uint32_t act = __ballot_sync(0xffffffffu, mine);
+            saw_flagged = saw_flagged || __any_sync(0xffffffffu, flagged);
             if (act) {
                 start_copy(__ffs(act) - 1, buf);
                 {   // 2. literal cursor chains: lane = (source q, ear e, chunk cc of this part)
@@ -497,8 +511,8 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             }
         }
         __syncwarp();
-        // 3'. the flagged jobs of this warp's batches, literally (rare: none on C3)
-        if (A.counters == nullptr || __ldcg(A.counters + ODB_CNT_GENERAL) != 0u) {
+        // 3'. the flagged jobs of this warp's batches, literally (rare: none on C3); the batch prologues noticed them
+        if (saw_flagged) {
             float2* tile = reinterpret_cast<float2*>(smem_raw + warp * CFG::WARP_BYTES);
             float* scratch = reinterpret_cast<float*>(smem_raw + warp * CFG::WARP_BYTES + CFG::PART_FRAMES * 8);
             for (int bi = gp; bi < n_batches; bi += GP) {
@@ -561,13 +575,13 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
         }
         __syncthreads();  // the warp regions are reused by the next tile
     }
-    if (!A.done) return;
-    // ---- the grid's last CTA finishes the callback: the exchange over NVLink and / or the hand-over to the host. Every
-    // other CTA leaves here, so its SM is free for the next callback's kernels while the last one waits on fences and peers.
+    // ---- the grid's last CTA finishes the callback: the exchange over NVLink and / or the hand-over to the host, and
+    // the completion sequence number. Every other CTA leaves here, so its SM is free for the next callback's kernels
+    // while the last one waits on fences and peers.
     __shared__ int last_done;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();  // one device-scope fence per CTA, cumulative over its xtile stores through the barrier
+        __threadfence();  // one device-scope fence per CTA, cumulative over its stores through the barrier
         const unsigned long long d = atomicAdd(A.done, 1ull) + 1ull;
         last_done = d == A.done_base + (unsigned long long)G;
         if (last_done) __threadfence();
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             for (int p = 0; p < A.xg.world; p++) sum = sum + __ldcv(in + (size_t)p * A.xg.cap + i);
             store_output(A, i / (2 * ODB_TILE_FRAMES), i % (2 * ODB_TILE_FRAMES), sum);
         }
-    } else if (A.push_seq == 0u) {
+    } else if (A.push_seq == 0u && A.xtile) {
         // one GPU, host tile: epilogue and store into (pinned) host memory, 512 coalesced lanes
         for (int i = threadIdx.x; i < n_floats; i += blockDim.x)
             store_output(A, i / (2 * ODB_TILE_FRAMES), i % (2 * ODB_TILE_FRAMES), __ldcg(A.xtile + i));
@@ -636,6 +650,11 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             __threadfence_system();
         }
         *reinterpret_cast<volatile unsigned long long*>(A.host_flag) = A.seq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // everything of this callback is done: its parity's buffers may be reused
+        __threadfence();
+        atomicMax(A.completed, A.my_seq);
     }
 }
 

@@ -50,17 +50,21 @@ __global__ void k_scatter_params(OdbSource* __restrict__ src, const OdbParamMsg*
 // ------------------------------------------------------------------------------------------
 // walk_set for the seek set (spatial.rs:191-265) and the per-chunk set-up of the mix closure: see odb_walk.cuh.
 constexpr int WALK_THREADS = 128;
+// LATE: round 1's multi-kernel callback (and the buffered set's companion): waits for the previous callback's kernels
+// before it touches the job counters. !LATE: the one-launch callback - no wait at all; ordering against earlier
+// callbacks comes from the launch dependencies and the callback kernel's own completion counter (odb_scene_mix.cu).
+template <bool LATE>
 __global__ void __launch_bounds__(WALK_THREADS) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                              OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
-                                                             int removed_cap, uint32_t* __restrict__ counters, OdbCallback cb) {
+                                                             int removed_cap, uint32_t* __restrict__ counters,
+                                                             uint32_t* __restrict__ zero_counters, OdbCallback cb) {
     __shared__ __align__(16) unsigned char smem[WalkSmem<WALK_THREADS>::BYTES];
     // Launched behind the previous callback's mix kernel, which lets its dependents start once ITS walk is complete:
-    // this grid's blocks run as SMs come free, under the tail of that kernel (its last CTA's exchange), and wait for it
-    // only before they touch the job counters (odb_walk.cuh). Control-plane scatter kernels are ordinary launches
+    // this grid's blocks run as SMs come free, under that kernel. Control-plane scatter kernels are ordinary launches
     // and therefore complete before this grid starts.
     pdl_launch_dependents();  // the mix kernel may be set up now; it waits for this grid before reading jobs
-    walk_seek_block<WALK_THREADS, true>(src, order, jobs, removed, removed_cap, counters, cb, blockIdx.x * (WALK_THREADS / 2), smem,
-                                  threadIdx.x);
+    walk_seek_block<WALK_THREADS, LATE>(src, order, jobs, removed, removed_cap, counters, zero_counters, cb,
+                                        blockIdx.x * (WALK_THREADS / 2), smem, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -282,11 +286,14 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
     k_scatter_params<<<(n + 127) / 128, 128, 0, st>>>(src, msgs, n);
 }
 void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
-                          uint32_t* counters, const OdbCallback& cb, cudaStream_t st) {
+                          uint32_t* counters, uint32_t* zero_counters, int late_wait, const OdbCallback& cb, cudaStream_t st) {
     if (cb.n_sources <= 0) return;
     const int per_block = WALK_THREADS / 2;
-    odb_launch_pdl(k_walk_seek, dim3((cb.n_sources + per_block - 1) / per_block), dim3(WALK_THREADS), 0, st, src, order, jobs, removed,
-                   removed_cap, counters, cb);
+    const dim3 grid((cb.n_sources + per_block - 1) / per_block);
+    if (late_wait)
+        odb_launch_pdl(k_walk_seek<true>, grid, dim3(WALK_THREADS), 0, st, src, order, jobs, removed, removed_cap, counters, zero_counters, cb);
+    else
+        odb_launch_pdl(k_walk_seek<false>, grid, dim3(WALK_THREADS), 0, st, src, order, jobs, removed, removed_cap, counters, zero_counters, cb);
 }
 
 static const int GEN_WARPS = 8;

@@ -40,8 +40,8 @@ struct WalkSmem {
 template <int THREADS, bool LATE_WAIT>
 __device__ __forceinline__ void walk_seek_block(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                 OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed, const int removed_cap,
-                                                uint32_t* __restrict__ counters, const OdbCallback& cb, const int first,
-                                                unsigned char* __restrict__ smem, const int tid) {
+                                                uint32_t* __restrict__ counters, uint32_t* __restrict__ zero_counters,
+                                                const OdbCallback& cb, const int first, unsigned char* __restrict__ smem, const int tid) {
     typedef WalkSmem<THREADS> SM;
     OdbSource* rec_sm = reinterpret_cast<OdbSource*>(smem);
     OdbJob* job_sm = reinterpret_cast<OdbJob*>(smem + SM::REC_BYTES);
@@ -256,9 +256,13 @@ __device__ __forceinline__ void walk_seek_block(OdbSource* __restrict__ src, con
         if (i < n_here) reinterpret_cast<uint4*>(src + slot_sm[i])[k] = reinterpret_cast<const uint4*>(rec_sm + i)[k];
     }
     // job counters: one atomic per warp into shared memory, one per block into HBM. Everything above only touches
-    // what no earlier kernel still uses (this callback's job records, the source table); the counters are reset by the
-    // previous callback's mix kernel, so this is where the grid waits for it (and, through it, for everything before).
+    // what no earlier kernel still uses (this callback's job records, the source table). LATE_WAIT (round 1's
+    // multi-kernel callback): the counters are reset by the previous callback's reduce kernel, so this is where the grid
+    // waits for it. Otherwise the counters live in a ring of four sets: this grid resets the set of the callback after
+    // next (`zero_counters`), which that callback's walk cannot reach before this grid has completed (the launch
+    // dependencies walk k -> mix k -> walk k + 1 -> mix k + 1 -> walk k + 2 are each "complete before start").
     if (LATE_WAIT) pdl_wait();
+    if (zero_counters && first == 0 && tid < ODB_CNT_WORDS) zero_counters[tid] = 0u;
     n_general = __reduce_add_sync(full, n_general);
     n_fast = __reduce_add_sync(full, n_fast);
     if (lane == 0 && n_general) atomicAdd(cnt_sm + 0, n_general);
