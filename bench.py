@@ -288,7 +288,7 @@ def timed_device_pass(rig, clk, exchange_mode, reduce_every=1, depth=4, lag=1):
     note = ""
     with torch.cuda.stream(stream):
         ctl, scene, handles = rig.new_scene()
-        if world == 1:
+        if world == 1 or exchange_mode == "none":
             tiles = [torch.zeros((M, 2), device=dev, dtype=torch.float32) for _ in range(2)]
             k_no = [0]
 
@@ -302,6 +302,7 @@ def timed_device_pass(rig, clk, exchange_mode, reduce_every=1, depth=4, lag=1):
             def last_tile():
                 return tiles[(k_no[0] - 1) & 1]
             launches_per_step = None
+            exch = None
         elif exchange_mode == "kernel":
             exch = PeerExchange.from_torch(rig.ctx, M * 2, depth=max(2, min(8, depth)))
             tiles = [torch.zeros((M, 2), device=dev, dtype=torch.float32) for _ in range(lag + 2)]
@@ -384,7 +385,7 @@ def timed_device_pass(rig, clk, exchange_mode, reduce_every=1, depth=4, lag=1):
         for _ in range(W):
             step()
         drain()
-        if world > 1 and exchange_mode != "kernel":  # every group buffer / inbox slot has been through the exchange once
+        if world > 1 and exchange_mode not in ("kernel", "none"):  # every group buffer / inbox slot has been through the exchange once
             for _ in range(NG * R):
                 step()
             drain()
@@ -407,7 +408,7 @@ def timed_device_pass(rig, clk, exchange_mode, reduce_every=1, depth=4, lag=1):
         assert scene.len() == rig.n_local, "a source finished during the timed region"
         checksum = float(last_tile().abs().sum().item())
         scene.close()
-        if world > 1 and exch is not None:
+        if world > 1 and exchange_mode != "none" and exch is not None:
             exch.close()
     return {"ms": ms, "host_us": host_us, "counters": counters, "checksum": checksum, "note": note,
             "launches_per_step": own + (launches_per_step or 0.0)}
@@ -679,7 +680,8 @@ def run_ours(args):
                                      f"into every rank's inbox over NVLink peer memory ({M * 8} B per rank pair) and sums callback k - {args.lag} "
                                      "in rank order (odb_scene_sample_exchange)",
                "peer": f", tiles summed by the library's stand-alone peer-memory kernels over NVLink, one exchange per {args.reduce_every} callbacks, overlapped with the next mixes",
-               "nccl": f", one NCCL all-reduce per {args.reduce_every} callbacks, overlapped with the next mixes"}[mode] + main["note"]
+               "nccl": f", one NCCL all-reduce per {args.reduce_every} callbacks, overlapped with the next mixes",
+               "none": ", NO exchange of the tiles (diagnostic: the per-rank callback rate)"}[mode] + main["note"]
         legacy = bool(args.variant & 0x200)
         kname = ("k_mix_fast" if legacy else "k_scene_mix") + ("<strict>" if (args.variant & 0xFF) == 0 else "<fma>")
         out = {
@@ -1051,7 +1053,7 @@ def main():
     ap.add_argument("--skip-extras", action="store_true", help="N > 1: headline only (no parity pass, no weak-scaling / reduce-every-8 passes)")
     ap.add_argument("--reduce-every", type=int, default=1, help="N > 1, --exchange peer|nccl: callbacks per exchange of the tiles")
     ap.add_argument("--exchange-depth", type=int, default=4, help="N > 1: group buffers (exchanges) in flight, 2..8")
-    ap.add_argument("--exchange", default="kernel", choices=["kernel", "peer", "nccl"],
+    ap.add_argument("--exchange", default="kernel", choices=["kernel", "peer", "nccl", "none"],
                     help="N > 1: how the per-GPU tiles are summed: kernel (default) = from inside the callback kernel over NVLink peer "
                          "memory, every callback; peer = the library's stand-alone push / pull kernels; nccl = torch.distributed")
     ap.add_argument("--variant", type=lambda v: int(v, 0), default=2,

@@ -56,8 +56,11 @@ void odb_launch_convert_i16(const short* in, float* out, size_t n, float max_val
 void odb_launch_scatter_sources(OdbSource* src, const OdbSource* staged, const uint32_t* slots, int n, cudaStream_t st);
 void odb_launch_scatter_motion(OdbSource* src, const OdbMotionMsg* msgs, int n, cudaStream_t st);
 void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, cudaStream_t st);
-void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
-                          uint32_t* counters, uint32_t* zero_counters, int late_wait, const OdbCallback& cb, cudaStream_t st);
+// `walked` != NULL: the one-launch callback's walk (no waits; every block counts itself into `walked` when it is done).
+// Returns the number of blocks launched.
+int odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
+                         uint32_t* counters, uint32_t* zero_counters, unsigned long long* walked, const OdbCallback& cb,
+                         cudaStream_t st);
 int odb_mix_general_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas,
                                    int only_flagged, const uint32_t* counters, cudaStream_t st);
@@ -72,6 +75,8 @@ struct OdbSceneMixArgs {
     unsigned long long arrive_base;   // its value before this launch
     unsigned long long* done;         // monotonic count of finished CTAs of this callback parity
     unsigned long long done_base;
+    const unsigned long long* walked; // walk blocks finished so far (all callbacks); this launch's job records are complete ...
+    unsigned long long walked_target; // ... when it reaches this
     unsigned long long* completed;    // sequence number of the last callback kernel that has finished entirely
     unsigned long long my_seq;        // this launch's sequence number; it starts once `completed` >= my_seq - 2
     unsigned long long* host_flag;    // pinned host word that receives `seq` when the whole grid has stored its output

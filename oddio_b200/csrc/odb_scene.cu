@@ -51,6 +51,7 @@ struct odb_scene {
     DevBuf<unsigned long long> d_sync;   // [0..1] arrivals by callback parity, [2..3] finished CTAs by parity, [4] last completed launch
     unsigned long long arrive_total[2] = {0, 0}, done_total[2] = {0, 0};
     unsigned long long fused_seq = 0;    // launches of the one-launch kernel so far
+    unsigned long long walked_total = 0; // walk blocks launched for it so far (d_sync[5] counts the finished ones)
     DevBuf<uint32_t> d_counters_ring;    // four sets of job counters: callback k uses set k % 4 (see odb_walk.cuh)
     uint32_t* last_counters = nullptr;   // the set the last callback counted into
     DevBuf<OdbJob> d_jobs_ring[3];       // the one-launch callback's job records: launch k uses set k % 3
@@ -443,13 +444,17 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         counters = scene->d_counters_ring.p + (k & 3) * ODB_CNT_WORDS;
         ODB_TRY(ensure_idle(scene, scene->d_jobs_ring[k % 3], (size_t)ns * nt));
         fused_jobs = scene->d_jobs_ring[k % 3].p;
-        odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, fused_jobs, scene->seek.d_removed.p,
-                             (int)scene->seek.removed_cap, counters, scene->d_counters_ring.p + ((k + 2) & 3) * ODB_CNT_WORDS,
-                             /*late_wait=*/0, cb, wst);
+        if (!scene->d_sync.p) {
+            ODB_TRY(ensure_idle(scene, scene->d_sync, 8));
+            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 8 * sizeof(unsigned long long), wst));
+        }
+        scene->walked_total += (unsigned long long)odb_launch_walk_seek(
+            scene->seek.d_src.p, scene->seek.d_order.p, fused_jobs, scene->seek.d_removed.p, (int)scene->seek.removed_cap, counters,
+            scene->d_counters_ring.p + ((k + 2) & 3) * ODB_CNT_WORDS, scene->d_sync.p + 5, cb, wst);
         launches++;
     } else if (ns > 0) {
         odb_launch_walk_seek(scene->seek.d_src.p, scene->seek.d_order.p, scene->d_jobs[p].p, scene->seek.d_removed.p,
-                             (int)scene->seek.removed_cap, counters, nullptr, /*late_wait=*/1, cb, wst);
+                             (int)scene->seek.removed_cap, counters, nullptr, nullptr, cb, wst);
         launches++;
     }
     scene->last_counters = counters;
@@ -464,10 +469,6 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     if (fused) {
         const int n_ctas = odb_scene_mix_ctas(ns, ctx->sm_count);
         ODB_TRY(ensure_idle(scene, scene->d_partials_fused[scene->fused_seq & 1], (size_t)nt * n_ctas * 2 * ODB_TILE_FRAMES));
-        if (!scene->d_sync.p) {
-            ODB_TRY(ensure_idle(scene, scene->d_sync, 8));
-            ODB_CUDA(cudaMemsetAsync(scene->d_sync.p, 0, 8 * sizeof(unsigned long long), st));
-        }
         const int fp = (int)(scene->fused_seq & 1);  // parity of this launch among the one-launch kernels
         OdbSceneMixArgs a;
         memset(&a, 0, sizeof a);
@@ -482,6 +483,8 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
         a.done = scene->d_sync.p + 2 + fp;
         a.done_base = scene->done_total[fp];
         scene->done_total[fp] += (unsigned long long)n_ctas;
+        a.walked = scene->d_sync.p + 5;
+        a.walked_target = scene->walked_total;
         a.completed = scene->d_sync.p + 4;
         a.my_seq = ++scene->fused_seq;
         if (xr) {  // multi-GPU: the reduce phase pushes (and pulls) over NVLink peer memory

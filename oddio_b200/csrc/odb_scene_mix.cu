@@ -337,7 +337,12 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    pdl_wait();               // the job records come from the walk kernel launched just before
+    // The job records come from the walk kernel launched just before: this grid starts when every walk block has
+    // counted itself into `walked` (its trigger comes after that), and acquires the count - no griddepcontrol.wait,
+    // which would also wait for everything the walk was launched behind (the previous callback's exchange tail).
+    if (threadIdx.x == 0)
+        while (ld_acquire_u64(A.walked) < A.walked_target) __nanosleep(20);
+    __syncthreads();
     // Neither this kernel nor the walk waits for the PREVIOUS callback's kernel to finish (its last CTA may still be
     // exchanging tiles with the other GPUs while this grid mixes). What consecutive callbacks share is double-buffered
     // by callback parity - partial tiles, xtile, the arrive / done counters - and the job records live in a ring of

@@ -57,14 +57,26 @@ template <bool LATE>
 __global__ void __launch_bounds__(WALK_THREADS) k_walk_seek(OdbSource* __restrict__ src, const uint32_t* __restrict__ order,
                                                              OdbJob* __restrict__ jobs, uint32_t* __restrict__ removed,
                                                              int removed_cap, uint32_t* __restrict__ counters,
-                                                             uint32_t* __restrict__ zero_counters, OdbCallback cb) {
+                                                             uint32_t* __restrict__ zero_counters,
+                                                             unsigned long long* __restrict__ walked, OdbCallback cb) {
     __shared__ __align__(16) unsigned char smem[WalkSmem<WALK_THREADS>::BYTES];
     // Launched behind the previous callback's mix kernel, which lets its dependents start once ITS walk is complete:
     // this grid's blocks run as SMs come free, under that kernel. Control-plane scatter kernels are ordinary launches
     // and therefore complete before this grid starts.
-    pdl_launch_dependents();  // the mix kernel may be set up now; it waits for this grid before reading jobs
+    if (LATE) pdl_launch_dependents();  // round 1's mix kernel may be set up now; it waits for this grid (griddepcontrol.wait)
     walk_seek_block<WALK_THREADS, LATE>(src, order, jobs, removed, removed_cap, counters, zero_counters, cb,
                                         blockIdx.x * (WALK_THREADS / 2), smem, threadIdx.x);
+    if (!LATE) {
+        // The one-launch callback kernel does not use griddepcontrol.wait (a dependent grid's completion is ordered
+        // behind its primary's, which would put the previous callback's exchange tail back on the critical path): it
+        // starts when every block of this grid has got here, and reads `walked` with acquire semantics.
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(walked, 1ull);
+        }
+        pdl_launch_dependents();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -285,15 +297,19 @@ void odb_launch_scatter_params(OdbSource* src, const OdbParamMsg* msgs, int n, c
     if (n <= 0) return;
     k_scatter_params<<<(n + 127) / 128, 128, 0, st>>>(src, msgs, n);
 }
-void odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
-                          uint32_t* counters, uint32_t* zero_counters, int late_wait, const OdbCallback& cb, cudaStream_t st) {
-    if (cb.n_sources <= 0) return;
+int odb_launch_walk_seek(OdbSource* src, const uint32_t* order, OdbJob* jobs, uint32_t* removed, int removed_cap,
+                         uint32_t* counters, uint32_t* zero_counters, unsigned long long* walked, const OdbCallback& cb,
+                         cudaStream_t st) {
+    if (cb.n_sources <= 0) return 0;
     const int per_block = WALK_THREADS / 2;
     const dim3 grid((cb.n_sources + per_block - 1) / per_block);
-    if (late_wait)
-        odb_launch_pdl(k_walk_seek<true>, grid, dim3(WALK_THREADS), 0, st, src, order, jobs, removed, removed_cap, counters, zero_counters, cb);
+    if (!walked)
+        odb_launch_pdl(k_walk_seek<true>, grid, dim3(WALK_THREADS), 0, st, src, order, jobs, removed, removed_cap, counters, zero_counters,
+                       walked, cb);
     else
-        odb_launch_pdl(k_walk_seek<false>, grid, dim3(WALK_THREADS), 0, st, src, order, jobs, removed, removed_cap, counters, zero_counters, cb);
+        odb_launch_pdl(k_walk_seek<false>, grid, dim3(WALK_THREADS), 0, st, src, order, jobs, removed, removed_cap, counters, zero_counters,
+                       walked, cb);
+    return (int)grid.x;
 }
 
 static const int GEN_WARPS = 8;
