@@ -133,8 +133,14 @@ __global__ void __launch_bounds__(128) k_walk_buffered(OdbSource* __restrict__ s
             fj->base[e][c] = 0;
             fj->off0[e][c] = off0;
             const int lo = (int)off0;
-            const int hi = ds_ok ? (int)__fmaf_rn((float)(m - 1), rds, off0) + 4 : 0x7ffffff0;
-            if (!ds_ok || lo < 0 || hi > s.ring_cap - 2) wrap_tiles |= 1u << tl;  // x + 1 must stay below buffer.len()
+            // The staged kernel's window and its index split assume the f32 chain `offset += ds` stays within a few
+            // samples of off0 + k * rds. off0 is an absolute ring offset here: from 2^17 samples on, ulp(off0) >= 1/64
+            // and 255 roundings may drift by more than the margin - those reads take the literal ring kernel, which
+            // walks the chain itself (a ring that long is max_distance > 900 m at 48 kHz).
+            const float last_est = __fmaf_rn((float)(m - 1), rds, off0);
+            const bool far = !(last_est < 131072.0f);
+            const int hi = (ds_ok && !far) ? (int)last_est + 4 : 0x7ffffff0;
+            if (!ds_ok || far || lo < 0 || hi > s.ring_cap - 2) wrap_tiles |= 1u << tl;  // x + 1 must stay below buffer.len()
             const int h = c / ODB_FAST_HALF_CHUNKS;
             wlo[tl][h] = min(wlo[tl][h], lo);
             whi[tl][h] = max(whi[tl][h], hi);

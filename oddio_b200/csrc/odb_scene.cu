@@ -220,7 +220,7 @@ extern "C" int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain,
     s.state_dt = 0.0f;
     const float max_delay = max_distance / 343.0f + buffer_duration;             // spatial.rs:330
     const float capf = ceilf(max_delay * (float)rate);                           // spatial.rs:39
-    if (!(capf >= 1.0f) || capf > 268435456.0f) {
+    if (!(capf >= 1.0f) || capf > 8388607.0f) {  // below 2^23: ring offsets stay exactly representable cursors (ring.rs:6)
         ctx->frames_unref(chain->frames);
         return odb_fail(ODB_E_INVALID, "delay ring of %g samples is out of range", (double)capf);
     }

@@ -105,3 +105,25 @@ def test_buffered_ring_wrap_and_finish(oracle, odb, ctx):
         for hr, hd in zip(pair.ref_handles, pair.dev_handles):
             assert hr.is_finished() == hd.is_finished()
     assert lens[0] == 2 and lens[-1] == 0
+
+
+def test_multi_second_ring_reads_far_offsets_literally(oracle, odb, ctx):
+    """A delay ring of > 2^17 samples (max_distance 1500 m at 48 kHz: 4.5 s): at such absolute offsets the f32 cursor
+    chain drifts by more than the staged kernel's window margin, so those reads take the literal ring kernel - and
+    stay bit-exact against Ring::sample (ring.rs:51-79)."""
+    rng = np.random.default_rng(61)
+    rate = 48000
+    pcm = synth_pcm(rng, 400000, rate)
+    pair = ScenePair(oracle, odb, ctx)
+    pair.dev.set_kernel_variant(0)
+    pair.play_buffered(rate, pcm, 0.0, [900.0, 50.0, -120.0], [-40.0, 3.0, 4.0], 0.5, max_distance=1500.0, ring_rate=rate,
+                       buffer_duration=0.1)
+    kinds = set()
+    for n in (1024, 2048, 4096) * 30:   # ~4.5 s: the write cursor passes 2^17 and the ring's end
+        ref, _, out = pair.step(rate, n)
+        np.testing.assert_array_equal(out, ref)
+        cursors_equal(pair)
+        cnt = pair.dev.last_job_counters()
+        kinds.add("staged" if cnt["staged"] else "literal")
+    assert np.abs(out).max() > 0
+    assert kinds == {"staged", "literal"}
