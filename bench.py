@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — source-frames/s of the spatial-mix hot path (BASELINE.json metric) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C3b|C4|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2], "C3"): one SpatialScene with 65 536 moving point sources
@@ -11,17 +11,21 @@ callback over all sources. Every source owns its own PCM (no sharing; 19 GB in H
 callback reads fresh PCM, so the inputs of a step are larger than L2 by construction.
 
 One JSON line on stdout (rank 0). `value` = N_sources * frames / device time per callback with
-everything resident in HBM; `e2e` = the same through the host-buffer C-ABI call
-(`odb_scene_run`: host output tile, D2H inside the timed region, plus `set_motion` updates for 1/16 of
-the sources every callback, H2D inside the timed region); `roofline` = algorithmic PCM bytes of the
-staged mix kernel / its device time against the measured HBM peak; `cpu_baseline` = the CPU oracle
-(the only runnable statement of the Rust reference here) on a bounded sample of the same workload.
+everything resident in HBM (CUDA events on the launch stream, max over ranks); `e2e` = the same through the
+host-buffer C-ABI call, one callback at a time (`odb_scene_run`: host output tile, D2H inside the timed region, plus
+`set_motion` updates for 1/16 of the sources every callback from a second thread, H2D inside the timed region) -
+at N = 1 driven by the compiled C harness tools/e2e_native.c (the Python-driven figure is `e2e.python_driven_value`);
+`roofline` = algorithmic PCM bytes of the callback kernel / its device time against the measured HBM peak;
+`cpu_baseline` = the CPU oracle (the only runnable statement of the Rust reference here) on a bounded sample.
 
-N > 1: one process per GPU; every rank mixes its own shard of the scene's sources and each callback ends
-with a sum all-reduce of the 8 KiB stereo tile. The sum is linear, so `--reduce-every R` (default 8, the offline
-rendering shape of examples/offline.rs) exchanges R tiles in one NCCL all-reduce issued on a second stream that
-overlaps the next callbacks' mixes; the timed region ends after the last all-reduce. R = 1 is live playback. Default `--scaling weak`: 65 536 sources per GPU (the scene grows with
-the box); `--scaling strong`: the 65 536 sources are split over the ranks.
+N > 1: one process per GPU. Default `--scaling strong`: the fixed scene of --sources sources is split over the ranks
+(round-robin) and EVERY callback ends with the sum of the ranks' tiles, done from inside the callback kernel over
+NVLink peer memory (`odb_scene_sample_exchange`, `--lag 1`: callback k receives the sum of callback k - 1, the
+pipelined-renderer shape; the `e2e` pass uses lag 0 and writes the summed tile into pinned host memory). The line
+then also carries `parity` (a 4096-source sharded scene after the timing: exchanged tile == rank-order sum of the
+gathered per-rank tiles bit for bit, identical on all ranks, within tolerance of the CPU oracle) and `extra`
+(`weak`: --sources per GPU; `strong_reduce_every_8`: the offline shape with the stand-alone exchange kernels).
+`--exchange peer|nccl|none` select the stand-alone kernels, torch.distributed, or no exchange (diagnostic).
 """
 from __future__ import annotations
 
