@@ -280,19 +280,29 @@ int SourceSet::apply(odb_ctx* ctx, cudaStream_t st, uint32_t* launches) {
     if (nm) {
         ODB_TRY(d_motions.ensure(nm, st, false));
         const int b = mot_buf;
-        if (mot_n) {  // the pinned buffer the control side filled goes to the device as it lies
+        if (mot_n && motions.empty()) {
+            // The common case: the scatter kernel reads the pinned buffer the control side filled directly over PCIe
+            // (unified addressing) - no copy-engine operation in front of the callback's kernels. The event behind
+            // the kernel tells the control side when the buffer may be refilled.
             if (!ev_mot[b]) ODB_CUDA(cudaEventCreateWithFlags(&ev_mot[b], cudaEventDisableTiming));
-            ODB_CUDA(cudaMemcpyAsync(d_motions.p, h_mot[b].p, mot_n * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+            odb_launch_scatter_motion(d_src.p, h_mot[b].p, (int)mot_n, st);
             ODB_CUDA(cudaEventRecord(ev_mot[b], st));
             ev_mot_pending[b] = true;
+        } else {
+            if (mot_n) {  // the pinned buffer the control side filled goes to the device as it lies
+                if (!ev_mot[b]) ODB_CUDA(cudaEventCreateWithFlags(&ev_mot[b], cudaEventDisableTiming));
+                ODB_CUDA(cudaMemcpyAsync(d_motions.p, h_mot[b].p, mot_n * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+                ODB_CUDA(cudaEventRecord(ev_mot[b], st));
+                ev_mot_pending[b] = true;
+            }
+            if (!motions.empty()) {  // what did not fit (rare: sources played since the buffers were sized)
+                ODB_TRY(h_motions.ensure(motions.size()));
+                memcpy(h_motions.p, motions.data(), motions.size() * sizeof(OdbMotionMsg));
+                ODB_CUDA(cudaMemcpyAsync(d_motions.p + mot_n, h_motions.p, motions.size() * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
+                motions.clear();
+            }
+            odb_launch_scatter_motion(d_src.p, d_motions.p, (int)nm, st);
         }
-        if (!motions.empty()) {  // what did not fit (rare: sources played since the buffers were sized)
-            ODB_TRY(h_motions.ensure(motions.size()));
-            memcpy(h_motions.p, motions.data(), motions.size() * sizeof(OdbMotionMsg));
-            ODB_CUDA(cudaMemcpyAsync(d_motions.p + mot_n, h_motions.p, motions.size() * sizeof(OdbMotionMsg), cudaMemcpyHostToDevice, st));
-            motions.clear();
-        }
-        odb_launch_scatter_motion(d_src.p, d_motions.p, (int)nm, st);
         (*launches)++;
         mot_n = 0;
         mot_gen++;  // forgets every slot's queued-message index at once

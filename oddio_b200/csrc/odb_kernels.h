@@ -68,6 +68,7 @@ cudaError_t odb_launch_mix_general(const OdbJob* jobs, int n_sources, int n_tile
 struct OdbSceneMixArgs {
     const OdbJob* jobs;               // [n_tiles][n_sources], written by the walk kernel
     int n_sources, n_tiles, n_frames;
+    int batch;                        // sources per batch (odb_scene_mix_shape)
     int epilogue;                     // 0 none, 1 Tanh, 2 Reinhard, | ODB_EPILOGUE_I16_BIT
     float* partials;                  // [n_tiles][grid][2 * ODB_TILE_FRAMES]
     float* out;                       // interleaved stereo, device or pinned host memory (f32, or int16 with the I16 bit)
@@ -93,7 +94,7 @@ struct OdbSceneMixArgs {
     uint32_t push_seq, pull_seq;
     float* xtile;                     // [n_tiles][2 * ODB_TILE_FRAMES] raw sum of this rank, for the grid's last CTA (exchange / host tile)
 };
-int odb_scene_mix_ctas(int n_sources, int sm_count);
+void odb_scene_mix_shape(int n_sources, int sm_count, int* batch, int* ctas);
 cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mode, cudaStream_t st);
 int odb_mix_fast_ctas(int n_sources, int sm_count);
 cudaError_t odb_launch_mix_fast(const OdbJob* jobs, int n_sources, int n_tiles, float* partials, int n_ctas, int mode,

@@ -467,13 +467,15 @@ static int scene_sample_impl(odb_scene* scene, float interval, float* dev_out, u
     const bool use_fast = scene->variant != 1;
     // ---- the one-launch callback: staged mix + literal tail + grid reduce + epilogue (seek set only) ----------------
     if (fused) {
-        const int n_ctas = odb_scene_mix_ctas(ns, ctx->sm_count);
+        int n_ctas = 1, batch = 8;
+        odb_scene_mix_shape(ns, ctx->sm_count, &batch, &n_ctas);
         ODB_TRY(ensure_idle(scene, scene->d_partials_fused[scene->fused_seq & 1], (size_t)nt * n_ctas * 2 * ODB_TILE_FRAMES));
         const int fp = (int)(scene->fused_seq & 1);  // parity of this launch among the one-launch kernels
         OdbSceneMixArgs a;
         memset(&a, 0, sizeof a);
         a.jobs = fused_jobs;
         a.n_sources = ns; a.n_tiles = nt; a.n_frames = (int)n_frames;
+        a.batch = batch;
         a.epilogue = scene->epilogue | (as_i16 ? ODB_EPILOGUE_I16_BIT : 0);
         a.partials = scene->d_partials_fused[fp].p;
         a.out = dev_out;

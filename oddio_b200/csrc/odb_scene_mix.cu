@@ -319,7 +319,9 @@ __device__ __forceinline__ void store_output(const OdbSceneMixArgs& A, const int
     }
 }
 
-template <class CFG, bool STRICT>
+// VARBATCH: the batch size is a run-time argument (small scenes, sharded scenes); otherwise it is the compile-time
+// CFG::BATCH - measurably faster on the full-size scene (90.2 vs 93.5 us on C3), where the chooser picks 8 anyway.
+template <class CFG, bool STRICT, bool VARBATCH>
 __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbSceneMixArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WARPS = CFG::WARPS, SPLIT = CFG::SPLIT, HCHUNKS = CFG::HCHUNKS, BATCH = CFG::BATCH, NACC = CFG::NACC;
@@ -363,7 +365,11 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
     const u64 nz = A.nz;
     const int G = (int)gridDim.x;
     const int gp = blockIdx.x * (WARPS / SPLIT) + team, GP = G * (WARPS / SPLIT);
-    const int n_batches = (n_sources + BATCH - 1) / BATCH;
+    // Sources per batch: at most BATCH (the 32 chain lanes), fewer when that evens out the rounds - a warp's work is
+    // whole batches, so e.g. 8192 sources are 1024 batches of 8 for 1184 teams (160 teams idle, the others 8 sources
+    // each) but 1171 batches of 7 (every team busy, 7 sources each). Chosen by the host (odb_scene_mix_batch).
+    const int bsz = VARBATCH ? A.batch : BATCH;
+    const int n_batches = (n_sources + bsz - 1) / bsz;
     const int first_frame = part * CFG::PART_FRAMES;
     const int c0 = part * HCHUNKS;
 
@@ -388,12 +394,12 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
         const OdbJob* tile_jobs = A.jobs + (size_t)tl * n_sources;
 
         for (int bi = gp; bi < n_batches; bi += GP) {
-            const int s0 = bi * BATCH;
+            const int s0 = bi * bsz;
             // 1. stage the batch's job records (one 128-byte line each: lane l moves word l)
 #pragma unroll
             for (int q = 0; q < BATCH; q++) {
                 uint32_t w = lane == ODB_JW_FLAGS ? ODB_JF_SKIP : 0u;
-                if (s0 + q < n_sources) w = __ldcg(reinterpret_cast<const uint32_t*>(tile_jobs + s0 + q) + lane);
+                if (q < bsz && s0 + q < n_sources) w = __ldcg(reinterpret_cast<const uint32_t*>(tile_jobs + s0 + q) + lane);
                 sts_u32(rec(q, lane), w);
             }
             __syncwarp();
@@ -521,9 +527,9 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             float2* tile = reinterpret_cast<float2*>(smem_raw + warp * CFG::WARP_BYTES);
             float* scratch = reinterpret_cast<float*>(smem_raw + warp * CFG::WARP_BYTES + CFG::PART_FRAMES * 8);
             for (int bi = gp; bi < n_batches; bi += GP) {
-                const int s0 = bi * BATCH;
+                const int s0 = bi * bsz;
                 uint32_t f = ODB_JF_SKIP;
-                if (lane < BATCH && s0 + lane < n_sources) f = __ldcg(&tile_jobs[s0 + lane].flags);
+                if (lane < bsz && s0 + lane < n_sources) f = __ldcg(&tile_jobs[s0 + lane].flags);
                 uint32_t m = __ballot_sync(0xffffffffu, (f & ODB_JF_GENERAL) && !(f & (ODB_JF_SKIP | ODB_JF_RING)));
                 while (m) {
                     const int q = __ffs(m) - 1;
@@ -667,48 +673,60 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
 
 using namespace odbk;
 
-// Shapes built into the library; `odb_scene_mix_select` picks one (experiments: ODB_SMX_CFG in the environment).
+// Shapes built into the library (experiments: ODB_SMX_CFG = 1 or 3 in the environment selects the alternatives measured
+// in DESIGN.md section 7; the 8-frames-in-flight variants measured there are not kept in the build).
 typedef SmxCfg<2, 16, 0, 4> SmxDefault;
 typedef SmxCfg<2, 16, 1, 4> SmxPairs;
-typedef SmxCfg<2, 16, 0, 8> SmxIlp8;
 typedef SmxCfg<1, 12, 0, 4> SmxWhole;
-typedef SmxCfg<1, 12, 0, 8> SmxWholeIlp8;
 
 static int g_smx_cfg = -1;
 static int smx_cfg() {
     if (g_smx_cfg < 0) {
         const char* e = getenv("ODB_SMX_CFG");
         g_smx_cfg = e ? atoi(e) : 0;
-        if (g_smx_cfg < 0 || g_smx_cfg > 4) g_smx_cfg = 0;
+        if (g_smx_cfg != 1 && g_smx_cfg != 3) g_smx_cfg = 0;
     }
     return g_smx_cfg;
 }
 
+// Sources per batch and CTAs for `n_sources`: the batch size (1..BATCH) that minimises a team's work, rounds x (batch
+// + the per-batch overhead of prologue and cursor chains, about 0.6 of a source's consume), over the whole chip.
 template <class CFG>
-static int smx_ctas(int n_sources, int sm_count) {
-    const int per_cta = (CFG::WARPS / CFG::SPLIT) * CFG::BATCH;
-    int want = (n_sources + per_cta - 1) / per_cta;
-    return want < 1 ? 1 : (want > sm_count ? sm_count : want);
+static void smx_shape(int n_sources, int sm_count, int* batch, int* ctas) {
+    const int teams_per_cta = CFG::WARPS / CFG::SPLIT;
+    const long long teams = (long long)teams_per_cta * sm_count;
+    int best = CFG::BATCH;
+    double best_cost = 1e300;
+    for (int b = CFG::BATCH; b >= 1; b--) {
+        const long long batches = ((long long)n_sources + b - 1) / b;
+        const long long rounds = (batches + teams - 1) / teams;
+        const double cost = (double)rounds * ((double)b + 0.6);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
+    }
+    const long long batches = ((long long)n_sources + best - 1) / best;
+    long long want = (batches + teams_per_cta - 1) / teams_per_cta;
+    *batch = best;
+    *ctas = (int)(want < 1 ? 1 : (want > sm_count ? sm_count : want));
 }
-int odb_scene_mix_ctas(int n_sources, int sm_count) {
+void odb_scene_mix_shape(int n_sources, int sm_count, int* batch, int* ctas) {
     switch (smx_cfg()) {
-        case 1: return smx_ctas<SmxPairs>(n_sources, sm_count);
-        case 2: return smx_ctas<SmxIlp8>(n_sources, sm_count);
-        case 3: return smx_ctas<SmxWhole>(n_sources, sm_count);
-        case 4: return smx_ctas<SmxWholeIlp8>(n_sources, sm_count);
-        default: return smx_ctas<SmxDefault>(n_sources, sm_count);
+        case 1: return smx_shape<SmxPairs>(n_sources, sm_count, batch, ctas);
+        case 3: return smx_shape<SmxWhole>(n_sources, sm_count, batch, ctas);
+        default: return smx_shape<SmxDefault>(n_sources, sm_count, batch, ctas);
     }
 }
 
-template <class CFG, bool STRICT>
+template <class CFG, bool STRICT, bool VARBATCH>
 static cudaError_t launch_scene_mix(const OdbSceneMixArgs& a, int n_ctas, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_scene_mix<CFG, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_scene_mix<CFG, STRICT, VARBATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return odb_launch_pdl(k_scene_mix<CFG, STRICT>, dim3(n_ctas), dim3(CFG::WARPS * 32), (size_t)CFG::SMEM_BYTES, st, a);
+    return odb_launch_pdl(k_scene_mix<CFG, STRICT, VARBATCH>, dim3(n_ctas), dim3(CFG::WARPS * 32), (size_t)CFG::SMEM_BYTES, st, a);
 }
 template <class CFG>
 static cudaError_t launch_scene_mix_mode(const OdbSceneMixArgs& a, int n_ctas, int mode, cudaStream_t st) {
-    return (mode & 1) ? launch_scene_mix<CFG, false>(a, n_ctas, st) : launch_scene_mix<CFG, true>(a, n_ctas, st);
+    if (a.batch == CFG::BATCH)
+        return (mode & 1) ? launch_scene_mix<CFG, false, false>(a, n_ctas, st) : launch_scene_mix<CFG, true, false>(a, n_ctas, st);
+    return (mode & 1) ? launch_scene_mix<CFG, false, true>(a, n_ctas, st) : launch_scene_mix<CFG, true, true>(a, n_ctas, st);
 }
 
 // mode bit 0: value multiply-adds contracted to FMA
@@ -717,9 +735,7 @@ cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mo
     a.nz = 0x8000000080000000ull;
     switch (smx_cfg()) {
         case 1: return launch_scene_mix_mode<SmxPairs>(a, n_ctas, mode, st);
-        case 2: return launch_scene_mix_mode<SmxIlp8>(a, n_ctas, mode, st);
         case 3: return launch_scene_mix_mode<SmxWhole>(a, n_ctas, mode, st);
-        case 4: return launch_scene_mix_mode<SmxWholeIlp8>(a, n_ctas, mode, st);
         default: return launch_scene_mix_mode<SmxDefault>(a, n_ctas, mode, st);
     }
 }

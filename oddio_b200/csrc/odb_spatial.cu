@@ -26,7 +26,11 @@ __global__ void k_scatter_sources(OdbSource* __restrict__ src, const OdbSource* 
 __global__ void k_scatter_motion(OdbSource* __restrict__ src, const OdbMotionMsg* __restrict__ msgs, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    OdbMotionMsg m = msgs[i];
+    // two 16-byte loads per message: the buffer may be pinned host memory read over PCIe (odb_host.cu apply())
+    static_assert(sizeof(OdbMotionMsg) == 32, "a message is two 16-byte words");
+    OdbMotionMsg m;
+    reinterpret_cast<uint4*>(&m)[0] = __ldcs(reinterpret_cast<const uint4*>(msgs + i));
+    reinterpret_cast<uint4*>(&m)[1] = __ldcs(reinterpret_cast<const uint4*>(msgs + i) + 1);
     if (m.slot == 0xFFFFFFFFu) return;  // withdrawn: its source was removed after the message was queued
     OdbSource* s = src + m.slot;
     s->ppos[0] = m.pos[0]; s->ppos[1] = m.pos[1]; s->ppos[2] = m.pos[2];

@@ -17,7 +17,7 @@ OUT = os.path.join(ROOT, "profiles", "sass_k_scene_mix.txt")
 def main():
     sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", sass)
-    pick = [f for f in funcs if f.startswith("_ZN4odbk11k_scene_mixINS_6SmxCfgILi2ELi16ELi0ELi4EEELb0EEE")]
+    pick = [f for f in funcs if f.startswith("_ZN4odbk11k_scene_mixINS_6SmxCfgILi2ELi16ELi0ELi4EEELb0ELb0EEE")]
     assert pick, "the default FMA instantiation of k_scene_mix is not in the library"
     body = pick[0]
     ins = re.findall(r"/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body)
@@ -28,7 +28,7 @@ def main():
     start = max(0, idx[0] - 14) if idx else 0
     excerpt = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip() for l in lines[start:start + 96] if "/*" in l and not re.match(r"\s*/\* 0x", l)]
     with open(OUT, "w") as f:
-        f.write("k_scene_mix<SmxCfg<2,16,0,4>, STRICT=false> in oddio_b200/liboddio_b200.so (cuobjdump -sass), sm_100a\n")
+        f.write("k_scene_mix<SmxCfg<2,16,0,4>, STRICT=false, VARBATCH=false> in oddio_b200/liboddio_b200.so (cuobjdump -sass), sm_100a\n")
         f.write(f"{len(ins)} instructions. Mnemonic counts (top 28):\n")
         for k, v in counts.most_common(28):
             f.write(f"  {k:10s} {v}\n")
