@@ -689,19 +689,24 @@ static int smx_cfg() {
     return g_smx_cfg;
 }
 
-// Sources per batch and CTAs for `n_sources`: the batch size (1..BATCH) that minimises a team's work, rounds x (batch
-// + the per-batch overhead of prologue and cursor chains, about 0.6 of a source's consume), over the whole chip.
+// Sources per batch and CTAs for `n_sources`. Scenes that give every team at least half a full batch keep the
+// compile-time batch of 8 (the faster instantiation; and at 8 GPUs the 128-CTA grid of an 8192-source shard leaves 20
+// SMs on which the next callback's walk runs underneath the mix - batches of 7 would fill 147 SMs and expose the walk:
+// measured 29.7 us per callback instead of 23.6). Smaller scenes take the batch size (1..BATCH) that minimises a
+// team's work, rounds x (batch + the per-batch overhead of prologue and cursor chains, about 0.6 of a source's consume).
 template <class CFG>
 static void smx_shape(int n_sources, int sm_count, int* batch, int* ctas) {
     const int teams_per_cta = CFG::WARPS / CFG::SPLIT;
     const long long teams = (long long)teams_per_cta * sm_count;
     int best = CFG::BATCH;
-    double best_cost = 1e300;
-    for (int b = CFG::BATCH; b >= 1; b--) {
-        const long long batches = ((long long)n_sources + b - 1) / b;
-        const long long rounds = (batches + teams - 1) / teams;
-        const double cost = (double)rounds * ((double)b + 0.6);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
+    if ((long long)n_sources < teams * (CFG::BATCH / 2)) {
+        double best_cost = 1e300;
+        for (int b = CFG::BATCH; b >= 1; b--) {
+            const long long batches = ((long long)n_sources + b - 1) / b;
+            const long long rounds = (batches + teams - 1) / teams;
+            const double cost = (double)rounds * ((double)b + 0.6);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
+        }
     }
     const long long batches = ((long long)n_sources + best - 1) / best;
     long long want = (batches + teams_per_cta - 1) / teams_per_cta;
