@@ -47,6 +47,7 @@ extern "C" int odb_ctx_destroy(odb_ctx* ctx) {
     if (!ctx) return ODB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (char* p : ctx->dead_blocks) cudaFree(p);
     for (auto& b : ctx->blocks)
         if (b.base) cudaFree(b.base);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -87,16 +88,45 @@ int odb_ctx::arena_alloc(size_t bytes, float** out, int* block) {
     *block = bi;
     return ODB_OK;
 }
-void odb_ctx::arena_unref(int block) {
+void odb_ctx::arena_unref(int block, bool defer) {
     if (block < 0 || block >= (int)blocks.size()) return;
     ArenaBlock& b = blocks[block];
     if (--b.live == 0 && block != (int)blocks.size() - 1) {
-        cudaStreamSynchronize(stream);
-        cudaFree(b.base);
+        if (defer) {
+            dead_blocks.push_back(b.base);
+        } else {
+            cudaStreamSynchronize(stream);
+            cudaFree(b.base);
+        }
         b.base = nullptr;
     } else if (b.live == 0) {
         b.used = 0;  // the open block can be reused from the start
     }
+}
+void odb_ctx::arena_collect() {  // takes `mu` only to detach the list: the synchronisation and the frees run without it
+    std::vector<char*> dead;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        dead.swap(dead_blocks);
+    }
+    if (dead.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (char* p : dead) cudaFree(p);
+}
+int odb_ctx::ring_alloc(size_t bytes, float** out, int* block) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    auto it = free_rings.find(bytes);
+    if (it != free_rings.end() && !it->second.empty()) {
+        *out = it->second.back().p;
+        *block = it->second.back().block;
+        it->second.pop_back();
+        return ODB_OK;
+    }
+    return arena_alloc(bytes, out, block);
+}
+void odb_ctx::ring_release(float* p, size_t bytes, int block) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    free_rings[bytes].push_back(FreeRing{p, block});  // keeps its arena reference: the block stays alive for the next tenant
 }
 int odb_ctx::frames_ref(odb_frames id, FramesRec* out) {
     std::lock_guard<std::mutex> lk(mu);
@@ -111,7 +141,7 @@ void odb_ctx::frames_unref(odb_frames id) {
     auto it = frames.find(id);
     if (it == frames.end()) return;
     if (--it->second.refs == 0) {
-        arena_unref(it->second.block);
+        arena_unref(it->second.block, /*defer=*/true);  // may run on the audio thread (a finished source's last reference)
         frames.erase(it);
     }
 }
@@ -127,6 +157,7 @@ static int frames_new(odb_ctx* ctx, uint32_t rate, int channels, const void* sam
     size_t elems = (size_t)n_frames * channels;
     float* base = nullptr;
     {
+        ctx->arena_collect();  // blocks the audio thread found dead are freed here, on the control side
         std::lock_guard<std::mutex> lk(ctx->mu);
         ODB_TRY(ctx->arena_alloc((elems + 2 * ODB_PCM_PAD) * sizeof(float), &base, &rec.block));
     }
@@ -433,10 +464,11 @@ int SourceSet::fold_count(odb_ctx* ctx, cudaStream_t st, uint32_t count, std::mu
         sh.motion_idx = sh.speed_idx = sh.gain_idx = -1;
         if (sh.frames) ctx->frames_unref(sh.frames);
         sh.frames = 0;
-        if (sh.ring_block >= 0) {
+        if (sh.ring_block >= 0) {  // the delay ring goes to the context's free list for the next play_buffered of that size
             std::lock_guard<std::mutex> lk(ctx->mu);
-            ctx->arena_unref(sh.ring_block);
+            ctx->ring_release(sh.ring_ptr, sh.ring_bytes, sh.ring_block);
             sh.ring_block = -1;
+            sh.ring_ptr = nullptr;
         }
         free_slots.push_back(slot);
     }
@@ -449,7 +481,7 @@ void SourceSet::release_all(odb_ctx* ctx) {
         if (sh.in_use && sh.frames) ctx->frames_unref(sh.frames);
         if (sh.in_use && sh.ring_block >= 0) {
             std::lock_guard<std::mutex> lk(ctx->mu);
-            ctx->arena_unref(sh.ring_block);
+            ctx->ring_release(sh.ring_ptr, sh.ring_bytes, sh.ring_block);
         }
     }
     slots.clear();

@@ -127,8 +127,18 @@ struct odb_ctx {
     std::unordered_map<uint64_t, FramesRec> frames;
     uint64_t next_frames_id = 1;
     std::vector<ArenaBlock> blocks;
+    std::vector<char*> dead_blocks;  // blocks whose last allocation died on the audio thread: freed by the next control call
+    // Delay rings of finished buffered sources, by byte size: a steady stream of play_buffered sounds reuses them
+    // instead of bump-allocating new arena space (a ring lives in a block shared with long-lived PCM, which the
+    // block-level reference count would keep pinned).
+    struct FreeRing { float* p; int block; };
+    std::unordered_map<size_t, std::vector<FreeRing>> free_rings;
     int arena_alloc(size_t bytes, float** out, int* block);
-    void arena_unref(int block);
+    // `defer`: called from the audio thread - never cudaFree there; the block goes to dead_blocks
+    void arena_unref(int block, bool defer = false);
+    void arena_collect();            // control side: free what the audio thread left in dead_blocks
+    int ring_alloc(size_t bytes, float** out, int* block);
+    void ring_release(float* p, size_t bytes, int block);
     int frames_ref(odb_frames id, FramesRec* out);
     void frames_unref(odb_frames id);
 };
@@ -147,6 +157,8 @@ struct SlotHost {
     bool stop_requested = false;  // Mixed::stop() was called (mixer.rs:34-36); visible to is_stopped at once
     uint32_t chain_flags = 0;
     int ring_block = -1;    // arena block of a buffered source's delay ring, -1 if none
+    float* ring_ptr = nullptr;  // ... the ring itself and its size, so that it can be reused when the source is gone
+    size_t ring_bytes = 0;
     uint64_t n_frames = 0;  // FramesSignalControl::samples
     double rate = 0.0;
     // latest-wins de-duplication of queued control messages (swap.rs semantics): index into the

@@ -230,9 +230,10 @@ extern "C" int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain,
     int block = -1;
     ODB_CUDA(cudaSetDevice(ctx->device));
     int rc;
+    ctx->arena_collect();
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        rc = ctx->arena_alloc((size_t)cap * sizeof(float), &ring, &block);
+        rc = ctx->ring_alloc((size_t)cap * sizeof(float), &ring, &block);
     }
     if (rc != ODB_OK) {
         ctx->frames_unref(chain->frames);
@@ -256,6 +257,8 @@ extern "C" int odb_scene_play_buffered(odb_scene* scene, const odb_chain* chain,
     SlotHost& sh = scene->buffered.slots[slot];
     sh.frames = chain->frames; sh.chain_flags = chain->flags; sh.n_frames = rec.n_frames; sh.rate = (double)rec.rate;
     sh.ring_block = block;
+    sh.ring_ptr = ring;
+    sh.ring_bytes = (size_t)cap * sizeof(float);
     scene->buffered.ins_src.push_back(s);
     scene->buffered.ins_slot.push_back(slot);
     *out = scene->buffered.handle_of(slot, ODB_TAG_BUFFERED);
