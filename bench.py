@@ -1011,7 +1011,7 @@ def run_reference(args):
     t0 = time.time()
     M = args.frames
     N = args.sources  # the fixed scene; its CPU time does not depend on how many GPUs the other arm uses
-    steps, warm = max(1, min(args.steps, args.ref_steps)), 1
+    steps, warm = max(1, min(args.steps, args.ref_steps)), max(1, min(args.warmup, 3))
     base = cpu_baseline(args, threads=1, n=N, reps=steps, warm=warm)
     threads = os.cpu_count() or 1
     many = cpu_baseline(args, threads=threads, n=N, reps=steps, warm=warm) if threads > 1 else None
@@ -1049,7 +1049,7 @@ def main():
     ap.add_argument("--sources", type=int, default=65536)
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--cpu-sources", type=int, default=2048, help="sources in the bounded CPU sample")
-    ap.add_argument("--ref-steps", type=int, default=5, help="--impl reference: timed whole-scene callbacks (about 0.9 s each on one thread)")
+    ap.add_argument("--ref-steps", type=int, default=32, help="--impl reference: cap on the timed whole-scene callbacks (about 0.85 s each on one thread)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong (default) = the fixed scene of --sources sources split over the ranks, weak = --sources per GPU")

@@ -58,6 +58,14 @@ int odb_ctx_synchronize(odb_ctx* ctx);
 /* The context's CUDA stream (a cudaStream_t) so callers can order their own work after it. */
 int odb_ctx_stream(odb_ctx* ctx, void** out_stream);
 
+/* Page-locks (cudaHostRegister) / releases a host buffer of the caller, so that a host without the CUDA runtime can make
+ * its output tile directly writable by the device: `odb_scene_sample` renders straight into an `out` that is pinned
+ * or registered (no staging tile, no memcpy on the way back); any other `out` goes through the scene's own pinned tile.
+ * Optional; the buffer must stay valid until it is unpinned. No reference counterpart (the reference mixes into
+ * ordinary memory, lib.rs:90). */
+int odb_pin_buffer(odb_ctx* ctx, void* host_ptr, uint64_t bytes);
+int odb_unpin_buffer(odb_ctx* ctx, void* host_ptr);
+
 /* ---- Frames (frames.rs:19-77) ------------------------------------------------------------------ */
 /* Frames::from_slice (frames.rs:26-47): copies `n_frames` interleaved frames of `channels`
  * (1 = Sample, 2 = [Sample; 2]) from HOST memory into HBM. */

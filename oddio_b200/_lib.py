@@ -60,6 +60,8 @@ SIGNATURES = {
     "odb_ctx_destroy": [vp],
     "odb_ctx_synchronize": [vp],
     "odb_ctx_stream": [vp, pvp],
+    "odb_pin_buffer": [vp, vp, u64],
+    "odb_unpin_buffer": [vp, vp],
     "odb_frames_from_slice": [vp, u32, i32, fp, u64, pu64],
     "odb_frames_from_device": [vp, u32, i32, vp, u64, pu64],
     "odb_frames_release": [vp, u64],

@@ -60,6 +60,18 @@ extern "C" int odb_ctx_synchronize(odb_ctx* ctx) {
     ODB_CUDA(cudaStreamSynchronize(ctx->stream));
     return ODB_OK;
 }
+extern "C" int odb_pin_buffer(odb_ctx* ctx, void* host_ptr, uint64_t bytes) {
+    if (!ctx || !host_ptr || !bytes) return odb_fail(ODB_E_INVALID, "NULL argument");
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    ODB_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return ODB_OK;
+}
+extern "C" int odb_unpin_buffer(odb_ctx* ctx, void* host_ptr) {
+    if (!ctx || !host_ptr) return odb_fail(ODB_E_INVALID, "NULL argument");
+    ODB_CUDA(cudaSetDevice(ctx->device));
+    ODB_CUDA(cudaHostUnregister(host_ptr));
+    return ODB_OK;
+}
 extern "C" int odb_ctx_stream(odb_ctx* ctx, void** out_stream) {
     if (!ctx || !out_stream) return odb_fail(ODB_E_INVALID, "NULL argument");
     *out_stream = (void*)ctx->stream;

@@ -342,18 +342,16 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
     // The job records come from the walk kernel launched just before: this grid starts when every walk block has
     // counted itself into `walked` (its trigger comes after that), and acquires the count - no griddepcontrol.wait,
     // which would also wait for everything the walk was launched behind (the previous callback's exchange tail).
-    if (threadIdx.x == 0)
-        while (ld_acquire_u64(A.walked) < A.walked_target) __nanosleep(20);
-    __syncthreads();
     // Neither this kernel nor the walk waits for the PREVIOUS callback's kernel to finish (its last CTA may still be
     // exchanging tiles with the other GPUs while this grid mixes). What consecutive callbacks share is double-buffered
     // by callback parity - partial tiles, xtile, the arrive / done counters - and the job records live in a ring of
-    // three, so the one thing to wait for is the callback before the previous one (almost never an actual wait).
-    if (A.my_seq > 2ull) {
-        if (threadIdx.x == 0)
-            while (ld_acquire_u64(A.completed) < A.my_seq - 2ull) __nanosleep(40);
-        __syncthreads();
-    }
+    // three, so the other thing to wait for is the callback before the previous one (almost never an actual wait).
+    // Two threads poll the two words side by side (one L2 round trip instead of two).
+    if (threadIdx.x == 0)
+        while (ld_acquire_u64(A.walked) < A.walked_target) __nanosleep(20);
+    if (threadIdx.x == 32 && A.my_seq > 2ull)
+        while (ld_acquire_u64(A.completed) < A.my_seq - 2ull) __nanosleep(40);
+    __syncthreads();
     // Only now may the next callback's walk start: it finds this callback's walk complete (the wait above) and callback
     // my_seq - 2 finished entirely, whose job records it overwrites.
     pdl_launch_dependents();

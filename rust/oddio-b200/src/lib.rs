@@ -76,6 +76,8 @@ pub mod sys {
         pub fn odb_ctx_destroy(ctx: *mut odb_ctx) -> c_int;
         pub fn odb_ctx_synchronize(ctx: *mut odb_ctx) -> c_int;
         pub fn odb_ctx_stream(ctx: *mut odb_ctx, out_stream: *mut *mut c_void) -> c_int;
+        pub fn odb_pin_buffer(ctx: *mut odb_ctx, host_ptr: *mut c_void, bytes: u64) -> c_int;
+        pub fn odb_unpin_buffer(ctx: *mut odb_ctx, host_ptr: *mut c_void) -> c_int;
         pub fn odb_frames_from_slice(ctx: *mut odb_ctx, rate: u32, channels: c_int, samples: *const f32, n_frames: u64, out: *mut odb_frames) -> c_int;
         pub fn odb_frames_from_device(ctx: *mut odb_ctx, rate: u32, channels: c_int, dev_samples: *const c_void, n_frames: u64, out: *mut odb_frames) -> c_int;
         pub fn odb_frames_from_i16(ctx: *mut odb_ctx, rate: u32, channels: c_int, samples: *const i16, n_frames: u64, bits_per_sample: c_int, out: *mut odb_frames) -> c_int;
@@ -154,6 +156,22 @@ impl Context {
     /// Blocks until everything queued on the context's stream has finished.
     pub fn synchronize(&self) {
         check(unsafe { sys::odb_ctx_synchronize(self.raw) });
+    }
+    /// Page-locks an output buffer so that `sample` renders straight into it (no staging tile, no memcpy). The buffer
+    /// must outlive the returned guard.
+    pub fn pin<'a, T>(self: &Arc<Self>, buf: &'a mut [T]) -> Pinned<'a, T> {
+        check(unsafe { sys::odb_pin_buffer(self.raw, buf.as_mut_ptr().cast(), std::mem::size_of_val(buf) as u64) });
+        Pinned { ctx: self.clone(), buf }
+    }
+}
+/// A caller buffer registered with the device for the guard's lifetime.
+pub struct Pinned<'a, T> {
+    ctx: Arc<Context>,
+    pub buf: &'a mut [T],
+}
+impl<T> Drop for Pinned<'_, T> {
+    fn drop(&mut self) {
+        unsafe { sys::odb_unpin_buffer(self.ctx.raw, self.buf.as_mut_ptr().cast()) };
     }
 }
 impl Drop for Context {

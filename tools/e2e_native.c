@@ -117,6 +117,9 @@ int main(int argc, char** argv) {
     pthread_t th;
     pthread_create(&th, NULL, control_thread, &c);
     float* out = (float*)malloc(FRAMES * 2 * sizeof(float));
+    /* The output tile is the caller's own buffer; page-locking it through the ABI lets the callback kernel store the
+     * tile straight into it (E2E_NO_PIN=1: leave it pageable - the library then stages through its own pinned tile). */
+    const int pinned = getenv("E2E_NO_PIN") ? 0 : (odb_pin_buffer(ctx, out, FRAMES * 2 * sizeof(float)) == ODB_OK);
     double t0 = 0.0;
     for (uint32_t k = 0; k < total; k++) {
         if (k == WARMUP) t0 = now_us();
@@ -127,8 +130,9 @@ int main(int argc, char** argv) {
     pthread_join(th, NULL);
     double acc = 0.0;
     for (uint32_t i = 0; i < FRAMES * 2; i++) acc += fabs((double)out[i]);
-    printf("{\"sources\": %u, \"frames\": %u, \"callbacks\": %u, \"us_per_callback\": %.1f, \"source_frames_per_s\": %.4e, \"checksum\": %.6f}\n",
-           n_src, FRAMES, n_cb, us, (double)n_src * FRAMES / (us * 1e-6), acc);
+    printf("{\"sources\": %u, \"frames\": %u, \"callbacks\": %u, \"us_per_callback\": %.1f, \"source_frames_per_s\": %.4e, \"checksum\": %.6f, \"out_pinned\": %d}\n",
+           n_src, FRAMES, n_cb, us, (double)n_src * FRAMES / (us * 1e-6), acc, pinned);
+    if (pinned) CHECK(odb_unpin_buffer(ctx, out));
     CHECK(odb_scene_destroy(scene));
     CHECK(odb_ctx_destroy(ctx));
     return 0;
