@@ -628,7 +628,9 @@ static int scene_wait(odb_scene* scene) {
 static int scene_fold_after(odb_scene* scene) {
     odb_ctx* ctx = scene->ctx;
     cudaStream_t ws = scene->pipelined ? scene->wst : ctx->stream;
-    ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
+    // a set without members cannot have reported a removal: no read-back (a 4-byte copy + event wait is ~11 us)
+    if (!scene->buffered.order.empty()) ODB_TRY(scene->buffered.fold_removed(ctx, ws, true, &scene->mu));
+    if (scene->seek.order.empty()) return ODB_OK;
     if (scene->count_by_kernel) return scene->seek.fold_count(ctx, ws, scene->seek.h_removed_count.p[0], &scene->mu);
     return scene->seek.fold_removed(ctx, ws, true, &scene->mu);
 }
