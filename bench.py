@@ -685,7 +685,7 @@ def run_ours(args):
                                      "in rank order (odb_scene_sample_exchange)",
                "peer": f", tiles summed by the library's stand-alone peer-memory kernels over NVLink, one exchange per {args.reduce_every} callbacks, overlapped with the next mixes",
                "nccl": f", one NCCL all-reduce per {args.reduce_every} callbacks, overlapped with the next mixes",
-               "none": ", NO exchange of the tiles (diagnostic: the per-rank callback rate)"}[mode] + main["note"]
+               "none": "" if world == 1 else ", NO exchange of the tiles (diagnostic: the per-rank callback rate)"}[mode] + main["note"]
         legacy = bool(args.variant & 0x200)
         kname = ("k_mix_fast" if legacy else "k_scene_mix") + ("<strict>" if (args.variant & 0xFF) == 0 else "<fma>")
         out = {
