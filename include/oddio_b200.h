@@ -196,11 +196,12 @@ int odb_last_job_counters(void* owner, uint32_t out[4]);
  * dominant (staged mix) kernel of the last call. Off by default (events cost a few microseconds). */
 int odb_set_profiling(void* owner, int enabled);
 int odb_last_mix_kernel_ms(void* owner, float* out_ms);
-/* Selects the mix-kernel variant: 0 = default (staged kernel, strict arithmetic: a source's
- * contribution is bit-identical to the reference's; general kernel per source as fallback), 1 = force the
- * literal general kernel for every source (slow, used to cross-check), 2 = staged kernel with the three
- * value multiply-adds contracted to FMA (cursors and indices still bit-exact). Adding 0x100 runs a scene's
- * per-source set-up kernels on a second stream so that they overlap the previous callback's mix. */
+/* Selects the mix-kernel variant: 2 = default: the three value multiply-adds (lerp, gain ramp, accumulate) contracted
+ * to FMA, cursors and indices bit-exact; 0 = strict arithmetic: every value operation unfused in the reference's
+ * order, so a source's contribution is bit-identical to the reference's; 1 = force the literal path for every source
+ * (slow, used to cross-check). Adding 0x100 runs a scene's per-source set-up kernels on a second stream; adding 0x200
+ * selects the multi-kernel callback (walk, staged mix, literal mix, reduce as separate launches) instead of the
+ * one-launch callback kernel. */
 int odb_set_kernel_variant(void* owner, int variant);
 
 /* ---- multi-GPU: sum of the per-GPU tiles over NVLink peer memory ---------------------------------------

@@ -1,28 +1,33 @@
 // One-launch scene callback for the seek path: SpatialScene's mix closure (spatial.rs:445-469) over
 // FramesSignal::sample (frames.rs:176-201) for every source of the scene, the literal path for the jobs the
-// walk kernel flagged, the sum of the per-CTA partial tiles and the Tanh / Reinhard epilogue - what used to be
-// k_mix_fast + k_mix_general + k_reduce_tiles (three launches, two grid-wide dependencies) in one persistent grid.
+// walk kernel flagged, the sum of the per-CTA partial tiles, the Tanh / Reinhard epilogue and - for a source-sharded
+// scene - the exchange of the tile with the other GPUs: what used to be k_mix_fast + k_mix_general + k_reduce_tiles
+// (+ k_exchange_push / _pull), three to five launches and as many grid-wide dependencies, in one persistent grid.
 //
-// A persistent grid of one 16-warp CTA per SM; the two warps of a pair mix the two 512-frame halves of the same
+// A persistent grid of one 16-warp CTA per SM; the two warps of a team mix the two 512-frame halves of the same
 // sources. Per 1024-frame tile of the callback (the tile loop is inside the kernel, so a callback may have any length):
-//   1. batches of 8 sources per warp, as in k_mix_fast (odb_mix_fast.cu): job records staged in bank-swizzled shared
-//      memory, the PCM window of each source fetched by one elected lane with a bulk async copy (TMA, UBLKCP) into
-//      one of two buffers, the reference's serial cursor `offset += ds` (frames.rs:195) walked literally on 32 lanes
-//      (source x ear x chunk) with every 4th value parked in shared memory;
-//   2. consume: lane l owns the frame PAIRS (64 j + 2 l, 64 j + 2 l + 1) of a 256-frame chunk. One checkpoint load
-//      serves both frames: even lanes sit on a checkpoint, odd lanes two literal steps behind one, and the second
-//      frame of the pair is one more literal step - 3 packed additions and one load per two frames where the
-//      lane-strided layout of k_mix_fast needs 6 and 2. Index/fraction split, taps, lerp, gain ramp and the packed
-//      (L, R) accumulators are k_mix_fast's. The price is a 2-way bank conflict on the tap loads (lanes l and l + 16
-//      are 32 ds words apart); the shared-memory pipe has the room;
+//   1. batches of up to 8 sources per warp, as in k_mix_fast (odb_mix_fast.cu): job records staged in bank-swizzled
+//      shared memory, the PCM window of each source fetched by one elected lane with a bulk async copy (TMA, UBLKCP)
+//      into one of two buffers, the reference's serial cursor `offset += ds` (frames.rs:195) walked literally on 32
+//      lanes (source x ear x chunk) with every 4th value parked in shared memory;
+//   2. consume (shipped shape, SmxCfg<2, 16, 0, 4>): lane l owns frames l + 32 j of a 256-frame chunk; it reloads its
+//      checkpoint, applies <= 3 more literal additions, splits the cursor into index and fraction with a round-down
+//      magic add (no F2I / I2F), gathers the sample pair from shared memory, lerps (frame.rs:39-41), applies the
+//      per-frame gain ramp (spatial.rs:459) and accumulates into packed (L, R) register accumulators (FADD2 / FFMA2).
+//      Alternative shapes measured on C3 and kept selectable for experiments: frame pairs per
+//      lane (3 cursor steps per 2 frames, but 2-way bank conflicts on the taps), one warp per whole tile (12 warps);
 //   3. tail: jobs flagged ODB_JF_GENERAL (any ds, windows outside the block, FixedGain, Cycle) are mixed literally by
-//      the warp that owns their batch, straight into its parked accumulators (general_half, the code of
-//      k_mix_general for one half tile);
+//      the warp that owns their batch, straight into its parked accumulators (general_part, the code of
+//      k_mix_general for one part of the tile);
 //   4. fold warp -> CTA in fixed order, one partial tile per CTA to HBM, then a grid-wide arrive counter: when every
 //      CTA of the grid has arrived, CTA b sums 16-float slices b, b + grid, ... of all partial tiles in index order
-//      (deterministic; no float atomics), applies the epilogue and stores the output - f32 or 16-bit PCM, device
-//      memory or pinned host memory. All CTAs are resident (grid <= SM count, one CTA per SM), so the wait cannot
-//      deadlock. The last CTA to finish publishes the callback's sequence number to an optional host flag.
+//      (deterministic; no float atomics) and either applies the epilogue and stores the output, or leaves the raw sum
+//      for the grid's last CTA, which finishes the callback while all other CTAs have left their SMs: the tile into
+//      pinned host memory + the host's completion flag, or the push / pull of the multi-GPU exchange over NVLink
+//      peer memory (odb_exchange.h). All CTAs are resident (grid <= SM count, one CTA per SM), so the arrive wait
+//      cannot deadlock.
+// Ordering against the kernels around it is device-side (`walked`, `completed`): see the comments at the top of the
+// kernel and DESIGN.md section 4.
 #include <cuda_runtime.h>
 
 #include <cstdlib>

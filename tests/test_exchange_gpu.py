@@ -228,3 +228,48 @@ def test_single_rank_in_kernel_exchange_equals_plain_sample(oracle):
             else:
                 assert np.array_equal(got, (want.astype(np.float32) / (np.float32(1.0) + np.abs(want.astype(np.float32)))))
         a.close(); b.close(); ex.close()
+
+
+def test_in_kernel_exchange_entry_point_with_buffered_sources_falls_back_to_the_stand_alone_kernels(oracle):
+    """A scene with play_buffered sources takes the multi-kernel callback; odb_scene_sample_exchange then exchanges
+    with the stand-alone push / pull kernels - same result as the plain callback (world size 1), same lag protocol."""
+    import torch
+
+    import oddio_b200 as odb
+    from helpers import rand_in_shell, synth_pcm
+    from oddio_b200.sharding import PeerExchange
+
+    ctx = odb.init(0)
+    rng = np.random.default_rng(9)
+    pcm = synth_pcm(rng, 90000, 48000)
+    fr = odb.Frames.from_slice(48000, pcm, ctx)
+    pos = [rand_in_shell(rng, 2, 60) for _ in range(12)]
+    vel = [rng.uniform(-20, 20, 3).astype(np.float32) for _ in range(12)]
+
+    def scene():
+        ctl, sc = odb.SpatialScene.new(ctx)
+        for i in range(12):
+            if i % 3 == 0:
+                ctl.play_buffered(odb.FramesSignal(fr, 0.0), odb.SpatialOptions(pos[i], vel[i], 0.1), 100.0, 48000, 0.1)
+            else:
+                ctl.play(odb.FramesSignal(fr, 1.0), odb.SpatialOptions(pos[i], vel[i], 0.1))
+        return ctl, sc
+
+    interval, n = float(np.float32(1.0) / np.float32(48000)), 1024
+    ex = PeerExchange(ctx, 0, 1, 2 * n, depth=3)
+    (_, a), (_, b) = scene(), scene()
+    tile = torch.zeros((n, 2), device="cuda", dtype=torch.float32)
+    want = [a.sample(interval, n).copy() for _ in range(4)]
+    got = []
+    for k in range(4):
+        if b.sample_exchange(ex, interval, tile.data_ptr(), n, lag=1):
+            ctx.synchronize()
+            got.append(tile.cpu().numpy().copy())
+    ex.pull(tile.data_ptr(), 2 * n)
+    ctx.synchronize()
+    got.append(tile.cpu().numpy().copy())
+    assert len(got) == 4
+    for k in range(4):
+        assert np.array_equal(got[k], want[k])
+    assert np.abs(want[-1]).max() > 0
+    a.close(); b.close(); ex.close()
