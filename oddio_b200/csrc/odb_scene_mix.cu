@@ -711,8 +711,13 @@ static void smx_shape(int n_sources, int sm_count, int* batch, int* ctas) {
             if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
         }
     }
+    // The grid: the FEWEST CTAs that still finish in the same number of rounds as the whole chip would. A team's work
+    // is whole batches, so e.g. the 4096 batches of a 32 768-source shard take four rounds on 148 SMs (3.46 per team)
+    // and exactly four on 128 - and the 20 SMs left over are where the next callback's walk kernel runs underneath
+    // this grid instead of after it.
     const long long batches = ((long long)n_sources + best - 1) / best;
-    long long want = (batches + teams_per_cta - 1) / teams_per_cta;
+    const long long rounds = (batches + teams - 1) / teams;
+    long long want = (batches + teams_per_cta * rounds - 1) / (teams_per_cta * rounds);
     *batch = best;
     *ctas = (int)(want < 1 ? 1 : (want > sm_count ? sm_count : want));
 }
