@@ -47,6 +47,8 @@ namespace odbk {
 template <int SPLIT_, int WARPS_, int LOOP_, int ILP_>
 struct SmxCfg {
     static constexpr int SPLIT = SPLIT_, WARPS = WARPS_, LOOP = LOOP_, ILP = ILP_;
+    static constexpr bool WS = false;                                         // every warp does everything (see SmxWsCfg)
+    static constexpr int CWARPS = WARPS_;                                     // warps that mix
     static constexpr int HCHUNKS = ODB_TILE_CHUNKS / SPLIT;                   // 256-frame chunks per part
     static constexpr int NACC = HCHUNKS * 8;                                  // packed (L, R) accumulators per lane
     static constexpr int BATCH = 16 / HCHUNKS;                                // sources per batch: BATCH x 2 ears x HCHUNKS = 32 chains
@@ -66,6 +68,42 @@ struct SmxCfg {
     static_assert(SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
     static_assert(WARPS % SPLIT == 0 && (WARPS * 32) % 16 == 0, "warps come in groups of SPLIT");
 };
+// Warp-specialised shape: CWARPS_ consumer warps (teams of two, one 512-frame half each, as SmxCfg<2, ..>) never leave
+// the consume loop; CWARPS_ / 4 producer warps do what is serial or once-per-source for them - fetch the job records
+// (bulk async copies into a private staging buffer), derive each half's window / tap offsets, walk the literal cursor
+// chains (one producer pass = 2 sources of each of its 2 teams = 32 chains) and hand the result over through a ring of
+// S_ slots per consumer warp (record + cursor rows; mbarrier pairs full / empty per team and slot). The consumer still
+// issues the bulk copy of its PCM windows itself (double-buffered, one source ahead). REGC_ / REGP_ != 0: the
+// register file is re-divided with setmaxnreg (consumers REGC_, producers REGP_ registers per thread; the launch
+// allocates 96 x 640 threads) - 16 x 32 x 120 + 4 x 32 x 32 is the whole file.
+template <int CWARPS_, int S_, int REGC_, int REGP_>
+struct SmxWsCfg {
+    static constexpr bool WS = true;
+    static constexpr int SPLIT = 2, LOOP = 0, ILP = 4;
+    static constexpr int CWARPS = CWARPS_, PWARPS = CWARPS_ / 4, WARPS = CWARPS + PWARPS, S = S_, REGC = REGC_, REGP = REGP_;
+    static constexpr int HCHUNKS = ODB_TILE_CHUNKS / SPLIT, NACC = HCHUNKS * 8, BATCH = 16 / HCHUNKS;
+    static constexpr int PCM_FLOATS = ODB_FAST_PCM_CAP * HCHUNKS / 2, PCM_BYTES = PCM_FLOATS * 4;
+    static constexpr int POINTS = ODB_SPATIAL_CHUNK / 4, ROW_BYTES = POINTS * 8 + 8;
+    static constexpr int SLOT_ROWS = HCHUNKS * ROW_BYTES;                     // cursor rows of one (source, half)
+    static constexpr int REC_BYTES = 128;
+    static constexpr int ROWS_OFF = 2 * PCM_BYTES, RECS_OFF = ROWS_OFF + S * SLOT_ROWS;
+    static constexpr int WARP_BYTES = RECS_OFF + S * REC_BYTES;               // per consumer warp
+    static constexpr int PART_FRAMES = ODB_TILE_FRAMES / SPLIT;
+    static constexpr int STAGE_OFF = CWARPS * WARP_BYTES;                     // per producer warp: 2 x 4 raw job records
+    static constexpr int STAGE_BYTES = 2 * 4 * REC_BYTES;
+    static constexpr int BARS_OFF = STAGE_OFF + PWARPS * STAGE_BYTES;         // per consumer warp 2 (windows), per team 2 S, per producer 2
+    static constexpr int TEAM_BARS_OFF = BARS_OFF + CWARPS * 16;
+    static constexpr int PROD_BARS_OFF = TEAM_BARS_OFF + (CWARPS / 2) * 16 * S;
+    static constexpr int SMEM_BYTES = PROD_BARS_OFF + PWARPS * 16;
+    static_assert(CWARPS % 4 == 0, "a producer warp serves two teams of two consumer warps");
+    static_assert(S >= 4, "a producer pass fills two slots per team while the consumer holds up to two");
+    static_assert(WARP_BYTES >= PART_FRAMES * 8 + 2 * PART_FRAMES * 4, "parked part of the tile + literal-path scratch");
+    static_assert(WARP_BYTES % 16 == 0 && RECS_OFF % 16 == 0 && SLOT_ROWS % 8 == 0, "alignment of windows, records, rows");
+    static_assert(SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
+    static_assert(REGC == 0 || (CWARPS * 32 * REGC + PWARPS * 32 * REGP <= 65536 && PWARPS == 4), "register file; setmaxnreg acts on warpgroups");
+};
+#define SMX_WS_SKIP 0x100u      // code bits of a slot record: nothing to mix for this half
+#define SMX_WS_FLAGGED 0x200u   // the job takes the literal path (tail)
 constexpr int SMX_SLICE = 16;                                              // output floats one reducing CTA sums at a time
 constexpr int SMX_SLICES = 2 * ODB_TILE_FRAMES / SMX_SLICE;                // 128
 
@@ -324,23 +362,311 @@ __device__ __forceinline__ void store_output(const OdbSceneMixArgs& A, const int
     }
 }
 
+// ---- warp-specialised mix phase (SmxWsCfg) ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// Ring positions that carry over from tile to tile (the barriers' phases do). A consumer warp: the slot of its next
+// source and that slot's `full` parity, PCM windows issued / consumed. A producer warp: per team the slot of the next
+// source and how often the ring has wrapped (`empty` parity), staging buffers issued / consumed.
+// (One set of registers for both roles: a warp is a consumer or a producer for the whole kernel.)
+struct WsState {
+    uint32_t a = 0, b = 0, c = 0, d = 0;  // consumer: slot, parity, windows, -; producer: slot A, wraps A, slot B, wraps B
+    uint32_t n = 0;                       // producer: passes staged so far
+};
+
+template <class CFG>
+__device__ __forceinline__ void ws_init_barriers(const uint32_t smem_sa, const int warp, const int lane) {
+    if (lane != 0) return;
+    if (warp < CFG::CWARPS) {
+        const uint32_t tma_sa = smem_sa + (uint32_t)(CFG::BARS_OFF + warp * 16);
+        mbar_init(tma_sa, 1);
+        mbar_init(tma_sa + 8, 1);
+        if ((warp & 1) == 0) {  // the team's slot barriers: full (one arrival: the producer), empty (both consumer warps)
+            const uint32_t tb = smem_sa + (uint32_t)(CFG::TEAM_BARS_OFF + (warp >> 1) * 16 * CFG::S);
+            for (int s = 0; s < CFG::S; s++) {
+                mbar_init(tb + 8 * s, 1);
+                mbar_init(tb + 8 * CFG::S + 8 * s, 2);
+            }
+        }
+    } else {
+        const uint32_t pb = smem_sa + (uint32_t)(CFG::PROD_BARS_OFF + (warp - CFG::CWARPS) * 16);
+        mbar_init(pb, 1);
+        mbar_init(pb + 8, 1);
+    }
+}
+
+// One 1024-frame tile of the callback, warp-specialised. Returns whether one of this (consumer) warp's jobs needs the
+// literal path. The team -> source assignment is the shipped kernel's (batches of `bsz` consecutive sources, batch
+// gp + r GP in round r), and so is the order in which a warp accumulates them: the output is bit-identical.
+template <class CFG, bool STRICT, bool VARBATCH>
+__device__ __forceinline__ bool ws_mix_tile(WsState& ws, const uint32_t smem_sa, const int warp, const int lane,
+                                            const OdbJob* __restrict__ tile_jobs, const int n_sources, const int bsz, const int G,
+                                            const int tl, const u64 nz) {
+    constexpr int S = CFG::S, HCHUNKS = CFG::HCHUNKS, NACC = CFG::NACC, TEAMS = CFG::CWARPS / 2;
+    const int GP = G * TEAMS;
+    bool saw_flagged = false;
+    if (warp < CFG::CWARPS) {
+        // ================= consumer: never leaves the consume loop =================
+        if (CFG::REGC) reg_inc<CFG::REGC ? CFG::REGC : 96>();
+        const int part = warp & 1, team = warp >> 1;
+        const int gp = blockIdx.x * TEAMS + team;
+        const uint32_t win_sa = smem_sa + (uint32_t)(warp * CFG::WARP_BYTES);
+        const uint32_t rows_base = win_sa + CFG::ROWS_OFF, recs_base = win_sa + CFG::RECS_OFF;
+        const uint32_t tma_sa = smem_sa + (uint32_t)(CFG::BARS_OFF + warp * 16);
+        const uint32_t full_sa = smem_sa + (uint32_t)(CFG::TEAM_BARS_OFF + team * 16 * S), empty_sa = full_sa + 8 * S;
+        const float lanef = (float)(tl * ODB_TILE_FRAMES + lane);
+        u64 acc[NACC];
+#pragma unroll
+        for (int j = 0; j < NACC; j++) acc[j] = 0ull;
+        uint32_t slot = ws.a, par = ws.b, wi = ws.c, wc = ws.c;  // (every window issued in a tile is consumed in it)
+        auto issue = [&](const uint4& d) {  // the PCM window of a source into window buffer wi & 1 (one elected lane)
+            const u64 p = ((u64)d.y << 32) | (u64)d.x;
+            const uint32_t b = wi & 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t"
+                "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}" ::"r"(tma_sa + b * 8),
+                "r"(d.z), "r"(win_sa + b * CFG::PCM_BYTES), "l"(p)
+                : "memory");
+            wi++;
+        };
+        int r = 0, q = 0;  // position in the team's sequence: source q of its batch of round r
+        if ((gp + r * GP) * bsz + q < n_sources) {
+            mbar_wait(full_sa + 8 * slot, par);
+            uint4 hdr = lds_u128(recs_base + slot * CFG::REC_BYTES);  // window address (2 words), bytes, code
+            if (!(hdr.w & SMX_WS_SKIP)) issue(hdr);
+            for (;;) {
+                int q1 = q + 1, r1 = r;
+                if (q1 == bsz) { q1 = 0; r1++; }
+                const bool more = (gp + r1 * GP) * bsz + q1 < n_sources;
+                uint32_t nslot = slot + 1u, npar = par;
+                if (nslot == (uint32_t)S) { nslot = 0u; npar ^= 1u; }
+                uint4 hdr1 = make_uint4(0u, 0u, 0u, SMX_WS_SKIP);
+                if (more) {  // the next source's window streams in while this one is consumed
+                    mbar_wait(full_sa + 8 * nslot, npar);
+                    hdr1 = lds_u128(recs_base + nslot * CFG::REC_BYTES);
+                    if (!(hdr1.w & SMX_WS_SKIP)) issue(hdr1);
+                }
+                if (!(hdr.w & SMX_WS_SKIP)) {
+                    const uint32_t rec_sa = recs_base + slot * CFG::REC_BYTES;
+                    const uint4 P = lds_u128(rec_sa + ODB_JW_DS * 4);   // ds (L, R), prev gain (L, R)
+                    const uint4 B = lds_u128(rec_sa + ODB_JW_DG * 4);   // d_gain (L, R), -, n_frames
+                    uint32_t K[2 * HCHUNKS];
+#pragma unroll
+                    for (int i = 0; i < 2 * HCHUNKS; i += 4) {
+                        const uint4 k4 = lds_u128(rec_sa + (SJ_K + i) * 4);
+                        K[i] = k4.x; K[i + 1] = k4.y; K[i + 2] = k4.z; K[i + 3] = k4.w;
+                    }
+                    const u64 dsp = ((u64)P.y << 32) | P.x, pgp = ((u64)P.w << 32) | P.z, dgp = ((u64)B.y << 32) | B.x;
+                    const int nfr = (int)B.w;
+                    const int rr = lane & 3;
+                    const u64 d1 = rr >= 1 ? dsp : 0ull, d2 = rr >= 2 ? dsp : 0ull, d3 = rr >= 3 ? dsp : 0ull;
+                    const uint32_t rows_sa = rows_base + slot * CFG::SLOT_ROWS + (uint32_t)((lane >> 2) * 8);
+                    const uint32_t b = wc & 1u;
+                    const uint32_t pcm_b = win_sa + b * CFG::PCM_BYTES;
+                    mbar_wait(tma_sa + b * 8, (wc >> 1) & 1u);
+                    wc++;
+                    const uint32_t code = hdr.w & 7u;
+#define ODB_CONSUME(F, L, R) consume_source<CFG, STRICT, F, L, R>(acc, lane, lanef, part, rec_sa, 0u, pcm_b, rows_sa, K, nfr, d1, d2, d3, pgp, dgp, nz)
+                    if (code == 4u) ODB_CONSUME(true, false, false);  // the common case: full tile, both ears on the doppler path
+                    else if (code == 7u) ODB_CONSUME(true, true, true);
+                    else if (code == 0u) ODB_CONSUME(false, false, false);
+                    else if (code == 3u) ODB_CONSUME(false, true, true);
+                    else if (code == 6u) ODB_CONSUME(true, true, false);
+                    else if (code == 5u) ODB_CONSUME(true, false, true);
+                    else if (code == 2u) ODB_CONSUME(false, true, false);
+                    else ODB_CONSUME(false, false, true);
+#undef ODB_CONSUME
+                }
+                saw_flagged = saw_flagged || (hdr.w & SMX_WS_FLAGGED) != 0u;
+                __syncwarp();  // every lane is done with the slot (and the window) before it is handed back
+                if (lane == 0) mbar_arrive(empty_sa + 8 * slot);
+                slot = nslot; par = npar;
+                if (!more) break;
+                hdr = hdr1; q = q1; r = r1;
+            }
+        }
+        ws.a = slot; ws.b = par; ws.c = wc;
+        // park the accumulators: float2 per frame of this part at the start of the warp's region (nothing of the ring is
+        // in use any more: the producer has delivered, and this warp consumed, all of the tile's sources)
+#pragma unroll
+        for (int j = 0; j < NACC; j++)
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(win_sa + (uint32_t)((32 * j + lane) * 8)), "l"(acc[j]) : "memory");
+        if (CFG::REGC) reg_dec<96>();
+    } else {
+        // ================= producer: records, windows' addresses, cursor chains for two teams =================
+        if (CFG::REGC) reg_dec<CFG::REGP ? CFG::REGP : 96>();
+        const int pw = warp - CFG::CWARPS;
+        const int gA = blockIdx.x * TEAMS + 2 * pw;             // team A; team B = gA + 1
+        const uint32_t stage_sa = smem_sa + (uint32_t)(CFG::STAGE_OFF + pw * CFG::STAGE_BYTES);
+        const uint32_t pbar_sa = smem_sa + (uint32_t)(CFG::PROD_BARS_OFF + pw * 16);
+        // this lane's chain: source k of the pass (team k >> 1, entry k & 1), ear e, chunk c of the tile
+        const int k = lane >> 3, e = (lane >> 2) & 1, c = lane & 3;
+        uint32_t slotA = ws.a, useA = ws.b, slotB = ws.c, useB = ws.d, si = ws.n, sc = ws.n;  // (every pass staged in a tile is used in it)
+        auto team_region = [&](int kk, int half) {  // region of the consumer warp that mixes `half` of pass source kk
+            return smem_sa + (uint32_t)((2 * (2 * pw + (kk >> 1)) + half) * CFG::WARP_BYTES);
+        };
+        auto team_bars = [&](int kk) { return smem_sa + (uint32_t)(CFG::TEAM_BARS_OFF + (2 * pw + (kk >> 1)) * 16 * S); };
+        // raw job records of a pass (entries (r, q) and the next one of both teams) into staging buffer si & 1
+        auto stage = [&](int r, int q) {
+            int q1 = q + 1, r1 = r;
+            if (q1 == bsz) { q1 = 0; r1++; }
+            const int src[4] = {(gA + r * GP) * bsz + q, (gA + r1 * GP) * bsz + q1, (gA + 1 + r * GP) * bsz + q, (gA + 1 + r1 * GP) * bsz + q1};
+            int n = 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) n += src[kk] < n_sources ? 1 : 0;
+            if (n == 0) return;
+            const uint32_t b = si & 1u;
+            if (lane == 0) {
+                mbar_expect_tx(pbar_sa + b * 8, (uint32_t)(n * CFG::REC_BYTES));
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+                    if (src[kk] < n_sources)
+                        bulk_g2s(stage_sa + (uint32_t)((b * 4 + kk) * CFG::REC_BYTES), tile_jobs + src[kk], CFG::REC_BYTES, pbar_sa + b * 8);
+            }
+            si++;
+        };
+        int r = 0, q = 0;
+        stage(r, q);
+        for (;;) {
+            int q1 = q + 1, r1 = r;
+            if (q1 == bsz) { q1 = 0; r1++; }
+            const bool vA0 = (gA + r * GP) * bsz + q < n_sources, vA1 = (gA + r1 * GP) * bsz + q1 < n_sources;
+            const bool vB0 = (gA + 1 + r * GP) * bsz + q < n_sources, vB1 = (gA + 1 + r1 * GP) * bsz + q1 < n_sources;
+            if (!vA0 && !vB0) break;
+            int q2 = q1 + 1, r2 = r1;
+            if (q2 == bsz) { q2 = 0; r2++; }
+            // slots of the pass: (slotA, useA), the one after it, and the same for team B
+            uint32_t slotA1 = slotA + 1u, useA1 = useA, slotB1 = slotB + 1u, useB1 = useB;
+            if (slotA1 == (uint32_t)S) { slotA1 = 0u; useA1++; }
+            if (slotB1 == (uint32_t)S) { slotB1 = 0u; useB1++; }
+            const uint32_t sl[4] = {slotA, slotA1, slotB, slotB1}, us[4] = {useA, useA1, useB, useB1};
+            const bool va[4] = {vA0, vA1, vB0, vB1};
+            // this pass's raw records have arrived; the next pass's are requested at once
+            {
+                const uint32_t b = sc & 1u;
+                mbar_wait(pbar_sa + b * 8, (sc >> 1) & 1u);
+                sc++;
+                // both consumers of a team have handed the slot back (its previous tenant is `S` sources ago)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+                    if (va[kk] && us[kk] > 0u) mbar_wait(team_bars(kk) + 8 * S + 8 * sl[kk], (us[kk] - 1u) & 1u);
+                // record -> both halves' slots (lane l moves word l)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+                    if (va[kk]) {
+                        const uint32_t w = lds_u32(stage_sa + (uint32_t)((b * 4 + kk) * CFG::REC_BYTES + lane * 4));
+                        sts_u32(team_region(kk, 0) + CFG::RECS_OFF + sl[kk] * CFG::REC_BYTES + lane * 4, w);
+                        sts_u32(team_region(kk, 1) + CFG::RECS_OFF + sl[kk] * CFG::REC_BYTES + lane * 4, w);
+                    }
+            }
+            __syncwarp();
+            stage(r2, q2);  // (after the barrier: every lane has read the other staging buffer in the previous pass)
+            // lane (kk, half) < 8 derives what that half's consumer needs: window address and bytes, dispatch code, per
+            // chunk the shared-memory offset of PCM index `base` minus the magic bits (k_mix_fast's prologue)
+            if (lane < 8) {
+                const int kk = lane >> 1, half = lane & 1;
+                uint32_t slk = sl[0];
+                bool vk = va[0];
+#pragma unroll
+                for (int i = 1; i < 4; i++)
+                    if (kk == i) { slk = sl[i]; vk = va[i]; }
+                if (vk) {
+                    const uint32_t rec_sa = team_region(kk, half) + CFG::RECS_OFF + slk * CFG::REC_BYTES;
+                    const uint4 h = lds_u128(rec_sa);                                           // pcm lo/hi, len, flags
+                    const int nfr = (int)lds_u32(rec_sa + ODB_JW_N_FRAMES * 4);
+                    const bool mine = !(h.w & (ODB_JF_SKIP | ODB_JF_GENERAL)) && nfr > half * CFG::PART_FRAMES;
+                    const bool flagged = (h.w & ODB_JF_GENERAL) && !(h.w & (ODB_JF_SKIP | ODB_JF_RING));
+                    if (mine) {
+                        const uint2 win = lds_u64x(rec_sa + (ODB_JW_WINDOW + 2 * half) * 4);
+                        const int w_start = (int)win.x, w_len = (int)win.y;
+                        const u64 p = (((u64)h.y << 32) | (u64)h.x) + (u64)((long long)w_start * 4);
+                        const uint32_t mL = (h.w & ODB_JF_FAST_L) ? 0u : (ODB_MAGIC_BITS << 2);
+                        const uint32_t mR = (h.w & ODB_JF_FAST_R) ? 0u : (ODB_MAGIC_BITS << 2);
+                        int bL[HCHUNKS], bR[HCHUNKS];
+#pragma unroll
+                        for (int cc = 0; cc < HCHUNKS; cc++) {
+                            bL[cc] = (int)lds_u32(rec_sa + (ODB_JW_BASE + half * HCHUNKS + cc) * 4);
+                            bR[cc] = (int)lds_u32(rec_sa + (ODB_JW_BASE + ODB_TILE_CHUNKS + half * HCHUNKS + cc) * 4);
+                        }
+                        const uint32_t code = (nfr == ODB_TILE_FRAMES ? 4u : 0u) | ((h.w & ODB_JF_FAST_L) ? 2u : 0u) | ((h.w & ODB_JF_FAST_R) ? 1u : 0u);
+                        sts_u32(rec_sa, (uint32_t)p);
+                        sts_u32(rec_sa + 4, (uint32_t)(p >> 32));
+                        sts_u32(rec_sa + 8, (uint32_t)w_len * 4u);
+                        sts_u32(rec_sa + 12, code);
+#pragma unroll
+                        for (int cc = 0; cc < HCHUNKS; cc++) {  // SJ_K + 2 cc (+ 1): overwrites `base` words, read above
+                            sts_u32(rec_sa + (SJ_K + 2 * cc) * 4, (uint32_t)((bL[cc] - w_start) * 4) - mL);
+                            sts_u32(rec_sa + (SJ_K + 2 * cc + 1) * 4, (uint32_t)((bR[cc] - w_start) * 4) - mR);
+                        }
+                    } else {
+                        sts_u32(rec_sa + 12, SMX_WS_SKIP | (flagged ? SMX_WS_FLAGGED : 0u));
+                    }
+                }
+            }
+            __syncwarp();
+            // the literal cursor chains (frames.rs:195), every 4th value into the consumer's rows
+            {
+                uint32_t slk = sl[0];
+                bool vk = va[0];
+#pragma unroll
+                for (int i = 1; i < 4; i++)
+                    if (k == i) { slk = sl[i]; vk = va[i]; }
+                if (vk) {
+                    const int half = c / HCHUNKS, cc = c % HCHUNKS;
+                    const uint32_t reg_sa = team_region(k, half);
+                    const uint32_t rec_sa = reg_sa + CFG::RECS_OFF + slk * CFG::REC_BYTES;
+                    const uint32_t code = lds_u32(rec_sa + 12);
+                    if (!(code & SMX_WS_SKIP) && !(code & (e ? 1u : 2u))) {
+                        float o = __uint_as_float(lds_u32(rec_sa + (ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c) * 4));
+                        const float ds = __uint_as_float(lds_u32(rec_sa + (ODB_JW_DS + e) * 4));
+                        const uint32_t dst = reg_sa + CFG::ROWS_OFF + slk * CFG::SLOT_ROWS + (uint32_t)(cc * CFG::ROW_BYTES + e * 4);
+#pragma unroll 8
+                        for (int m = 0; m < CFG::POINTS; m++) {
+                            sts_f32(dst + (uint32_t)(m * 8), o);  // checkpoint m = cursor of frame 4 m
+                            o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds);
+                        }
+                    }
+                }
+                __syncwarp();  // the release below is cumulative over the warp's stores through this barrier
+                if ((lane & 7) == 0 && vk) mbar_arrive(team_bars(k) + 8 * slk);
+            }
+            // next pass
+            if (vA1) { slotA = slotA1 + 1u; useA = useA1; if (slotA == (uint32_t)S) { slotA = 0u; useA++; } }
+            else if (vA0) { slotA = slotA1; useA = useA1; }
+            if (vB1) { slotB = slotB1 + 1u; useB = useB1; if (slotB == (uint32_t)S) { slotB = 0u; useB++; } }
+            else if (vB0) { slotB = slotB1; useB = useB1; }
+            r = r2; q = q2;
+        }
+        ws.a = slotA; ws.b = useA; ws.c = slotB; ws.d = useB; ws.n = sc;
+        if (CFG::REGC) reg_inc<96>();
+    }
+    return saw_flagged;
+}
+
 // VARBATCH: the batch size is a run-time argument (small scenes, sharded scenes); otherwise it is the compile-time
 // CFG::BATCH - measurably faster on the full-size scene (90.2 vs 93.5 us on C3), where the chooser picks 8 anyway.
 template <class CFG, bool STRICT, bool VARBATCH>
 __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbSceneMixArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int WARPS = CFG::WARPS, SPLIT = CFG::SPLIT, HCHUNKS = CFG::HCHUNKS, BATCH = CFG::BATCH, NACC = CFG::NACC;
+    constexpr int WARPS = CFG::WARPS, CWARPS = CFG::CWARPS, SPLIT = CFG::SPLIT, HCHUNKS = CFG::HCHUNKS, BATCH = CFG::BATCH, NACC = CFG::NACC;
     constexpr int THREADS = WARPS * 32, RGROUPS = THREADS / SMX_SLICE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int part = warp % SPLIT, team = warp / SPLIT;  // the SPLIT warps of a team mix the parts of the same sources
     const uint32_t smem_sa = smem_u32(smem_raw);
-    const uint32_t pcm_sa = smem_sa + (uint32_t)(warp * CFG::WARP_BYTES);
-    const uint32_t offs_sa = pcm_sa + 2 * CFG::PCM_BYTES;
-    const uint32_t jobs_sa = smem_sa + (uint32_t)(CFG::JOBS_OFF + warp * BATCH * CFG::REC_BYTES);
-    const uint32_t bar_sa = smem_sa + (uint32_t)(CFG::BARS_OFF + warp * 16);
-    if (lane == 0) {
-        mbar_init(bar_sa, 1);
-        mbar_init(bar_sa + 8, 1);
+    const uint32_t pcm_sa = smem_sa + (uint32_t)(warp * CFG::WARP_BYTES);  // a mixing warp's region: PCM windows first
+    if constexpr (!CFG::WS) {
+        const uint32_t bar_sa = smem_sa + (uint32_t)(CFG::BARS_OFF + warp * 16);
+        if (lane == 0) {
+            mbar_init(bar_sa, 1);
+            mbar_init(bar_sa + 8, 1);
+        }
+    } else {
+        ws_init_barriers<CFG>(smem_sa, warp, lane);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -363,38 +689,44 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
     bool saw_flagged = false;  // one of this warp's jobs needs the literal path
     uint32_t parity = 0;  // bit b = phase parity of PCM buffer b's barrier
     uint32_t buf = 0;
+    WsState ws;           // warp-specialised shape: ring positions that carry over from tile to tile
 
     const int n_sources = A.n_sources;
     const u64 nz = A.nz;
     const int G = (int)gridDim.x;
-    const int gp = blockIdx.x * (WARPS / SPLIT) + team, GP = G * (WARPS / SPLIT);
+    const int gp = blockIdx.x * (CWARPS / SPLIT) + team, GP = G * (CWARPS / SPLIT);
     // Sources per batch: at most BATCH (the 32 chain lanes), fewer when that evens out the rounds - a warp's work is
     // whole batches, so e.g. 8192 sources are 1024 batches of 8 for 1184 teams (160 teams idle, the others 8 sources
     // each) but 1171 batches of 7 (every team busy, 7 sources each). Chosen by the host (odb_scene_mix_batch).
     const int bsz = VARBATCH ? A.batch : BATCH;
     const int n_batches = (n_sources + bsz - 1) / bsz;
     const int first_frame = part * CFG::PART_FRAMES;
-    const int c0 = part * HCHUNKS;
-
-    auto rec = [&](int q, int w) { return jobs_sa + (uint32_t)(q * CFG::REC_BYTES) + (uint32_t)((w * 4) ^ (q * 16)); };
-    auto start_copy = [&](int q, uint32_t b) {
-        const uint4 d = lds_u128(rec(q, SJ_SRC));
-        const u64 p = ((u64)d.y << 32) | (u64)d.x;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t"
-            "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
-            "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}" ::"r"(bar_sa + b * 8),
-            "r"(d.z), "r"(pcm_sa + b * CFG::PCM_BYTES), "l"(p)
-            : "memory");
-    };
 
     for (int tl = 0; tl < A.n_tiles; tl++) {
+        saw_flagged = false;
+        const OdbJob* tile_jobs = A.jobs + (size_t)tl * n_sources;
+      if constexpr (CFG::WS) {
+        saw_flagged = ws_mix_tile<CFG, STRICT, VARBATCH>(ws, smem_sa, warp, lane, tile_jobs, n_sources, bsz, G, tl, nz);
+      } else {
+        const uint32_t offs_sa = pcm_sa + 2 * CFG::PCM_BYTES;
+        const uint32_t jobs_sa = smem_sa + (uint32_t)(CFG::JOBS_OFF + warp * BATCH * CFG::REC_BYTES);
+        const uint32_t bar_sa = smem_sa + (uint32_t)(CFG::BARS_OFF + warp * 16);
+        const int c0 = part * HCHUNKS;
+        auto rec = [&](int q, int w) { return jobs_sa + (uint32_t)(q * CFG::REC_BYTES) + (uint32_t)((w * 4) ^ (q * 16)); };
+        auto start_copy = [&](int q, uint32_t b) {
+            const uint4 d = lds_u128(rec(q, SJ_SRC));
+            const u64 p = ((u64)d.y << 32) | (u64)d.x;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t"
+                "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}" ::"r"(bar_sa + b * 8),
+                "r"(d.z), "r"(pcm_sa + b * CFG::PCM_BYTES), "l"(p)
+                : "memory");
+        };
         u64 acc[NACC];
 #pragma unroll
         for (int j = 0; j < NACC; j++) acc[j] = 0ull;
-        saw_flagged = false;
         const float lanef = (float)(tl * ODB_TILE_FRAMES + (CFG::LOOP == 0 ? lane : 2 * lane));
-        const OdbJob* tile_jobs = A.jobs + (size_t)tl * n_sources;
 
         for (int bi = gp; bi < n_batches; bi += GP) {
             const int s0 = bi * bsz;
@@ -524,6 +856,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
                 asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(pcm_sa + (uint32_t)(f * 8)), "l"(acc[2 * j]), "l"(acc[2 * j + 1]) : "memory");
             }
         }
+      }  // !CFG::WS
         __syncwarp();
         // 3'. the flagged jobs of this warp's batches, literally (rare: none on C3); the batch prologues noticed them
         if (saw_flagged) {
@@ -549,7 +882,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             const int h = f / PART_FLOATS, fh = f - h * PART_FLOATS;
             float sum = 0.0f;
 #pragma unroll
-            for (int w = 0; w < WARPS / SPLIT; w++)
+            for (int w = 0; w < CWARPS / SPLIT; w++)
                 sum = sum + *reinterpret_cast<const float*>(smem_raw + (w * SPLIT + h) * CFG::WARP_BYTES + fh * 4);
             __stcg(pdst + f, sum);
         }
@@ -681,13 +1014,15 @@ using namespace odbk;
 typedef SmxCfg<2, 16, 0, 4> SmxDefault;
 typedef SmxCfg<2, 16, 1, 4> SmxPairs;
 typedef SmxCfg<1, 12, 0, 4> SmxWhole;
+typedef SmxWsCfg<16, 6, 120, 32> SmxWs;        // 16 consumer + 4 producer warps, register file re-divided (setmaxnreg)
+typedef SmxWsCfg<12, 8, 0, 0> SmxWs12;         // 12 consumer + 3 producer warps at the launch's 136 registers
 
 static int g_smx_cfg = -1;
 static int smx_cfg() {
     if (g_smx_cfg < 0) {
         const char* e = getenv("ODB_SMX_CFG");
         g_smx_cfg = e ? atoi(e) : 0;
-        if (g_smx_cfg != 1 && g_smx_cfg != 3) g_smx_cfg = 0;
+        if (g_smx_cfg != 1 && g_smx_cfg != 3 && g_smx_cfg != 4 && g_smx_cfg != 5) g_smx_cfg = 0;
     }
     return g_smx_cfg;
 }
@@ -699,7 +1034,7 @@ static int smx_cfg() {
 // team's work, rounds x (batch + the per-batch overhead of prologue and cursor chains, about 0.6 of a source's consume).
 template <class CFG>
 static void smx_shape(int n_sources, int sm_count, int* batch, int* ctas) {
-    const int teams_per_cta = CFG::WARPS / CFG::SPLIT;
+    const int teams_per_cta = CFG::CWARPS / CFG::SPLIT;
     const long long teams = (long long)teams_per_cta * sm_count;
     int best = CFG::BATCH;
     if ((long long)n_sources < teams * (CFG::BATCH / 2)) {
@@ -725,6 +1060,8 @@ void odb_scene_mix_shape(int n_sources, int sm_count, int* batch, int* ctas) {
     switch (smx_cfg()) {
         case 1: return smx_shape<SmxPairs>(n_sources, sm_count, batch, ctas);
         case 3: return smx_shape<SmxWhole>(n_sources, sm_count, batch, ctas);
+        case 4: return smx_shape<SmxWs>(n_sources, sm_count, batch, ctas);
+        case 5: return smx_shape<SmxWs12>(n_sources, sm_count, batch, ctas);
         default: return smx_shape<SmxDefault>(n_sources, sm_count, batch, ctas);
     }
 }
@@ -749,6 +1086,8 @@ cudaError_t odb_launch_scene_mix(const OdbSceneMixArgs& args, int n_ctas, int mo
     switch (smx_cfg()) {
         case 1: return launch_scene_mix_mode<SmxPairs>(a, n_ctas, mode, st);
         case 3: return launch_scene_mix_mode<SmxWhole>(a, n_ctas, mode, st);
+        case 4: return launch_scene_mix_mode<SmxWs>(a, n_ctas, mode, st);
+        case 5: return launch_scene_mix_mode<SmxWs12>(a, n_ctas, mode, st);
         default: return launch_scene_mix_mode<SmxDefault>(a, n_ctas, mode, st);
     }
 }
