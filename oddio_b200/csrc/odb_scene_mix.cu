@@ -71,11 +71,12 @@ struct SmxCfg {
 // Warp-specialised shape: CWARPS_ consumer warps (teams of two, one 512-frame half each, as SmxCfg<2, ..>) never leave
 // the consume loop; CWARPS_ / 4 producer warps do what is serial or once-per-source for them - fetch the job records
 // (bulk async copies into a private staging buffer), derive each half's window / tap offsets, walk the literal cursor
-// chains (one producer pass = 2 sources of each of its 2 teams = 32 chains) and hand the result over through a ring of
+// chains (one producer pass = 4 sources of each of its 2 teams: 32 lanes x both ears packed = 64 chains) and hand the
+// result over through a ring of
 // S_ slots per consumer warp (record + cursor rows; mbarrier pairs full / empty per team and slot). The consumer still
 // issues the bulk copy of its PCM windows itself (double-buffered, one source ahead). REGC_ / REGP_ != 0: the
-// register file is re-divided with setmaxnreg (consumers REGC_, producers REGP_ registers per thread; the launch
-// allocates 96 x 640 threads) - 16 x 32 x 120 + 4 x 32 x 32 is the whole file.
+// register file is re-divided with setmaxnreg (consumers REGC_, producers REGP_ registers per thread, out of the
+// 96 x 640 the launch allocates: 16 x 32 x 112 + 4 x 32 x 32).
 template <int CWARPS_, int S_, int REGC_, int REGP_>
 struct SmxWsCfg {
     static constexpr bool WS = true;
@@ -89,18 +90,20 @@ struct SmxWsCfg {
     static constexpr int ROWS_OFF = 2 * PCM_BYTES, RECS_OFF = ROWS_OFF + S * SLOT_ROWS;
     static constexpr int WARP_BYTES = RECS_OFF + S * REC_BYTES;               // per consumer warp
     static constexpr int PART_FRAMES = ODB_TILE_FRAMES / SPLIT;
-    static constexpr int STAGE_OFF = CWARPS * WARP_BYTES;                     // per producer warp: 2 x 4 raw job records
-    static constexpr int STAGE_BYTES = 2 * 4 * REC_BYTES;
+    static constexpr int STAGE_OFF = CWARPS * WARP_BYTES;                     // per producer warp: 2 x (2 PASS) raw job records
+    static constexpr int PASS = 4;                                            // sources per team and producer pass
+    static constexpr int STAGE_BYTES = 2 * 2 * PASS * REC_BYTES;
     static constexpr int BARS_OFF = STAGE_OFF + PWARPS * STAGE_BYTES;         // per consumer warp 2 (windows), per team 2 S, per producer 2
     static constexpr int TEAM_BARS_OFF = BARS_OFF + CWARPS * 16;
     static constexpr int PROD_BARS_OFF = TEAM_BARS_OFF + (CWARPS / 2) * 16 * S;
     static constexpr int SMEM_BYTES = PROD_BARS_OFF + PWARPS * 16;
     static_assert(CWARPS % 4 == 0, "a producer warp serves two teams of two consumer warps");
-    static_assert(S >= 4, "a producer pass fills two slots per team while the consumer holds up to two");
+    static_assert(S >= PASS + 2, "a producer pass fills PASS slots per team while the consumer holds up to two");
     static_assert(WARP_BYTES >= PART_FRAMES * 8 + 2 * PART_FRAMES * 4, "parked part of the tile + literal-path scratch");
     static_assert(WARP_BYTES % 16 == 0 && RECS_OFF % 16 == 0 && SLOT_ROWS % 8 == 0, "alignment of windows, records, rows");
     static_assert(SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
-    static_assert(REGC == 0 || (CWARPS * 32 * REGC + PWARPS * 32 * REGP <= 65536 && PWARPS == 4), "register file; setmaxnreg acts on warpgroups");
+    // setmaxnreg moves registers inside what the launch gave the CTA (96 x 32 x WARPS), between whole warpgroups
+    static_assert(REGC == 0 || (CWARPS * 32 * REGC + PWARPS * 32 * REGP <= 96 * 32 * WARPS && PWARPS == 4 && WARPS == 20), "register pool of the CTA");
 };
 #define SMX_WS_SKIP 0x100u      // code bits of a slot record: nothing to mix for this half
 #define SMX_WS_FLAGGED 0x200u   // the job takes the literal path (tail)
@@ -500,83 +503,81 @@ __device__ __forceinline__ bool ws_mix_tile(WsState& ws, const uint32_t smem_sa,
     } else {
         // ================= producer: records, windows' addresses, cursor chains for two teams =================
         if (CFG::REGC) reg_dec<CFG::REGP ? CFG::REGP : 96>();
+        constexpr int E = CFG::PASS;                            // entries (sources) per team and pass: 2 teams x E = 8 sources
         const int pw = warp - CFG::CWARPS;
         const int gA = blockIdx.x * TEAMS + 2 * pw;             // team A; team B = gA + 1
         const uint32_t stage_sa = smem_sa + (uint32_t)(CFG::STAGE_OFF + pw * CFG::STAGE_BYTES);
         const uint32_t pbar_sa = smem_sa + (uint32_t)(CFG::PROD_BARS_OFF + pw * 16);
-        // this lane's chain: source k of the pass (team k >> 1, entry k & 1), ear e, chunk c of the tile
-        const int k = lane >> 3, e = (lane >> 2) & 1, c = lane & 3;
-        uint32_t slotA = ws.a, useA = ws.b, slotB = ws.c, useB = ws.d, si = ws.n, sc = ws.n;  // (every pass staged in a tile is used in it)
-        auto team_region = [&](int kk, int half) {  // region of the consumer warp that mixes `half` of pass source kk
-            return smem_sa + (uint32_t)((2 * (2 * pw + (kk >> 1)) + half) * CFG::WARP_BYTES);
+        // this lane's pair of chains (both ears packed): pass source k (team k / E, entry k % E), chunk c of the tile
+        const int k = lane >> 2, c = lane & 3;
+        const int kt = k / E, kj = k % E;
+        const uint32_t my_bars = smem_sa + (uint32_t)(CFG::TEAM_BARS_OFF + (2 * pw + kt) * 16 * S);
+        uint32_t slotA = ws.a, useA = ws.b, slotB = ws.c, useB = ws.d, staged = ws.n, used = ws.n;  // (every pass staged in a tile is used in it)
+        auto region = [&](int t, int half) {  // region of the consumer warp that mixes `half` for team t of the pair
+            return smem_sa + (uint32_t)((2 * (2 * pw + t) + half) * CFG::WARP_BYTES);
         };
-        auto team_bars = [&](int kk) { return smem_sa + (uint32_t)(CFG::TEAM_BARS_OFF + (2 * pw + (kk >> 1)) * 16 * S); };
-        // raw job records of a pass (entries (r, q) and the next one of both teams) into staging buffer si & 1
+        auto src_of = [&](int t, int r, int q, int j) {  // source of entry j after position (r, q) in team t's sequence
+            int qq = q + j, rr = r;
+            while (qq >= bsz) { qq -= bsz; rr++; }
+            return (gA + t + rr * GP) * bsz + qq;
+        };
+        // raw job records of the pass that starts at (r, q) into staging buffer staged & 1: lane kk < 2 E fetches one
         auto stage = [&](int r, int q) {
-            int q1 = q + 1, r1 = r;
-            if (q1 == bsz) { q1 = 0; r1++; }
-            const int src[4] = {(gA + r * GP) * bsz + q, (gA + r1 * GP) * bsz + q1, (gA + 1 + r * GP) * bsz + q, (gA + 1 + r1 * GP) * bsz + q1};
-            int n = 0;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) n += src[kk] < n_sources ? 1 : 0;
-            if (n == 0) return;
-            const uint32_t b = si & 1u;
-            if (lane == 0) {
-                mbar_expect_tx(pbar_sa + b * 8, (uint32_t)(n * CFG::REC_BYTES));
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++)
-                    if (src[kk] < n_sources)
-                        bulk_g2s(stage_sa + (uint32_t)((b * 4 + kk) * CFG::REC_BYTES), tile_jobs + src[kk], CFG::REC_BYTES, pbar_sa + b * 8);
-            }
-            si++;
+            const bool v = lane < 2 * E && src_of(lane / E, r, q, lane % E) < n_sources;
+            const uint32_t m = __ballot_sync(0xffffffffu, v);
+            if (m == 0u) return;
+            const uint32_t b = staged & 1u;
+            if (lane == 0) mbar_expect_tx(pbar_sa + b * 8, (uint32_t)(__popc(m) * CFG::REC_BYTES));
+            __syncwarp();
+            if (v) bulk_g2s(stage_sa + (uint32_t)((b * 2 * E + lane) * CFG::REC_BYTES), tile_jobs + src_of(lane / E, r, q, lane % E), CFG::REC_BYTES, pbar_sa + b * 8);
+            staged++;
         };
         int r = 0, q = 0;
         stage(r, q);
         for (;;) {
-            int q1 = q + 1, r1 = r;
-            if (q1 == bsz) { q1 = 0; r1++; }
-            const bool vA0 = (gA + r * GP) * bsz + q < n_sources, vA1 = (gA + r1 * GP) * bsz + q1 < n_sources;
-            const bool vB0 = (gA + 1 + r * GP) * bsz + q < n_sources, vB1 = (gA + 1 + r1 * GP) * bsz + q1 < n_sources;
-            if (!vA0 && !vB0) break;
-            int q2 = q1 + 1, r2 = r1;
-            if (q2 == bsz) { q2 = 0; r2++; }
-            // slots of the pass: (slotA, useA), the one after it, and the same for team B
-            uint32_t slotA1 = slotA + 1u, useA1 = useA, slotB1 = slotB + 1u, useB1 = useB;
-            if (slotA1 == (uint32_t)S) { slotA1 = 0u; useA1++; }
-            if (slotB1 == (uint32_t)S) { slotB1 = 0u; useB1++; }
-            const uint32_t sl[4] = {slotA, slotA1, slotB, slotB1}, us[4] = {useA, useA1, useB, useB1};
-            const bool va[4] = {vA0, vA1, vB0, vB1};
-            // this pass's raw records have arrived; the next pass's are requested at once
-            {
-                const uint32_t b = sc & 1u;
-                mbar_wait(pbar_sa + b * 8, (sc >> 1) & 1u);
-                sc++;
-                // both consumers of a team have handed the slot back (its previous tenant is `S` sources ago)
+            // valid entries of this pass per team (a team's sources end at n_sources; team B's lie behind team A's)
+            int nA = 0, nB = 0;
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++)
-                    if (va[kk] && us[kk] > 0u) mbar_wait(team_bars(kk) + 8 * S + 8 * sl[kk], (us[kk] - 1u) & 1u);
-                // record -> both halves' slots (lane l moves word l)
+            for (int j = 0; j < E; j++) {
+                nA += src_of(0, r, q, j) < n_sources ? 1 : 0;
+                nB += src_of(1, r, q, j) < n_sources ? 1 : 0;
+            }
+            if (nA == 0) break;
+            int r2 = r, q2 = q + E;
+            while (q2 >= bsz) { q2 -= bsz; r2++; }
+            // this lane's slot: entry kj of team kt
+            const bool my_valid = kj < (kt ? nB : nA);
+            uint32_t my_slot = (kt ? slotB : slotA) + (uint32_t)kj, my_use = kt ? useB : useA;
+            if (my_slot >= (uint32_t)S) { my_slot -= (uint32_t)S; my_use++; }
+            // the pass's raw records have arrived
+            const uint32_t b = used & 1u;
+            mbar_wait(pbar_sa + b * 8, (used >> 1) & 1u);
+            used++;
+            // both consumers of the team have handed the slot back (its previous tenant was S sources ago)
+            if (my_valid && my_use > 0u) mbar_wait(my_bars + 8 * S + 8 * my_slot, (my_use - 1u) & 1u);
+            __syncwarp();
+            // record -> both halves' slots (lane l moves word l)
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++)
-                    if (va[kk]) {
-                        const uint32_t w = lds_u32(stage_sa + (uint32_t)((b * 4 + kk) * CFG::REC_BYTES + lane * 4));
-                        sts_u32(team_region(kk, 0) + CFG::RECS_OFF + sl[kk] * CFG::REC_BYTES + lane * 4, w);
-                        sts_u32(team_region(kk, 1) + CFG::RECS_OFF + sl[kk] * CFG::REC_BYTES + lane * 4, w);
-                    }
+            for (int kk = 0; kk < 2 * E; kk++) {
+                const int t = kk / E, j = kk % E;
+                if (j < (t ? nB : nA)) {
+                    uint32_t sl = (t ? slotB : slotA) + (uint32_t)j;
+                    if (sl >= (uint32_t)S) sl -= (uint32_t)S;
+                    const uint32_t w = lds_u32(stage_sa + (uint32_t)((b * 2 * E + kk) * CFG::REC_BYTES + lane * 4));
+                    sts_u32(region(t, 0) + CFG::RECS_OFF + sl * CFG::REC_BYTES + lane * 4, w);
+                    sts_u32(region(t, 1) + CFG::RECS_OFF + sl * CFG::REC_BYTES + lane * 4, w);
+                }
             }
             __syncwarp();
-            stage(r2, q2);  // (after the barrier: every lane has read the other staging buffer in the previous pass)
-            // lane (kk, half) < 8 derives what that half's consumer needs: window address and bytes, dispatch code, per
+            stage(r2, q2);  // the next pass's records are requested at once (its staging buffer was read a pass ago)
+            // lane (kk, half) < 4 E derives what that half's consumer needs: window address and bytes, dispatch code, per
             // chunk the shared-memory offset of PCM index `base` minus the magic bits (k_mix_fast's prologue)
-            if (lane < 8) {
-                const int kk = lane >> 1, half = lane & 1;
-                uint32_t slk = sl[0];
-                bool vk = va[0];
-#pragma unroll
-                for (int i = 1; i < 4; i++)
-                    if (kk == i) { slk = sl[i]; vk = va[i]; }
-                if (vk) {
-                    const uint32_t rec_sa = team_region(kk, half) + CFG::RECS_OFF + slk * CFG::REC_BYTES;
+            {
+                const int kk = lane >> 1, half = lane & 1, t = kk / E, j = kk % E;
+                if (lane < 4 * E && j < (t ? nB : nA)) {
+                    uint32_t sl = (t ? slotB : slotA) + (uint32_t)j;
+                    if (sl >= (uint32_t)S) sl -= (uint32_t)S;
+                    const uint32_t rec_sa = region(t, half) + CFG::RECS_OFF + sl * CFG::REC_BYTES;
                     const uint4 h = lds_u128(rec_sa);                                           // pcm lo/hi, len, flags
                     const int nfr = (int)lds_u32(rec_sa + ODB_JW_N_FRAMES * 4);
                     const bool mine = !(h.w & (ODB_JF_SKIP | ODB_JF_GENERAL)) && nfr > half * CFG::PART_FRAMES;
@@ -609,40 +610,34 @@ __device__ __forceinline__ bool ws_mix_tile(WsState& ws, const uint32_t smem_sa,
                 }
             }
             __syncwarp();
-            // the literal cursor chains (frames.rs:195), every 4th value into the consumer's rows
-            {
-                uint32_t slk = sl[0];
-                bool vk = va[0];
-#pragma unroll
-                for (int i = 1; i < 4; i++)
-                    if (k == i) { slk = sl[i]; vk = va[i]; }
-                if (vk) {
-                    const int half = c / HCHUNKS, cc = c % HCHUNKS;
-                    const uint32_t reg_sa = team_region(k, half);
-                    const uint32_t rec_sa = reg_sa + CFG::RECS_OFF + slk * CFG::REC_BYTES;
-                    const uint32_t code = lds_u32(rec_sa + 12);
-                    if (!(code & SMX_WS_SKIP) && !(code & (e ? 1u : 2u))) {
-                        float o = __uint_as_float(lds_u32(rec_sa + (ODB_JW_OFF0 + ODB_TILE_CHUNKS * e + c) * 4));
-                        const float ds = __uint_as_float(lds_u32(rec_sa + (ODB_JW_DS + e) * 4));
-                        const uint32_t dst = reg_sa + CFG::ROWS_OFF + slk * CFG::SLOT_ROWS + (uint32_t)(cc * CFG::ROW_BYTES + e * 4);
+            // the literal cursor chains `offset += ds` (frames.rs:195) of both ears in one packed add per step, every 4th
+            // value into the consumer's rows (an ear on the ds ~= 1 path has a row nobody reads)
+            if (my_valid) {
+                const int half = c / HCHUNKS, cc = c % HCHUNKS;
+                const uint32_t reg_sa = region(kt, half);
+                const uint32_t rec_sa = reg_sa + CFG::RECS_OFF + my_slot * CFG::REC_BYTES;
+                if (!(lds_u32(rec_sa + 12) & SMX_WS_SKIP)) {
+                    u64 o = pk2(__uint_as_float(lds_u32(rec_sa + (ODB_JW_OFF0 + c) * 4)),
+                                __uint_as_float(lds_u32(rec_sa + (ODB_JW_OFF0 + ODB_TILE_CHUNKS + c) * 4)));
+                    const u64 ds = lds_u64(rec_sa + ODB_JW_DS * 4);
+                    const uint32_t dst = reg_sa + CFG::ROWS_OFF + my_slot * CFG::SLOT_ROWS + (uint32_t)(cc * CFG::ROW_BYTES);
 #pragma unroll 8
-                        for (int m = 0; m < CFG::POINTS; m++) {
-                            sts_f32(dst + (uint32_t)(m * 8), o);  // checkpoint m = cursor of frame 4 m
-                            o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds); o = __fadd_rn(o, ds);
-                        }
+                    for (int m = 0; m < CFG::POINTS; m++) {
+                        asm volatile("st.shared.b64 [%0], %1;" ::"r"(dst + (uint32_t)(m * 8)), "l"(o) : "memory");  // checkpoint m = cursors of frame 4 m
+                        o = add2(o, ds); o = add2(o, ds); o = add2(o, ds); o = add2(o, ds);
                     }
                 }
-                __syncwarp();  // the release below is cumulative over the warp's stores through this barrier
-                if ((lane & 7) == 0 && vk) mbar_arrive(team_bars(k) + 8 * slk);
             }
+            __syncwarp();  // the release below is cumulative over the warp's stores through this barrier
+            if (c == 0 && my_valid) mbar_arrive(my_bars + 8 * my_slot);
             // next pass
-            if (vA1) { slotA = slotA1 + 1u; useA = useA1; if (slotA == (uint32_t)S) { slotA = 0u; useA++; } }
-            else if (vA0) { slotA = slotA1; useA = useA1; }
-            if (vB1) { slotB = slotB1 + 1u; useB = useB1; if (slotB == (uint32_t)S) { slotB = 0u; useB++; } }
-            else if (vB0) { slotB = slotB1; useB = useB1; }
+            slotA += (uint32_t)nA;
+            if (slotA >= (uint32_t)S) { slotA -= (uint32_t)S; useA++; }
+            slotB += (uint32_t)nB;
+            if (slotB >= (uint32_t)S) { slotB -= (uint32_t)S; useB++; }
             r = r2; q = q2;
         }
-        ws.a = slotA; ws.b = useA; ws.c = slotB; ws.d = useB; ws.n = sc;
+        ws.a = slotA; ws.b = useA; ws.c = slotB; ws.d = useB; ws.n = used;
         if (CFG::REGC) reg_inc<96>();
     }
     return saw_flagged;
@@ -826,7 +821,12 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
                     mbar_wait(bar_sa + buf * 8, (parity >> buf) & 1u);
                     parity ^= 1u << buf;
 #define ODB_CONSUME(F, L, R) consume_source<CFG, STRICT, F, L, R>(acc, lane, lanef, part, off0_sa, off0_x, pcm_b, rows_sa, K, nfr, d1, d2, d3, pgp, dgp, nz)
-                    if (B.z == 4u) ODB_CONSUME(true, false, false);  // the common case: full tile, both ears on the doppler path
+                    // The common case gets a direct branch: the comparison is hidden from the compiler, which would otherwise
+                    // fold it into the jump table of the switch below (a constant-bank load and an indirect branch in front
+                    // of every source's consume loop).
+                    uint32_t common;
+                    asm("set.eq.u32.u32 %0, %1, 4;" : "=r"(common) : "r"(B.z));
+                    if (common) ODB_CONSUME(true, false, false);  // full tile, both ears on the doppler path
                     else switch (B.z) {
                         case 7: ODB_CONSUME(true, true, true); break;
                         case 0: ODB_CONSUME(false, false, false); break;
@@ -1014,7 +1014,7 @@ using namespace odbk;
 typedef SmxCfg<2, 16, 0, 4> SmxDefault;
 typedef SmxCfg<2, 16, 1, 4> SmxPairs;
 typedef SmxCfg<1, 12, 0, 4> SmxWhole;
-typedef SmxWsCfg<16, 6, 120, 32> SmxWs;        // 16 consumer + 4 producer warps, register file re-divided (setmaxnreg)
+typedef SmxWsCfg<16, 7, 112, 32> SmxWs;        // 16 consumer + 4 producer warps, register file re-divided (setmaxnreg)
 typedef SmxWsCfg<12, 8, 0, 0> SmxWs12;         // 12 consumer + 3 producer warps at the launch's 136 registers
 
 static int g_smx_cfg = -1;
