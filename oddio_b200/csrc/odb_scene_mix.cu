@@ -649,7 +649,9 @@ template <class CFG, bool STRICT, bool VARBATCH>
 __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbSceneMixArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WARPS = CFG::WARPS, CWARPS = CFG::CWARPS, SPLIT = CFG::SPLIT, HCHUNKS = CFG::HCHUNKS, BATCH = CFG::BATCH, NACC = CFG::NACC;
-    constexpr int THREADS = WARPS * 32, RGROUPS = THREADS / SMX_SLICE;
+    // RGROUPS: groups of 16 threads that share the slice reduce. The warp-specialised shapes use the 512-thread shapes' 32
+    // (their extra warps sit the reduce out), so that their sums round exactly like the shipped kernel's.
+    constexpr int THREADS = WARPS * 32, RGROUPS = CFG::WS && THREADS / SMX_SLICE > 32 ? 32 : THREADS / SMX_SLICE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int part = warp % SPLIT, team = warp / SPLIT;  // the SPLIT warps of a team mix the parts of the same sources
     const uint32_t smem_sa = smem_u32(smem_raw);
@@ -907,9 +909,11 @@ __global__ void __launch_bounds__(CFG::WARPS * 32, 1) k_scene_mix(const OdbScene
             const int fl = threadIdx.x & (SMX_SLICE - 1), grp = threadIdx.x / SMX_SLICE;
             const int f = sl * SMX_SLICE + fl;
             const float* p = A.partials + (size_t)tl * G * (2 * ODB_TILE_FRAMES) + f;
-            float sum = 0.0f;
-            for (int i = grp; i < G; i += RGROUPS) sum = sum + __ldcg(p + (size_t)i * (2 * ODB_TILE_FRAMES));
-            red[grp * SMX_SLICE + fl] = sum;
+            if (!CFG::WS || grp < RGROUPS) {
+                float sum = 0.0f;
+                for (int i = grp; i < G; i += RGROUPS) sum = sum + __ldcg(p + (size_t)i * (2 * ODB_TILE_FRAMES));
+                red[grp * SMX_SLICE + fl] = sum;
+            }
             __syncthreads();
             if (threadIdx.x < SMX_SLICE) {
                 float total = 0.0f;

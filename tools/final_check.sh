@@ -6,3 +6,4 @@ import json
 d=json.load(open("gpurun_out/$1_bench_n1.json"))
 print("step %.1f us kernel %.1f us frac %.3f e2e %.3g checksum %.9f" % (d["ms_per_step"]*1e3, d["roofline"]["kernel_ms"]*1e3, d["roofline"]["frac"], d["e2e"]["value"], d["checksum"]))
 PY
+timeout 60 python bench.py --variant 0 --no-cpu-baseline --skip-e2e > gpurun_out/$1_bench_n1_strict.json 2>> gpurun_out/$1_bench_n1.err; echo "strict rc=$?"
