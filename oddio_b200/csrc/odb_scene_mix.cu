@@ -72,11 +72,12 @@ struct SmxCfg {
 // the consume loop; CWARPS_ / 4 producer warps do what is serial or once-per-source for them - fetch the job records
 // (bulk async copies into a private staging buffer), derive each half's window / tap offsets, walk the literal cursor
 // chains (one producer pass = 4 sources of each of its 2 teams: 32 lanes x both ears packed = 64 chains) and hand the
-// result over through a ring of
-// S_ slots per consumer warp (record + cursor rows; mbarrier pairs full / empty per team and slot). The consumer still
-// issues the bulk copy of its PCM windows itself (double-buffered, one source ahead). REGC_ / REGP_ != 0: the
+// result over through a ring of S_ slots per consumer warp (record + cursor rows; mbarrier pairs full / empty per
+// team and slot; tests/test_ws_handover_model.py checks the arithmetic of that hand-over on the CPU). The consumer
+// still issues the bulk copy of its PCM windows itself (double-buffered, one source ahead). REGC_ / REGP_ != 0: the
 // register file is re-divided with setmaxnreg (consumers REGC_, producers REGP_ registers per thread, out of the
 // 96 x 640 the launch allocates: 16 x 32 x 112 + 4 x 32 x 32).
+// Measured slower than SmxCfg<2, 16, 0, 4> on C3: an experiment behind ODB_SMX_CFG, not the default.
 template <int CWARPS_, int S_, int REGC_, int REGP_>
 struct SmxWsCfg {
     static constexpr bool WS = true;
@@ -98,7 +99,7 @@ struct SmxWsCfg {
     static constexpr int PROD_BARS_OFF = TEAM_BARS_OFF + (CWARPS / 2) * 16 * S;
     static constexpr int SMEM_BYTES = PROD_BARS_OFF + PWARPS * 16;
     static_assert(CWARPS % 4 == 0, "a producer warp serves two teams of two consumer warps");
-    static_assert(S >= PASS + 2, "a producer pass fills PASS slots per team while the consumer holds up to two");
+    static_assert(S >= PASS + 2, "a producer pass fills PASS slots per team while the consumer holds one (PASS + 1 is the minimum) - one to spare");
     static_assert(WARP_BYTES >= PART_FRAMES * 8 + 2 * PART_FRAMES * 4, "parked part of the tile + literal-path scratch");
     static_assert(WARP_BYTES % 16 == 0 && RECS_OFF % 16 == 0 && SLOT_ROWS % 8 == 0, "alignment of windows, records, rows");
     static_assert(SMEM_BYTES <= 232448, "fits the 227 KB a CTA may use");
