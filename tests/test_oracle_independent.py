@@ -1,0 +1,280 @@
+"""A second, independent statement of SpatialScene::sample's seek path, against the C++ oracle (CPU only).
+
+The reference holds no numeric test of `SpatialScene::sample` (spatial.rs:606-665 only checks when a finished signal is
+dropped), so the oracle's numbers for the headline path rest on how faithfully it restates the source (DESIGN.md
+section 6). This file restates the same lines a second time, in another language and written from the reference alone
+- scalar numpy float32 / float64 operations in the reference's order - and requires the C++ oracle to agree BIT FOR BIT
+on output, f64 cursors and removal behaviour. Two independent restatements agreeing is not the reference itself, but
+it rules out the slips a single restatement can hide (operation order, f32 vs f64 intermediates, truncation, chunking).
+
+Reference lines: lib.rs:90-93 (run), spatial.rs:191-265 (walk_set), 345-349 (set_listener_rotation), 376-471 (sample,
+seek set), 489-503 (smoothed_position), 522-543 (EarState::new), 563-598 (Ear), math/mod.rs:32-99, frames.rs:105-123
+(get_pair), 176-213 (FramesSignal), frame.rs:39-41 (lerp).
+
+(Writing it caught a slip - in THIS file: the first draft forgot that `set_listener_rotation` stores the inverse
+rotation; the C++ oracle had it right.)"""
+import numpy as np
+import pytest
+
+f32 = np.float32
+f64 = np.float64
+
+SPEED_OF_SOUND = f32(343.0)
+HEAD_RADIUS = f32(0.1075)
+POSITION_SMOOTHING_PERIOD = f32(0.5)
+EPSILON = np.finfo(np.float32).eps
+
+
+def v3(x):
+    return [f32(x[0]), f32(x[1]), f32(x[2])]
+
+
+def norm(x):  # math/mod.rs:32-34
+    s = f32(0.0)
+    for c in x:
+        s = f32(s + f32(c * c))
+    return f32(np.sqrt(s))
+
+
+def dot(x, y):  # :36-42
+    s = f32(0.0)
+    for a, b in zip(x, y):
+        s = f32(s + f32(a * b))
+    return s
+
+
+def scale(v, k):  # :44-46
+    return [f32(v[0] * k), f32(v[1] * k), f32(v[2] * k)]
+
+
+def sub(a, b):  # :48-50
+    return [f32(a[0] - b[0]), f32(a[1] - b[1]), f32(a[2] - b[2])]
+
+
+def add(a, b):  # :52-54
+    return [f32(a[0] + b[0]), f32(a[1] + b[1]), f32(a[2] + b[2])]
+
+
+def mix(a, b, r):  # :56-59
+    ir = f32(f32(1.0) - r)
+    return [f32(f32(ir * a[i]) + f32(r * b[i])) for i in range(3)]
+
+
+def quat_mul(q, r):  # :68-79; q = (s, [x, y, z])
+    qs, (qx, qy, qz) = q
+    rs, (rx, ry, rz) = r
+
+    def chain(a, b, c, d):  # a + b + c + d evaluated left to right, each term already rounded
+        return f32(f32(f32(a + b) + c) + d)
+
+    s = chain(f32(qs * rs), -f32(qx * rx), -f32(qy * ry), -f32(qz * rz))
+    x = chain(f32(qs * rx), f32(qx * rs), f32(qy * rz), -f32(qz * ry))
+    y = chain(f32(qs * ry), -f32(qx * rz), f32(qy * rs), f32(qz * rx))
+    z = chain(f32(qs * rz), f32(qx * ry), -f32(qy * rx), f32(qz * rs))
+    return (s, [x, y, z])
+
+
+def rotate(rot, p):  # :81-95
+    inv = (rot[0], [f32(-rot[1][0]), f32(-rot[1][1]), f32(-rot[1][2])])
+    return quat_mul(rot, quat_mul((f32(0.0), list(p)), inv))[1]
+
+
+SQRT17 = f32(np.sqrt(f32(17.0)))
+
+
+def ear_pos(ear):  # spatial.rs:565-576
+    return [f32(-HEAD_RADIUS) if ear == 0 else HEAD_RADIUS, f32(0.0), f32(0.0)]
+
+
+def ear_dir(ear):  # :579-597: [+-4, 0, -1] normalised
+    sign = f32(-1.0) if ear == 0 else f32(1.0)
+    return [f32(f32(sign * f32(4.0)) / SQRT17), f32(0.0), f32(f32(-1.0) / SQRT17)]
+
+
+def ear_state(p, ear, radius):  # :522-543 -> (offset, gain)
+    distance = norm(sub(p, ear_pos(ear)))
+    offset = f32(distance * f32(f32(-1.0) / SPEED_OF_SOUND))
+    distance_gain = f32(radius / max(distance, radius))
+    if distance < f32(1e-3):
+        stereo = f32(f32(0.5) + f32(0.5))
+    else:
+        stereo = f32(f32(0.5) + dot(ear_dir(ear), scale(p, f32(f32(0.5) / distance))))
+    return offset, f32(stereo * distance_gain)
+
+
+def trunc_isize(x):
+    return int(np.trunc(x))
+
+
+class PyFramesSignal:
+    def __init__(self, samples, rate, start_seconds):
+        self.samples, self.rate, self.t = np.asarray(samples, dtype=f32), f64(rate), f64(start_seconds)
+
+    def get_pair(self, s):  # frames.rs:105-123
+        n = self.samples.size
+        z = f32(0.0)
+        if s >= 0:
+            if s < n - 1:
+                return self.samples[s], self.samples[s + 1]
+            if s < n:
+                return self.samples[s], z
+            return z, z
+        if s < -1:
+            return z, z
+        return z, self.samples[0]
+
+    def sample(self, interval, n):  # :176-201
+        out = np.empty(n, dtype=f32)
+        s0 = f64(self.t * self.rate)
+        ds = f32(interval * f32(self.rate))
+        base = trunc_isize(s0)
+        if abs(f32(ds - f32(1.0))) <= EPSILON:
+            fract = f32(s0 - f64(base))
+            for i in range(n):
+                a, b = self.get_pair(base + i)
+                out[i] = f32(a + f32(fract * f32(b - a)))  # frame.rs:39-41
+        else:
+            offset = f32(s0 - f64(base))
+            for i in range(n):
+                tr = trunc_isize(offset)
+                a, b = self.get_pair(base + tr)
+                fract = f32(offset - f32(tr))
+                out[i] = f32(a + f32(fract * f32(b - a)))
+                offset = f32(offset + ds)
+        self.t = f64(self.t + f64(f64(interval) * f64(n)))
+        return out
+
+    def is_finished(self):  # :204-206
+        return self.t >= f64(self.samples.size - 1) / self.rate
+
+    def seek(self, seconds):  # :210-213
+        self.t = f64(self.t + f64(f32(seconds)))
+
+
+class PySource:
+    def __init__(self, inner, position, velocity, radius):  # spatial.rs:60-117
+        self.inner, self.radius = inner, f32(radius)
+        self.received = (v3(position), v3(velocity), False)
+        self.pending = None
+        self.prev_position, self.dt = v3(position), f32(0.0)
+        self.finished_for, self.stopped = None, False
+
+    def set_motion(self, position, velocity, discontinuity):  # :137-149
+        self.pending = (v3(position), v3(velocity), bool(discontinuity))
+
+    def smoothed_position(self, dt, motion):  # :489-503
+        dt = f32(self.dt + dt)
+        change = scale(motion[1], dt)
+        naive = add(self.prev_position, change)
+        intended = add(motion[0], change)
+        return mix(naive, intended, min(f32(dt / POSITION_SMOOTHING_PERIOD), f32(1.0)))
+
+
+class PyScene:
+    def __init__(self):
+        self.sources = []
+        self.rot_received = (f32(1.0), [f32(0.0)] * 3)
+        self.rot_pending = None
+
+    def play(self, inner, position, velocity, radius):
+        self.sources.append(PySource(inner, position, velocity, radius))
+        return self.sources[-1]
+
+    def set_listener_rotation(self, xyzs):  # spatial.rs:345-349: the scene turns the other way
+        self.rot_pending = (f32(xyzs[3]), [f32(-xyzs[0]), f32(-xyzs[1]), f32(-xyzs[2])])
+
+    def run(self, sample_rate, n):  # lib.rs:90-93, spatial.rs:376-471
+        interval = f32(f32(1.0) / f32(sample_rate))
+        prev_rot = self.rot_received
+        if self.rot_pending is not None:
+            self.rot_received, self.rot_pending = self.rot_pending, None
+        rot = self.rot_received
+        out = np.zeros((n, 2), dtype=f32)
+        elapsed = f32(interval * f32(n))
+        for i in reversed(range(len(self.sources))):  # walk_set, :204
+            src = self.sources[i]
+            orig_next = src.received
+            if src.pending is not None:  # motion.refresh(), :216-224
+                src.received, src.pending = src.pending, None
+                src.prev_position = src.received[0] if src.received[2] else src.smoothed_position(f32(0.0), orig_next)
+                src.dt = f32(0.0)
+            prev_position = rotate(prev_rot, src.smoothed_position(f32(0.0), src.received))
+            next_position = rotate(rot, src.smoothed_position(elapsed, src.received))
+            src.dt = f32(src.dt + elapsed)
+            distance = norm(prev_position)  # :241-258
+            if src.finished_for is not None:
+                if src.finished_for > f32(distance / SPEED_OF_SOUND):
+                    src.stopped = True
+                else:
+                    src.finished_for = f32(src.finished_for + elapsed)
+            elif src.inner.is_finished():
+                src.finished_for = elapsed
+            if src.stopped:
+                del self.sources[i]  # set.remove = swap_remove (set.rs:183-188); same thing at the walked index ...
+                if i < len(self.sources):  # ... unless something sits behind it: the last element moves into the hole
+                    self.sources.insert(i, self.sources.pop())
+                continue
+            for ear in (0, 1):  # :445-469
+                p_off, p_gain = ear_state(prev_position, ear, src.radius)
+                n_off, n_gain = ear_state(next_position, ear, src.radius)
+                src.inner.seek(p_off)
+                effective = f32(f32(elapsed + n_off) - p_off)
+                dt = f32(effective / f32(n))
+                d_gain = f32(f32(n_gain - p_gain) / f32(n))
+                k = 0
+                for c0 in range(0, n, 256):
+                    m = min(256, n - c0)
+                    buf = src.inner.sample(dt, m)
+                    for s in buf:
+                        gain = f32(p_gain + f32(f32(k) * d_gain))
+                        out[k, ear] = f32(out[k, ear] + f32(s * gain))
+                        k += 1
+                src.inner.seek(f32(f32(-effective) - p_off))
+            src.inner.seek(elapsed)
+        return out
+
+
+def make_pcm(rng, n, rate):
+    k = np.arange(n, dtype=np.float64)
+    return (0.5 * np.sin(2 * np.pi * rng.uniform(100.0, 4000.0) * k / rate + rng.uniform(0, 6.28)) + 0.05 * rng.uniform(-1, 1, n)).astype(f32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_scene_sample_seek_path_agrees_bit_for_bit(oracle, seed):
+    rng = np.random.default_rng(seed)
+    rate = 48000
+    ref, py = oracle.SpatialScene(), PyScene()
+    ref_src, py_src, ref_sig, py_sig = [], [], [], []
+    for i in range(4):
+        pcm_rate = rate if i != 2 else 44100
+        pcm = make_pcm(rng, 3000 if i == 3 else 9000, pcm_rate)  # source 3 runs off its end inside the test
+        start = float(rng.uniform(-0.01, 0.05))
+        d = rng.normal(size=3)
+        pos = (d / np.linalg.norm(d) * rng.uniform(1.0, 60.0)).astype(f32)
+        vel = np.zeros(3, f32) if i == 1 else rng.uniform(-40, 40, 3).astype(f32)  # source 1: the ds ~= 1 path
+        radius = float(rng.uniform(0.05, 0.5))
+        sig = oracle.FramesSignal(oracle.Frames.from_slice(pcm_rate, pcm), start)
+        ref_sig.append(sig)
+        ref_src.append(ref.play(sig, pos, vel, radius))
+        inner = PyFramesSignal(pcm, pcm_rate, start)
+        py_sig.append(inner)
+        py_src.append(py.play(inner, pos, vel, radius))
+    for step, n in enumerate((256, 300, 1, 1024, 700, 513, 2048, 4096, 4096, 4096, 1024)):
+        if step == 2:  # a motion update with and without a discontinuity, and a listener turn
+            for j, disc in ((0, False), (2, True)):
+                pos, vel = rng.uniform(-30, 30, 3).astype(f32), rng.uniform(-20, 20, 3).astype(f32)
+                ref_src[j].set_motion(pos, vel, disc)
+                py_src[j].set_motion(pos, vel, disc)
+            q = rng.normal(size=4)
+            q = (q / np.linalg.norm(q)).astype(f32)
+            ref.set_listener_rotation(q)
+            py.set_listener_rotation(q)
+        a = oracle.run(ref, rate, n)
+        b = py.run(rate, n)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"callback {step} ({n} frames)")
+        assert ref.len() == len(py.sources)
+        live = {id(s.inner) for s in py.sources}
+        for rs, ps in zip(ref_sig, py_sig):
+            if id(ps) in live:
+                assert rs.t == float(ps.t)
+    assert len(py.sources) < 4, "the short source should have been dropped after its propagation delay"
