@@ -107,12 +107,15 @@ def trunc_isize(x):
 
 
 class PyFramesSignal:
+    """FramesSignal<T> for T = f32 (samples of shape (n,)) or T = [f32; ch] (samples of shape (n, ch): elementwise f32
+    array arithmetic rounds every channel like the scalar operation, so the lerp lines below serve both)."""
+
     def __init__(self, samples, rate, start_seconds):
         self.samples, self.rate, self.t = np.asarray(samples, dtype=f32), f64(rate), f64(start_seconds)
 
     def get_pair(self, s):  # frames.rs:105-123
-        n = self.samples.size
-        z = f32(0.0)
+        n = self.samples.shape[0]
+        z = f32(0.0) if self.samples.ndim == 1 else np.zeros(self.samples.shape[1], dtype=f32)
         if s >= 0:
             if s < n - 1:
                 return self.samples[s], self.samples[s + 1]
@@ -124,7 +127,7 @@ class PyFramesSignal:
         return z, self.samples[0]
 
     def sample(self, interval, n):  # :176-201
-        out = np.empty(n, dtype=f32)
+        out = np.empty((n,) + self.samples.shape[1:], dtype=f32)
         s0 = f64(self.t * self.rate)
         ds = f32(interval * f32(self.rate))
         base = trunc_isize(s0)
@@ -145,7 +148,7 @@ class PyFramesSignal:
         return out
 
     def is_finished(self):  # :204-206
-        return self.t >= f64(self.samples.size - 1) / self.rate
+        return self.t >= f64(self.samples.shape[0] - 1) / self.rate
 
     def seek(self, seconds):  # :210-213
         self.t = f64(self.t + f64(f32(seconds)))
@@ -278,3 +281,139 @@ def test_scene_sample_seek_path_agrees_bit_for_bit(oracle, seed):
             if id(ps) in live:
                 assert rs.t == float(ps.t)
     assert len(py.sources) < 4, "the short source should have been dropped after its propagation delay"
+
+
+# ---- the mixer path: Mixer<T> over Gain(FixedGain(Speed(FramesSignal))) ------------------------------------------------
+SMOOTHING_PERIOD = f32(0.1)  # gain.rs:163
+
+
+class PySpeed:  # speed.rs:24-40
+    def __init__(self, inner):
+        self.inner, self.speed = inner, f32(1.0)
+
+    def sample(self, interval, n):
+        return self.inner.sample(f32(interval * self.speed), n)
+
+    def is_finished(self):
+        return self.inner.is_finished()
+
+
+class PyFixedGain:  # gain.rs:27-43; the ratio 10^(db / 20) itself is libm's powf and is taken from the oracle
+    def __init__(self, inner, ratio):
+        self.inner, self.gain = inner, f32(ratio)
+
+    def sample(self, interval, n):
+        return (self.inner.sample(interval, n) * self.gain).astype(f32)
+
+    def is_finished(self):
+        return self.inner.is_finished()
+
+
+class PyGain:  # gain.rs:58-127 over smooth.rs:26-91
+    def __init__(self, inner):
+        self.inner, self.shared = inner, f32(1.0)
+        self.prev, self.next, self.progress = f32(1.0), f32(1.0), f32(1.0)
+
+    def set_amplitude_ratio(self, factor):  # Gain::set_amplitude_ratio: no smoothing
+        self.shared = f32(factor)
+        self.prev, self.next, self.progress = f32(factor), f32(factor), f32(1.0)
+
+    def control_set_amplitude_ratio(self, factor):  # GainControl::set_amplitude_ratio
+        self.shared = f32(factor)
+
+    def get(self):  # Smoothed::get -> f32::interpolate
+        return f32(self.prev + f32(self.progress * f32(self.next - self.prev)))
+
+    def sample(self, interval, n):
+        out = self.inner.sample(interval, n)
+        if self.next != self.shared:  # Smoothed::set
+            self.prev, self.next, self.progress = self.get(), self.shared, f32(0.0)
+        if self.progress == f32(1.0):
+            g = self.get()
+            if g != f32(1.0):
+                out = (out * g).astype(f32)
+            return out
+        for i in range(n):
+            out[i] = f32(out[i] * self.get()) if out.ndim == 1 else (out[i] * self.get()).astype(f32)
+            self.progress = min(f32(self.progress + f32(interval / SMOOTHING_PERIOD)), f32(1.0))
+        return out
+
+    def is_finished(self):
+        return self.inner.is_finished()
+
+
+class PyMixer:  # mixer.rs:92-119
+    def __init__(self, channels):
+        self.channels, self.signals = channels, []
+
+    def play(self, signal):
+        entry = {"inner": signal, "stop": False}
+        self.signals.append(entry)
+        return entry
+
+    def run(self, sample_rate, n):
+        interval = f32(f32(1.0) / f32(sample_rate))
+        out = np.zeros((n, self.channels) if self.channels > 1 else (n,), dtype=f32)
+        for i in reversed(range(len(self.signals))):
+            sig = self.signals[i]
+            if sig["stop"] or sig["inner"].is_finished():
+                sig["stop"] = True
+                del self.signals[i]  # swap_remove
+                if i < len(self.signals):
+                    self.signals.insert(i, self.signals.pop())
+                continue
+            for c0 in range(0, n, 1024):  # the staging buffer holds 1024 frames (mixer.rs:77)
+                m = min(1024, n - c0)
+                out[c0:c0 + m] = (out[c0:c0 + m] + sig["inner"].sample(interval, m)).astype(f32)
+        return out
+
+
+@pytest.mark.parametrize("channels", [1, 2])
+def test_mixer_chain_agrees_bit_for_bit(oracle, channels):
+    rng = np.random.default_rng(10 + channels)
+    rate = 48000
+    ref, py = oracle.Mixer(channels), PyMixer(channels)
+    items = []
+    for i in range(6):
+        pcm_rate = 44100 if i == 4 else rate
+        n = 2500 if i == 5 else 30000  # signal 5 finishes inside the test
+        pcm = np.stack([make_pcm(rng, n, pcm_rate) for _ in range(channels)], axis=1) if channels > 1 else make_pcm(rng, n, pcm_rate)
+        start = float(rng.uniform(0.0, 0.02))
+        o = oracle.FramesSignal(oracle.Frames.from_slice(pcm_rate, pcm), start)
+        p = PyFramesSignal(pcm, pcm_rate, start)
+        it = {"ref_frames": o, "py_frames": p}
+        if i in (1, 3):
+            o, p = oracle.Speed(o), PySpeed(p)
+            it["ref_speed"], it["py_speed"] = o, p
+            o.set_speed(0.7)
+            p.speed = f32(0.7)
+        if i in (2, 3):
+            o = oracle.FixedGain(o, -6.0)
+            p = PyFixedGain(p, o.gain)
+        if i in (0, 3):
+            o, p = oracle.Gain(o), PyGain(p)
+            it["ref_gain"], it["py_gain"] = o, p
+            if i == 3:
+                o.set_amplitude_ratio(0.5)
+                p.set_amplitude_ratio(0.5)
+        it["ref_mixed"], it["py_mixed"] = ref.play(o), py.play(p)
+        items.append(it)
+    for step, n in enumerate((256, 1024, 1500, 3000, 700, 4096, 2048)):
+        if step == 2:  # a gain transition (0.1 s = 4800 frames: it spans callbacks and the 1024-frame staging chunks)
+            items[0]["ref_gain"].control_set_amplitude_ratio(0.25)
+            items[0]["py_gain"].control_set_amplitude_ratio(0.25)
+            items[1]["ref_speed"].set_speed(1.3)
+            items[1]["py_speed"].speed = f32(1.3)
+        if step == 3:  # retargeted in mid-transition
+            items[0]["ref_gain"].control_set_amplitude_ratio(0.8)
+            items[0]["py_gain"].control_set_amplitude_ratio(0.8)
+        if step == 4:
+            items[2]["ref_mixed"].stop()
+            items[2]["py_mixed"]["stop"] = True
+        a, b = oracle.run(ref, rate, n), py.run(rate, n)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"callback {step} ({n} frames)")
+        assert len(ref) == len(py.signals)
+        for it in items:
+            if any(e is it["py_mixed"] for e in py.signals):
+                assert it["ref_frames"].t == float(it["py_frames"].t)
+    assert len(py.signals) == 4, "one signal stopped, one ran off its end"
