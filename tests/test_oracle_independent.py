@@ -1,15 +1,18 @@
-"""A second, independent statement of SpatialScene::sample's seek path, against the C++ oracle (CPU only).
+"""A second, independent statement of the hot path - SpatialScene::sample (seek and buffered sets) and Mixer::sample
+over its chains - against the C++ oracle (CPU only).
 
 The reference holds no numeric test of `SpatialScene::sample` (spatial.rs:606-665 only checks when a finished signal is
-dropped), so the oracle's numbers for the headline path rest on how faithfully it restates the source (DESIGN.md
-section 6). This file restates the same lines a second time, in another language and written from the reference alone
+dropped) and none of a whole `Mixer` chain, so the oracle's numbers for the headline path rest on how faithfully it
+restates the source. This file restates the same lines a second time, in another language and written from the reference alone
 - scalar numpy float32 / float64 operations in the reference's order - and requires the C++ oracle to agree BIT FOR BIT
 on output, f64 cursors and removal behaviour. Two independent restatements agreeing is not the reference itself, but
 it rules out the slips a single restatement can hide (operation order, f32 vs f64 intermediates, truncation, chunking).
 
 Reference lines: lib.rs:90-93 (run), spatial.rs:191-265 (walk_set), 345-349 (set_listener_rotation), 376-471 (sample,
 seek set), 489-503 (smoothed_position), 522-543 (EarState::new), 563-598 (Ear), math/mod.rs:32-99, frames.rs:105-123
-(get_pair), 176-213 (FramesSignal), frame.rs:39-41 (lerp).
+(get_pair), 176-213 (FramesSignal), frame.rs:39-41 (lerp); buffered set: spatial.rs:30-57, 313-340, 395-433,
+ring.rs:9-79; mixer: mixer.rs:77, 92-119, gain.rs:27-43, 58-127, 163, smooth.rs:26-91, speed.rs:24-40. Not restated:
+libm (`powf` of FixedGain's ratio is read back from the oracle; `tanhf` of the Tanh epilogue is left out).
 
 (Writing it caught a slip - in THIS file: the first draft forgot that `set_listener_rotation` stores the inverse
 rotation; the C++ oracle had it right.)"""
@@ -217,24 +220,27 @@ class PyScene:
                 if i < len(self.sources):  # ... unless something sits behind it: the last element moves into the hole
                     self.sources.insert(i, self.sources.pop())
                 continue
-            for ear in (0, 1):  # :445-469
-                p_off, p_gain = ear_state(prev_position, ear, src.radius)
-                n_off, n_gain = ear_state(next_position, ear, src.radius)
-                src.inner.seek(p_off)
-                effective = f32(f32(elapsed + n_off) - p_off)
-                dt = f32(effective / f32(n))
-                d_gain = f32(f32(n_gain - p_gain) / f32(n))
-                k = 0
-                for c0 in range(0, n, 256):
-                    m = min(256, n - c0)
-                    buf = src.inner.sample(dt, m)
-                    for s in buf:
-                        gain = f32(p_gain + f32(f32(k) * d_gain))
-                        out[k, ear] = f32(out[k, ear] + f32(s * gain))
-                        k += 1
-                src.inner.seek(f32(f32(-effective) - p_off))
-            src.inner.seek(elapsed)
+            self.mix(src, prev_position, next_position, elapsed, n, out)
         return out
+
+    def mix(self, src, prev_position, next_position, elapsed, n, out):  # the seek set's closure, spatial.rs:445-469
+        for ear in (0, 1):
+            p_off, p_gain = ear_state(prev_position, ear, src.radius)
+            n_off, n_gain = ear_state(next_position, ear, src.radius)
+            src.inner.seek(p_off)
+            effective = f32(f32(elapsed + n_off) - p_off)
+            dt = f32(effective / f32(n))
+            d_gain = f32(f32(n_gain - p_gain) / f32(n))
+            k = 0
+            for c0 in range(0, n, 256):
+                m = min(256, n - c0)
+                buf = src.inner.sample(dt, m)
+                for s in buf:
+                    gain = f32(p_gain + f32(f32(k) * d_gain))
+                    out[k, ear] = f32(out[k, ear] + f32(s * gain))
+                    k += 1
+            src.inner.seek(f32(f32(-effective) - p_off))
+        src.inner.seek(elapsed)
 
 
 def make_pcm(rng, n, rate):
@@ -417,3 +423,124 @@ def test_mixer_chain_agrees_bit_for_bit(oracle, channels):
             if any(e is it["py_mixed"] for e in py.signals):
                 assert it["ref_frames"].t == float(it["py_frames"].t)
     assert len(py.signals) == 4, "one signal stopped, one ran off its end"
+
+
+# ---- the buffered path: SpatialSceneControl::play_buffered over Ring ------------------------------------------------
+def fmod32(a, b):  # Rust's `%` on f32 is fmod: exact
+    return f32(np.fmod(f32(a), f32(b)))
+
+
+def rem_euclid32(a, b):  # f32::rem_euclid
+    r = fmod32(a, b)
+    return f32(r + abs(b)) if r < f32(0.0) else r
+
+
+class PyRing:  # ring.rs:4-79
+    def __init__(self, capacity):
+        self.buffer, self.write = np.zeros(capacity, dtype=f32), f32(0.0)
+
+    def write_from(self, signal, rate, dt):  # Ring::write
+        n = f32(self.buffer.size)
+        end = fmod32(f32(self.write + f32(dt * f32(rate))), n)
+        start_idx, end_idx = int(np.ceil(self.write)), int(np.ceil(end))
+        interval = f32(f32(1.0) / f32(rate))
+        if end_idx > start_idx:
+            self.buffer[start_idx:end_idx] = signal.sample(interval, end_idx - start_idx)
+        else:
+            self.buffer[start_idx:] = signal.sample(interval, self.buffer.size - start_idx)
+            self.buffer[:end_idx] = signal.sample(interval, end_idx)
+        self.write = end
+
+    def delay(self, rate, dt):
+        self.write = fmod32(f32(self.write + f32(f32(rate) * dt)), f32(self.buffer.size))
+
+    def sample(self, rate, t, interval, n):
+        size = self.buffer.size
+        out = np.empty(n, dtype=f32)
+        offset = rem_euclid32(f32(self.write + f32(t * f32(rate))), f32(size))
+        ds = f32(interval * f32(rate))
+        for i in range(n):
+            trunc = int(np.trunc(offset))
+            fract = f32(offset - f32(trunc))
+            x = trunc
+            if x < size - 1:
+                a, b = self.buffer[x], self.buffer[x + 1]
+            elif x < size:
+                a, b = self.buffer[x], self.buffer[0]
+            else:
+                x = x % size
+                offset = f32(f32(x) + fract)
+                a, b = (self.buffer[x], self.buffer[x + 1]) if x < size - 1 else (self.buffer[x], self.buffer[0])
+            out[i] = f32(a + f32(fract * f32(b - a)))
+            offset = f32(offset + ds)
+        return out
+
+
+class PyBufferedScene(PyScene):
+    """The buffered set of SpatialScene::sample (spatial.rs:377-433); walk_set is shared with the seek set."""
+
+    def play_buffered(self, inner, position, velocity, radius, max_distance, rate, buffer_duration):  # :313-340, :30-57
+        src = PySource(inner, position, velocity, radius)
+        src.rate = int(rate)
+        src.max_delay = f32(f32(f32(max_distance) / SPEED_OF_SOUND) + f32(buffer_duration))
+        src.queue = PyRing(int(np.ceil(f32(src.max_delay * f32(rate)))) + 1)
+        src.queue.delay(rate, min(f32(norm(v3(position)) / SPEED_OF_SOUND), src.max_delay))
+        self.sources.append(src)
+        return src
+
+    def mix(self, src, prev_position, next_position, elapsed, n, out):  # the closure at :404-432
+        src.queue.write_from(src.inner, src.rate, elapsed)
+        for ear in (0, 1):
+            p_off, p_gain = ear_state(prev_position, ear, src.radius)
+            n_off, n_gain = ear_state(next_position, ear, src.radius)
+            prev_offset = max(f32(p_off - elapsed), f32(-src.max_delay))
+            next_offset = max(n_off, f32(-src.max_delay))
+            dt = f32(f32(next_offset - prev_offset) / f32(n))
+            d_gain = f32(f32(n_gain - p_gain) / f32(n))
+            k = 0
+            for c0 in range(0, n, 256):
+                m = min(256, n - c0)
+                t = f32(prev_offset + f32(f32(k) * dt))
+                buf = src.queue.sample(src.rate, t, dt, m)
+                for s in buf:
+                    gain = f32(p_gain + f32(f32(k) * d_gain))
+                    out[k, ear] = f32(out[k, ear] + f32(s * gain))
+                    k += 1
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_scene_sample_buffered_path_agrees_bit_for_bit(oracle, seed):
+    rng = np.random.default_rng(100 + seed)
+    rate = 48000
+    ref, py = oracle.SpatialScene(), PyBufferedScene()
+    ref_src, py_src = [], []
+    for i in range(3):
+        pcm_rate = 44100 if i == 1 else rate
+        pcm = make_pcm(rng, 4000 if i == 2 else 20000, pcm_rate)  # source 2 runs off its end
+        start = float(rng.uniform(0.0, 0.03))
+        d = rng.normal(size=3)
+        pos = (d / np.linalg.norm(d) * rng.uniform(1.0, 40.0)).astype(f32)
+        vel = rng.uniform(-30, 30, 3).astype(f32)
+        radius = float(rng.uniform(0.05, 0.5))
+        ring_rate = 48000 if i != 1 else 32000
+        o = oracle.FramesSignal(oracle.Frames.from_slice(pcm_rate, pcm), start)
+        p = PyFramesSignal(pcm, pcm_rate, start)
+        if i == 0:  # a chain that does not implement Seek: what play_buffered is for
+            o, p = oracle.Speed(o), PySpeed(p)
+            o.set_speed(1.1)
+            p.speed = f32(1.1)
+        ref_src.append(ref.play_buffered(o, pos, vel, radius, 50.0, ring_rate, 0.1))
+        py_src.append(py.play_buffered(p, pos, vel, radius, 50.0, ring_rate, 0.1))
+    for step, n in enumerate((256, 1024, 300, 2048, 4096, 4096, 4096, 1000)):
+        if step == 2:
+            pos, vel = rng.uniform(-20, 20, 3).astype(f32), rng.uniform(-20, 20, 3).astype(f32)
+            ref_src[1].set_motion(pos, vel, False)
+            py_src[1].set_motion(pos, vel, False)
+            q = rng.normal(size=4)
+            q = (q / np.linalg.norm(q)).astype(f32)
+            ref.set_listener_rotation(q)
+            py.set_listener_rotation(q)
+        a, b = oracle.run(ref, rate, n), py.run(rate, n)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"callback {step} ({n} frames)")
+        assert ref.len(buffered=True) == len(py.sources)
+    assert len(py.sources) == 2, "the short source should have been dropped after its propagation delay"
