@@ -3,6 +3,8 @@
 #include "oddio_oracle.hpp"
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 using namespace orc;
@@ -105,11 +107,40 @@ double orc_time_run(void* h, uint32_t rate, float* out, size_t n, int warmup, in
 // Returns total wall seconds of `reps` rounds (after `warmup` untimed rounds); out = last summed tile.
 double orc_time_run_sharded(void** sigs, int n_sig, uint32_t rate, float* out, size_t n, int channels, int warmup, int reps) {
     std::vector<std::vector<float>> tiles((size_t)n_sig, std::vector<float>(n * (size_t)channels, 0.0f));
+    // Persistent workers, released round by round (no thread is created or joined inside the timed region).
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    int round_no = 0, done = 0;
+    bool quit = false;
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_sig; i++)
+        th.emplace_back([&, i]() {
+            int seen = 0;
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_go.wait(lk, [&] { return quit || round_no != seen; });
+                    if (quit) return;
+                    seen = round_no;
+                }
+                run(*((Obj*)sigs[i])->signal, rate, tiles[(size_t)i].data(), n);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (++done == n_sig) cv_done.notify_one();
+                }
+            }
+        });
     auto round = [&]() {
-        std::vector<std::thread> th;
-        for (int i = 0; i < n_sig; i++)
-            th.emplace_back([&, i]() { run(*((Obj*)sigs[i])->signal, rate, tiles[(size_t)i].data(), n); });
-        for (auto& t : th) t.join();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            done = 0;
+            round_no++;
+        }
+        cv_go.notify_all();
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return done == n_sig; });
+        }
         for (size_t k = 0; k < n * (size_t)channels; k++) {
             float acc = 0.0f;
             for (int i = 0; i < n_sig; i++) acc = acc + tiles[(size_t)i][k];
@@ -120,6 +151,12 @@ double orc_time_run_sharded(void** sigs, int n_sig, uint32_t rate, float* out, s
     auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < reps; i++) round();
     auto t1 = std::chrono::steady_clock::now();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        quit = true;
+    }
+    cv_go.notify_all();
+    for (auto& t : th) t.join();
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
