@@ -178,7 +178,7 @@ class PySource:
 
 class PyScene:
     def __init__(self):
-        self.sources = []
+        self.sources, self.buffered = [], []  # the seek set and the buffered set
         self.rot_received = (f32(1.0), [f32(0.0)] * 3)
         self.rot_pending = None
 
@@ -197,8 +197,13 @@ class PyScene:
         rot = self.rot_received
         out = np.zeros((n, 2), dtype=f32)
         elapsed = f32(interval * f32(n))
-        for i in reversed(range(len(self.sources))):  # walk_set, :204
-            src = self.sources[i]
+        self.walk(self.buffered, self.mix_buffered, prev_rot, rot, elapsed, n, out)  # :395-433
+        self.walk(self.sources, self.mix, prev_rot, rot, elapsed, n, out)            # :435-470
+        return out
+
+    def walk(self, sources, mix_signal, prev_rot, rot, elapsed, n, out):  # walk_set, spatial.rs:191-265
+        for i in reversed(range(len(sources))):
+            src = sources[i]
             orig_next = src.received
             if src.pending is not None:  # motion.refresh(), :216-224
                 src.received, src.pending = src.pending, None
@@ -216,12 +221,11 @@ class PyScene:
             elif src.inner.is_finished():
                 src.finished_for = elapsed
             if src.stopped:
-                del self.sources[i]  # set.remove = swap_remove (set.rs:183-188); same thing at the walked index ...
-                if i < len(self.sources):  # ... unless something sits behind it: the last element moves into the hole
-                    self.sources.insert(i, self.sources.pop())
+                del sources[i]  # set.remove = swap_remove (set.rs:183-188); same thing at the walked index ...
+                if i < len(sources):  # ... unless something sits behind it: the last element moves into the hole
+                    sources.insert(i, sources.pop())
                 continue
-            self.mix(src, prev_position, next_position, elapsed, n, out)
-        return out
+            mix_signal(src, prev_position, next_position, elapsed, n, out)
 
     def mix(self, src, prev_position, next_position, elapsed, n, out):  # the seek set's closure, spatial.rs:445-469
         for ear in (0, 1):
@@ -476,43 +480,45 @@ class PyRing:  # ring.rs:4-79
         return out
 
 
-class PyBufferedScene(PyScene):
-    """The buffered set of SpatialScene::sample (spatial.rs:377-433); walk_set is shared with the seek set."""
+def play_buffered(self, inner, position, velocity, radius, max_distance, rate, buffer_duration):  # spatial.rs:313-340, :30-57
+    src = PySource(inner, position, velocity, radius)
+    src.rate = int(rate)
+    src.max_delay = f32(f32(f32(max_distance) / SPEED_OF_SOUND) + f32(buffer_duration))
+    src.queue = PyRing(int(np.ceil(f32(src.max_delay * f32(rate)))) + 1)
+    src.queue.delay(rate, min(f32(norm(v3(position)) / SPEED_OF_SOUND), src.max_delay))
+    self.buffered.append(src)
+    return src
 
-    def play_buffered(self, inner, position, velocity, radius, max_distance, rate, buffer_duration):  # :313-340, :30-57
-        src = PySource(inner, position, velocity, radius)
-        src.rate = int(rate)
-        src.max_delay = f32(f32(f32(max_distance) / SPEED_OF_SOUND) + f32(buffer_duration))
-        src.queue = PyRing(int(np.ceil(f32(src.max_delay * f32(rate)))) + 1)
-        src.queue.delay(rate, min(f32(norm(v3(position)) / SPEED_OF_SOUND), src.max_delay))
-        self.sources.append(src)
-        return src
 
-    def mix(self, src, prev_position, next_position, elapsed, n, out):  # the closure at :404-432
-        src.queue.write_from(src.inner, src.rate, elapsed)
-        for ear in (0, 1):
-            p_off, p_gain = ear_state(prev_position, ear, src.radius)
-            n_off, n_gain = ear_state(next_position, ear, src.radius)
-            prev_offset = max(f32(p_off - elapsed), f32(-src.max_delay))
-            next_offset = max(n_off, f32(-src.max_delay))
-            dt = f32(f32(next_offset - prev_offset) / f32(n))
-            d_gain = f32(f32(n_gain - p_gain) / f32(n))
-            k = 0
-            for c0 in range(0, n, 256):
-                m = min(256, n - c0)
-                t = f32(prev_offset + f32(f32(k) * dt))
-                buf = src.queue.sample(src.rate, t, dt, m)
-                for s in buf:
-                    gain = f32(p_gain + f32(f32(k) * d_gain))
-                    out[k, ear] = f32(out[k, ear] + f32(s * gain))
-                    k += 1
+def mix_buffered(self, src, prev_position, next_position, elapsed, n, out):  # the buffered set's closure, spatial.rs:404-432
+    src.queue.write_from(src.inner, src.rate, elapsed)
+    for ear in (0, 1):
+        p_off, p_gain = ear_state(prev_position, ear, src.radius)
+        n_off, n_gain = ear_state(next_position, ear, src.radius)
+        prev_offset = max(f32(p_off - elapsed), f32(-src.max_delay))
+        next_offset = max(n_off, f32(-src.max_delay))
+        dt = f32(f32(next_offset - prev_offset) / f32(n))
+        d_gain = f32(f32(n_gain - p_gain) / f32(n))
+        k = 0
+        for c0 in range(0, n, 256):
+            m = min(256, n - c0)
+            t = f32(prev_offset + f32(f32(k) * dt))
+            buf = src.queue.sample(src.rate, t, dt, m)
+            for s in buf:
+                gain = f32(p_gain + f32(f32(k) * d_gain))
+                out[k, ear] = f32(out[k, ear] + f32(s * gain))
+                k += 1
+
+
+PyScene.play_buffered = play_buffered
+PyScene.mix_buffered = mix_buffered
 
 
 @pytest.mark.parametrize("seed", [0, 1])
 def test_scene_sample_buffered_path_agrees_bit_for_bit(oracle, seed):
     rng = np.random.default_rng(100 + seed)
     rate = 48000
-    ref, py = oracle.SpatialScene(), PyBufferedScene()
+    ref, py = oracle.SpatialScene(), PyScene()
     ref_src, py_src = [], []
     for i in range(3):
         pcm_rate = 44100 if i == 1 else rate
@@ -542,5 +548,38 @@ def test_scene_sample_buffered_path_agrees_bit_for_bit(oracle, seed):
             py.set_listener_rotation(q)
         a, b = oracle.run(ref, rate, n), py.run(rate, n)
         np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"callback {step} ({n} frames)")
-        assert ref.len(buffered=True) == len(py.sources)
-    assert len(py.sources) == 2, "the short source should have been dropped after its propagation delay"
+        assert ref.len(buffered=True) == len(py.buffered)
+    assert len(py.buffered) == 2, "the short source should have been dropped after its propagation delay"
+
+
+
+def test_both_sets_and_edge_cases_agree_bit_for_bit(oracle):
+    """Both sets in one scene (one output buffer: the buffered set is mixed first, spatial.rs:395, 435), with the corner
+    cases: a source sitting exactly in an ear (distance < 1e-3, spatial.rs:528-530), one that starts before its first
+    sample (get_pair's negative indices, frames.rs:118-122), one passing through the centre of the head, a buffered
+    source beyond max_distance (the clamp at -max_delay, spatial.rs:411-412), one-frame and 257-frame callbacks."""
+    rng = np.random.default_rng(7)
+    rate = 48000
+    ref, py = oracle.SpatialScene(), PyScene()
+    pcm = make_pcm(rng, 12000, rate)
+    cases = [
+        ("seek", [-0.1075, 0.0, 0.0], [0.0, 0.0, 0.0], 0.0),      # in the left ear, static
+        ("seek", [4.0, -2.0, 1.0], [3.0, 1.0, -8.0], -0.05),      # starts 2400 frames before its first sample
+        ("seek", [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 0.01),         # through the centre of the head
+        ("buffered", [60.0, 5.0, -3.0], [-5.0, 0.0, 2.0], 0.0),   # beyond max_distance = 50 m
+        ("buffered", [0.5, 0.2, -0.1], [0.0, 0.0, 0.0], 0.002),   # close and static
+    ]
+    for kind, pos, vel, start in cases:
+        o = oracle.FramesSignal(oracle.Frames.from_slice(rate, pcm), start)
+        p = PyFramesSignal(pcm, rate, start)
+        pos, vel = np.array(pos, f32), np.array(vel, f32)
+        if kind == "seek":
+            ref.play(o, pos, vel, 0.1)
+            py.play(p, pos, vel, 0.1)
+        else:
+            ref.play_buffered(o, pos, vel, 0.1, 50.0, rate, 0.1)
+            py.play_buffered(p, pos, vel, 0.1, 50.0, rate, 0.1)
+    for n in (1, 257, 1024, 300, 2048):
+        a, b = oracle.run(ref, rate, n), py.run(rate, n)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{n} frames")
+        assert ref.len() == len(py.sources) and ref.len(buffered=True) == len(py.buffered)
