@@ -1,5 +1,7 @@
 """Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle).
-CPU: the oracle still reproduces them bit for bit. GPU: the device path matches them - f64 cursors bit-exact,
+CPU: the oracle still reproduces them bit for bit, and so does the second, independent restatement of the path
+(tests/independent.py) - the vectors are what two separately written statements of the reference agree on.
+GPU: the device path matches them - f64 cursors bit-exact,
 mixed samples within 1e-5 * max(|ref|, RMS) (summation order is the only freedom)."""
 import os
 import sys
@@ -23,6 +25,18 @@ def test_oracle_reproduces_golden(name, oracle):
     assert set(res) == set(gold)
     for k in gold:
         np.testing.assert_array_equal(res[k], gold[k], err_msg=f"{name}:{k}")
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_independent_restatement_reproduces_golden(name):
+    from independent import IndependentBackend
+
+    gold = load(name)
+    res = SCENARIOS[name](IndependentBackend())
+    assert set(res) == set(gold)
+    for k in gold:
+        np.testing.assert_array_equal(np.asarray(res[k]).view(np.uint32 if k.startswith("out") else np.uint64),
+                                      gold[k].view(np.uint32 if k.startswith("out") else np.uint64), err_msg=f"{name}:{k}")
 
 
 @pytest.mark.gpu
