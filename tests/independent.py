@@ -12,8 +12,9 @@ it rules out the slips a single restatement can hide (operation order, f32 vs f6
 Reference lines: lib.rs:90-93 (run), spatial.rs:191-265 (walk_set), 345-349 (set_listener_rotation), 376-471 (sample,
 seek set), 489-503 (smoothed_position), 522-543 (EarState::new), 563-598 (Ear), math/mod.rs:32-99, frames.rs:105-123
 (get_pair), 176-213 (FramesSignal), frame.rs:39-41 (lerp); buffered set: spatial.rs:30-57, 313-340, 395-433,
-ring.rs:9-79; mixer: mixer.rs:77, 92-119, gain.rs:27-43, 58-127, 163, smooth.rs:26-91, speed.rs:24-40. Not restated:
-libm: `powf` (FixedGain's ratio) and `tanhf` (the Tanh epilogue) are glibc's, called through ctypes - the same
+ring.rs:9-79; mixer: mixer.rs:77, 92-119, gain.rs:27-43, 58-127, 163, smooth.rs:26-91, speed.rs:24-40; the rest of the
+closed set: cycle.rs:6-61, sine.rs:6-46, signal.rs:62-86 (MonoToStereo), reinhard.rs:28-35, tanh.rs:24-28. Not restated:
+libm: `powf` (FixedGain's ratio), `tanhf` (the Tanh epilogue) and `sinf` (Sine) are glibc's, called through ctypes - the same
 library the oracle links and a Rust std build would call.
 
 (Writing it caught a slip - in THIS file: the first draft forgot that `set_listener_rotation` stores the inverse
@@ -513,3 +514,85 @@ class IndependentBackend:
                 return np.array([float(s.t) for s in sigs], dtype=np.float64)
 
         return M()
+
+
+# ---- the rest of the closed set: Cycle, Sine, MonoToStereo, Reinhard -------------------------------------------------
+_libm.sinf.restype = ctypes.c_float
+_libm.sinf.argtypes = [ctypes.c_float]
+TAU = f32(6.28318530717958647692528676655900577)  # core::f32::consts::TAU
+
+
+class PyCycle:  # cycle.rs:6-61
+    def __init__(self, samples, rate):
+        self.samples, self.rate, self.cursor = np.asarray(samples, dtype=f32), int(rate), f64(0.0)
+
+    def sample(self, interval, n):
+        size = self.samples.shape[0]
+        out = np.empty((n,) + self.samples.shape[1:], dtype=f32)
+        ds = f32(interval * f32(self.rate))
+        base = int(np.trunc(self.cursor))
+        offset = f32(self.cursor - f64(base))
+        for i in range(n):
+            trunc = int(np.trunc(offset))
+            fract = f32(offset - f32(trunc))
+            x = base + trunc
+            if x < size - 1:
+                a, b = self.samples[x], self.samples[x + 1]
+            elif x < size:
+                a, b = self.samples[x], self.samples[0]
+            else:
+                base = 0
+                offset = f32(f32(x % size) + fract)
+                x = int(np.trunc(offset))
+                a, b = (self.samples[x], self.samples[x + 1]) if x < size - 1 else (self.samples[x], self.samples[0])
+            out[i] = f32(a + f32(fract * f32(b - a)))
+            offset = f32(offset + ds)
+        self.cursor = f64(f64(base) + f64(offset))
+        return out
+
+    def is_finished(self):  # Signal's default
+        return False
+
+    def seek(self, seconds):
+        size = f64(self.samples.shape[0])
+        r = np.fmod(f64(self.cursor + f64(f64(f32(seconds)) * f64(self.rate))), size)
+        self.cursor = f64(r + size) if r < 0 else f64(r)
+
+
+class PySine:  # sine.rs:6-46
+    def __init__(self, phase, frequency_hz):
+        self.phase, self.frequency = f32(phase), f32(f32(frequency_hz) * TAU)
+
+    def seek(self, t):
+        self.phase = f32(np.fmod(f32(self.phase + f32(f32(t) * self.frequency)), TAU))
+
+    def sample(self, interval, n):
+        out = np.empty(n, dtype=f32)
+        for i in range(n):
+            t = f32(interval * f32(i))
+            out[i] = _libm.sinf(float(f32(f32(t * self.frequency) + self.phase)))
+        self.seek(f32(interval * f32(n)))
+        return out
+
+    def is_finished(self):
+        return False
+
+
+class PyMonoToStereo:  # signal.rs:62-86
+    def __init__(self, inner):
+        self.inner = inner
+
+    def sample(self, interval, n):
+        mono = self.inner.sample(interval, n)
+        return np.stack([mono, mono], axis=1)
+
+    def is_finished(self):
+        return self.inner.is_finished()
+
+    def seek(self, seconds):
+        self.inner.seek(seconds)
+
+
+def reinhard32(x):  # reinhard.rs:28-35: channel /= 1 + |channel|
+    x = np.asarray(x, dtype=f32)
+    return (x / (f32(1.0) + np.abs(x))).astype(f32)

@@ -167,3 +167,71 @@ def test_both_sets_and_edge_cases_agree_bit_for_bit(oracle):
         a, b = oracle.run(ref, rate, n), py.run(rate, n)
         np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{n} frames")
         assert ref.len() == len(py.sources) and ref.len(buffered=True) == len(py.buffered)
+
+
+def test_c1_sines_and_reinhard_agree_bit_for_bit(oracle):
+    """BASELINE config 1 (examples/offline.rs: Sine -> MonoToStereo -> Mixer) and Reinhard over the mixer; sinf is
+    glibc's on both sides, the phase wrap (sine.rs:25-28) and everything around it are restated."""
+    from independent import PyMonoToStereo, PySine, reinhard32
+
+    rng = np.random.default_rng(21)
+    rate = 48000
+    ref_mx, py = oracle.Mixer(2), PyMixer(2)
+    ref = oracle.Reinhard(ref_mx)
+    for _ in range(8):
+        phase, freq = float(f32(rng.uniform(0, 6.28))), float(f32(rng.uniform(100.0, 1000.0)))
+        ref_mx.play(oracle.MonoToStereo(oracle.Sine(phase, freq)))
+        py.play(PyMonoToStereo(PySine(phase, freq)))
+    for n in (1024, 1024, 300, 2048):
+        a, b = oracle.run(ref, rate, n), reinhard32(py.run(rate, n))
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{n} frames")
+
+
+@pytest.mark.parametrize("channels", [1, 2])
+def test_cycle_under_the_mixer_agrees_bit_for_bit(oracle, channels):
+    from independent import PyCycle
+
+    rng = np.random.default_rng(30 + channels)
+    rate = 48000
+    ref, py = oracle.Mixer(channels), PyMixer(channels)
+    pairs = []
+    for i in range(3):
+        pcm_rate = 44100 if i == 1 else rate
+        n = (700, 1531, 64)[i]  # short loops: many wraps per callback, one shorter than a callback's advance
+        pcm = np.stack([make_pcm(rng, n, pcm_rate) for _ in range(channels)], axis=1) if channels > 1 else make_pcm(rng, n, pcm_rate)
+        o, p = oracle.Cycle(oracle.Frames.from_slice(pcm_rate, pcm)), PyCycle(pcm, pcm_rate)
+        pairs.append((o, p))
+        if i == 2:
+            o, p = oracle.Speed(o), PySpeed(p)
+            o.set_speed(1.7)
+            p.speed = f32(1.7)
+        ref.play(o)
+        py.play(p)
+    for n in (256, 1024, 1500, 4096):
+        a, b = oracle.run(ref, rate, n), py.run(rate, n)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{n} frames")
+        for o, p in pairs:
+            assert o.cursor == float(p.cursor)
+
+
+def test_cycle_in_the_scene_agrees_bit_for_bit(oracle):
+    """Cycle is Seek (cycle.rs:56-61): under SpatialSceneControl::play its cursor goes through the five seeks per
+    callback and wraps with rem_euclid."""
+    from independent import PyCycle
+
+    rng = np.random.default_rng(40)
+    rate = 48000
+    ref, py = oracle.SpatialScene(), PyScene()
+    pairs = []
+    for i in range(2):
+        pcm = make_pcm(rng, (900, 5000)[i], rate)
+        o, p = oracle.Cycle(oracle.Frames.from_slice(rate, pcm)), PyCycle(pcm, rate)
+        pairs.append((o, p))
+        pos, vel = rng.uniform(-20, 20, 3).astype(f32), rng.uniform(-20, 20, 3).astype(f32)
+        ref.play(o, pos, vel, 0.1)
+        py.play(p, pos, vel, 0.1)
+    for n in (256, 1024, 700, 2048):
+        a, b = oracle.run(ref, rate, n), py.run(rate, n)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{n} frames")
+        for o, p in pairs:
+            assert o.cursor == float(p.cursor)
