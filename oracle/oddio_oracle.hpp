@@ -10,7 +10,9 @@
 // x86-64 SSE2 (no excess precision). It is PINNED against every known-answer vector the
 // reference's own unit tests hold for this path (tests/test_oracle_kat.py), see SURVEY.md §4.
 // What the reference itself leaves unpinned (the numeric output of SpatialScene::sample) is
-// unpinned here too and is stated so in DESIGN.md.
+// unpinned here too and is stated so in DESIGN.md; for that part a second restatement, written
+// separately from the reference in numpy (tests/independent.py), must agree with this one bit
+// for bit (tests/test_oracle_independent.py, tests/test_golden.py).
 //
 // libm: the reference's std build calls the platform libm (sinf/tanhf/powf/log10f); on Linux
 // that is glibc, which is what this file calls.
